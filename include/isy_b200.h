@@ -1,0 +1,163 @@
+/*
+ * isy_b200.h -- C ABI of the B200-native (sm_100a) compound-eye view renderer.
+ *
+ * This is the drop-in boundary for ONE hot path of InsectRobotics/InvertSy: what a set of
+ * viewing directions sees of a triangle world (invertsy.env.world.WorldBase.__call__) fused
+ * with the analytic sky (invertsy.env.sky.Sky.__call__ / UniformSky.__call__).
+ *
+ * The reference has no FFI: the interface it exposes for this path is the pair of Python
+ * callables
+ *     scene(pos, ori=..., init_c=..., noise=..., eta=..., rng=...) -> (N,3)   env/world.py:55
+ *     sky(ori, irgbu=..., noise=..., eta=..., rng=...) -> (Y, DoP, AoP)        env/sky.py:269, :47
+ * so each entry point below names the reference lines it replaces and the ctypes binding a
+ * maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative isy_status and
+ *     leaves a message in isy_last_error() (thread-local).  No exceptions cross the boundary.
+ *   - "dev" pointers are CUDA device pointers on the handle's device; "host" pointers are
+ *     ordinary (ideally pinned) host memory.  The caller owns every buffer it passes.
+ *   - handles (isy_world, isy_eye) own their device copies and are immutable after creation;
+ *     render calls are re-entrant on distinct streams with distinct workspaces.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All device
+ *     entry points are asynchronous with respect to the host.
+ *   - orientations are unit quaternions in SciPy order (x, y, z, w); angles are radians.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     ISY_ERR_CUDA.
+ */
+#ifndef ISY_B200_H_
+#define ISY_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISY_ABI_VERSION 1
+
+typedef enum {
+    ISY_OK = 0,
+    ISY_ERR_INVALID = -1,   /* bad argument (NULL, negative size, inconsistent flags)            */
+    ISY_ERR_CUDA = -2,      /* CUDA runtime error / no device                                     */
+    ISY_ERR_WORKSPACE = -3, /* workspace too small (use isy_render_workspace_bytes)               */
+    ISY_ERR_OVERFLOW = -4   /* a position saw more triangles than the workspace slab can hold     */
+} isy_status;
+
+/* what the sky contributes (env/sky.py) */
+typedef enum {
+    ISY_SKY_NONE = 0,    /* no sky: Y/DoP/AoP are not produced                                    */
+    ISY_SKY_UNIFORM = 1, /* UniformSky.__call__  env/sky.py:47-97: Y = luminance, DoP = 0, AoP = NaN */
+    ISY_SKY_PEREZ = 2    /* Sky.__call__         env/sky.py:269-346                               */
+} isy_sky_kind;
+
+/* Scalars of one Sky instance (env/sky.py:245-267, 376-554). Filled by the Python mirror. */
+typedef struct {
+    int32_t kind;      /* isy_sky_kind                                                            */
+    int32_t reserved;
+    double luminance;  /* UniformSky luminance (sky.py:34)                                        */
+    double A, B, C, D, E; /* Perez coefficients (sky.py:376-457)                                  */
+    double tau_L;      /* turbidity after the pinv round trip (sky.py:535-554)                    */
+    double c1, c2;     /* max-DoP coefficients (sky.py:264-265)                                   */
+} isy_sky_params;
+
+/* output selection / behaviour flags for the render calls */
+enum {
+    ISY_FLAG_INIT_FROM_SKY = 1 << 0, /* world starts from luminance2skycolour(Y) (world.py:82, :465-479)
+                                        instead of NaN (world.py:80); rgb is then on the reference's
+                                        mixed 0..255 / 0..1 scale                                     */
+    ISY_FLAG_BRUTE_FORCE = 1 << 1,   /* test every visible triangle for every ray (no angular bins);
+                                        same results, used as an on-device cross-check                */
+    ISY_FLAG_SUN_PER_VIEW = 1 << 2,  /* `sun` holds one (theta_s, phi_s) per view instead of one pair  */
+    ISY_FLAG_OUT_F64 = 1 << 3        /* rgb / depth / Y / dop / aop buffers are double instead of float */
+};
+
+/* Per-ray / per-ommatidium outputs. Any pointer may be NULL (not produced).
+ * B = number of views, R = rays per view (N ommatidia x S samples), N = ommatidia.        */
+typedef struct {
+    void* rgb;      /* [B][N][3]  world colour, cone-averaged over the S samples (world.py:79-123)   */
+    int32_t* hit;   /* [B][R]     winning triangle index per ray, -1 = none (painter's top, world.py:106-123) */
+    void* depth;    /* [B][R]     min-vertex distance of that triangle (world.py:97), NaN = none     */
+    void* Y;        /* [B][N]     sky luminance      (sky.py:313, :334), cone-averaged               */
+    void* dop;      /* [B][N]     degree of polarisation (sky.py:317)                                */
+    void* aop;      /* [B][N]     angle of polarisation  (sky.py:320-324), circular cone average     */
+} isy_outputs;      /* element type: float, or double with ISY_FLAG_OUT_F64                           */
+
+typedef struct isy_world isy_world;
+typedef struct isy_eye isy_eye;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int isy_abi_version(void);
+const char* isy_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
+int64_t isy_launch_count(void);
+
+/* ---- world: WorldBase.__init__ / .polygons / .colours / .horizon  (world.py:48-53, 131-163) ---
+ * tri_xyz: T*9 floats [t][vertex][x,y,z] (host) ; tri_rgb: T*3 floats (host) ; both copied.     */
+int isy_world_create(const float* tri_xyz, const float* tri_rgb, int64_t T, double horizon, int device,
+                     isy_world** out);
+int isy_world_destroy(isy_world* w);
+int64_t isy_world_triangles(const isy_world* w);
+
+/* ---- eye layout: the ommatidia orientations a CompoundEye hands to scene()/sky() -------------
+ * omm_quat: N*S*4 doubles (host), ray r = n*S + s is sample s of ommatidium n, eye frame.
+ * weights : N*S floats (host) cone weights, each ommatidium's S weights sum to 1 (NULL = 1/S).
+ * Replaces the `omm_ori` argument flow agent.py:742 -> InvertPy CompoundEye -> world.py:55 / sky.py:269. */
+int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int32_t S, int device, isy_eye** out);
+int isy_eye_destroy(isy_eye* e);
+int64_t isy_eye_rays(const isy_eye* e);
+
+/* ---- batched render: P positions x H orientations each = B = P*H views ----------------------
+ * The unit of work is a *position*: cull + angular projection of the world (world.py:94-110)
+ * is done once per position and shared by its H orientations.
+ *   pos_dev      [P][3] doubles  eye position (the nanmean(pos) of world.py:94)
+ *   yaw_dev      [P][H] doubles  heading about +Z in radians (R.from_euler('Z', yaw), simulation.py:836, 2706),
+ *                                or NULL when view_quat_dev is given
+ *   view_quat_dev[P][H][4] doubles full eye orientation, or NULL for yaw-only views
+ *   sun_dev      [2] or [P][H][2] doubles (theta_s = zenith distance, phi_s), NULL unless PEREZ
+ * Global ray orientation = view orientation * eye-frame ommatidium orientation (examples/test_sky.py:25).
+ * Views are ordered b = p*H + h.                                                                  */
+size_t isy_render_workspace_bytes(const isy_world* w, const isy_eye* e, int64_t P, int64_t H);
+int isy_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, const double* pos_dev,
+               const double* yaw_dev, const double* view_quat_dev, const double* sun_dev,
+               const isy_sky_params* sky, uint32_t flags, const isy_outputs* out_dev, void* workspace_dev,
+               size_t workspace_bytes, void* stream);
+
+/* Synchronises `stream` and returns the sticky device-side status of the renders that used this
+ * workspace (ISY_OK, or ISY_ERR_OVERFLOW when a position exceeded the slab).                    */
+int isy_workspace_status(void* workspace_dev, void* stream);
+
+/* Same call with HOST buffers: stages inputs H2D, renders, copies the selected outputs D2H in
+ * chunks overlapped with compute (pinned staging owned by the library) and returns after the
+ * results are in host memory.  This is the end-to-end path bench.py times as `e2e`.            */
+int isy_render_host(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, const double* pos_host,
+                    const double* yaw_host, const double* view_quat_host, const double* sun_host,
+                    const isy_sky_params* sky, uint32_t flags, const isy_outputs* out_host);
+
+/* ---- direct replacements of the two reference callables (explicit ray orientations) ----------
+ * WorldBase.__call__(pos, ori, init_c, ...) world.py:55-129: N rays given as global quaternions.
+ *   init_c_host: N doubles or NULL (world.py:79-82);  rgb_host: N*3 doubles (float64 like the
+ *   reference's init_c branch; the caller casts to float32 for the NaN-init branch)
+ *   hit_host / depth_host: optional N int32 / N doubles                                           */
+int isy_world_call_host(const isy_world* w, const double* pos3_host, const double* ray_quat_host, int64_t N,
+                        const double* init_c_host, double* rgb_host, int32_t* hit_host, double* depth_host);
+
+/* Sky.__call__(ori) / UniformSky.__call__(ori) sky.py:269-346, :47-97 before spectrum_influence:
+ *   eta_host: optional N bytes, non-zero = occluded ray (sky.py:327-332; applied before the sun disc :334)
+ *   Y/dop/aop_host: N doubles each; theta/phi_host: optional N doubles (sky.py:99-113 caches)     */
+int isy_sky_call_host(const isy_sky_params* sky, double theta_s, double phi_s, const double* ray_quat_host,
+                      int64_t N, const uint8_t* eta_host, int device, double* Y_host, double* dop_host,
+                      double* aop_host, double* theta_host, double* phi_host);
+
+/* spectrum_influence(v, irgbu) sky.py:671-703 over ONE call of n values (call-wide nansum /
+ * nanmax reductions); irgbu: rows*5 doubles with n % rows == 0 (tiled like sky.py:689).
+ *   channels_host: optional n*5 doubles (the function's return value)
+ *   sum_host     : optional n doubles   (.sum(axis=1), what Sky.__call__ returns as Y, sky.py:344) */
+int isy_spectrum_influence_host(const double* v_host, int64_t n, const double* irgbu_host, int64_t rows,
+                                int device, double* sum_host, double* channels_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISY_B200_H_ */

@@ -1,0 +1,517 @@
+// C ABI of the sm_100a view renderer (include/isy_b200.h). Host-side plumbing only:
+// handle management, workspace carving, launches, and the host-buffer variants.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "isy_kernels.cuh"
+
+using namespace isy;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                    \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(ISY_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct isy_world {
+    int device;
+    int64_t T;
+    double horizon;
+    float* d_planes;  // 9 planes of T floats
+    float* d_rgb;     // T*3
+};
+
+struct isy_eye {
+    int device;
+    int64_t N;
+    int32_t S;
+    int64_t R;
+    double* d_quat;  // R*4
+    double* d_py;    // R*2
+    float* d_w;      // R
+};
+
+extern "C" {
+
+int isy_abi_version(void) { return ISY_ABI_VERSION; }
+const char* isy_last_error(void) { return g_err.c_str(); }
+int64_t isy_launch_count(void) { return g_launches.load(); }
+
+int isy_world_create(const float* tri_xyz, const float* tri_rgb, int64_t T, double horizon, int device,
+                     isy_world** out) {
+    if (!tri_xyz || !tri_rgb || !out || T < 0 || T > (1 << 30)) return fail(ISY_ERR_INVALID, "isy_world_create: bad argument");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(ISY_ERR_CUDA, "isy_world_create: cannot select CUDA device %d (no CPU fallback)", device);
+    isy_world* w = new isy_world{device, T, horizon, nullptr, nullptr};
+    size_t n = (size_t)std::max<int64_t>(T, 1);
+    std::vector<float> planes(9 * n);
+    for (int64_t t = 0; t < T; ++t)
+        for (int k = 0; k < 9; ++k) planes[(size_t)k * T + t] = tri_xyz[t * 9 + k];
+    CUDA_TRY(cudaMalloc(&w->d_planes, 9 * n * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&w->d_rgb, 3 * n * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(w->d_planes, planes.data(), 9 * (size_t)T * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(w->d_rgb, tri_rgb, 3 * (size_t)T * sizeof(float), cudaMemcpyHostToDevice));
+    *out = w;
+    return ISY_OK;
+}
+
+int isy_world_destroy(isy_world* w) {
+    if (!w) return ISY_OK;
+    DeviceGuard g(w->device);
+    cudaFree(w->d_planes);
+    cudaFree(w->d_rgb);
+    delete w;
+    return ISY_OK;
+}
+
+int64_t isy_world_triangles(const isy_world* w) { return w ? w->T : -1; }
+
+int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int32_t S, int device, isy_eye** out) {
+    if (!omm_quat || !out || N <= 0 || S <= 0) return fail(ISY_ERR_INVALID, "isy_eye_create: bad argument");
+    if (S > 32 || (S & (S - 1))) return fail(ISY_ERR_INVALID, "isy_eye_create: samples per ommatidium must be 1,2,4,8,16 or 32 (got %d)", S);
+    if (N * S > (1ll << 30)) return fail(ISY_ERR_INVALID, "isy_eye_create: too many rays");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(ISY_ERR_CUDA, "isy_eye_create: cannot select CUDA device %d (no CPU fallback)", device);
+    isy_eye* e = new isy_eye{device, N, S, N * S, nullptr, nullptr, nullptr};
+    size_t R = (size_t)e->R;
+    CUDA_TRY(cudaMalloc(&e->d_quat, R * 4 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&e->d_py, R * 2 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&e->d_w, R * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(e->d_quat, omm_quat, R * 4 * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<float> w(R, 1.0f / (float)S);
+    if (weights) std::copy(weights, weights + R, w.begin());
+    CUDA_TRY(cudaMemcpy(e->d_w, w.data(), R * sizeof(float), cudaMemcpyHostToDevice));
+    eye_setup_kernel<<<(unsigned)((R + 255) / 256), 256>>>(e->d_quat, e->d_py, (int)R);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    *out = e;
+    return ISY_OK;
+}
+
+int isy_eye_destroy(isy_eye* e) {
+    if (!e) return ISY_OK;
+    DeviceGuard g(e->device);
+    cudaFree(e->d_quat);
+    cudaFree(e->d_py);
+    cudaFree(e->d_w);
+    delete e;
+    return ISY_OK;
+}
+
+int64_t isy_eye_rays(const isy_eye* e) { return e ? e->R : -1; }
+
+}  // extern "C"
+
+namespace {
+
+struct Plan {
+    int grid;
+    int splits;
+    int slab_cap;
+    size_t off_queue, off_status, off_sun, off_vis, off_entry, off_exact, total;
+};
+
+int device_sms(int device) {
+    static std::mutex mu;
+    static int cache[64] = {0};
+    std::lock_guard<std::mutex> lk(mu);
+    if (device >= 0 && device < 64 && cache[device]) return cache[device];
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
+    if (device >= 0 && device < 64) cache[device] = sms;
+    return sms;
+}
+
+Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
+    Plan pl;
+    int sms = device_sms(w->device);
+    int64_t rays = H * e->R;
+    int64_t passes = (rays + kPassRays - 1) / kPassRays;
+    int max_ctas = sms;  // one persistent CTA per SM (72 KB tile + 512 threads)
+    int64_t splits = 1;
+    if (P < max_ctas) splits = std::min<int64_t>(passes, (max_ctas + P - 1) / std::max<int64_t>(P, 1));
+    pl.splits = (int)std::max<int64_t>(splits, 1);
+    int64_t items = P * pl.splits;
+    pl.grid = (int)std::max<int64_t>(1, std::min<int64_t>(items, max_ctas));
+    pl.slab_cap = (int)std::min<int64_t>(2 * std::max<int64_t>(w->T, 1), 1 << 17);
+    size_t off = 0;
+    pl.off_queue = off, off += 256;
+    pl.off_status = off, off += 256;
+    pl.off_sun = off, off += align_up((size_t)std::max<int64_t>(P * H, 1) * sizeof(SunConst));
+    pl.off_vis = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(int));
+    pl.off_entry = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(Entry));
+    pl.off_exact = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(Exact));
+    pl.total = off;
+    return pl;
+}
+
+int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, const double* pos, const double* yaw,
+                  const double* vquat, const double* sun, const double* init_c, const isy_sky_params* sky,
+                  uint32_t flags, const isy_outputs* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!w || !e || !pos || !out || P < 0 || H <= 0) return fail(ISY_ERR_INVALID, "isy_render: bad argument");
+    if (w->device != e->device) return fail(ISY_ERR_INVALID, "isy_render: world and eye live on different devices");
+    if (P * H * e->R >= (1ll << 31) * 1024) return fail(ISY_ERR_INVALID, "isy_render: batch too large");
+    if (P == 0) return ISY_OK;
+    isy_sky_params sp;
+    memset(&sp, 0, sizeof sp);
+    if (sky) sp = *sky;
+    if (sp.kind == ISY_SKY_PEREZ && !sun) return fail(ISY_ERR_INVALID, "isy_render: Perez sky needs a sun position");
+    if ((out->Y || out->dop || out->aop) && sp.kind == ISY_SKY_NONE)
+        return fail(ISY_ERR_INVALID, "isy_render: sky outputs requested without a sky");
+    Plan pl = make_plan(w, e, P, H);
+    if (!ws || ws_bytes < pl.total)
+        return fail(ISY_ERR_WORKSPACE, "isy_render: workspace %zu B < required %zu B", ws_bytes, pl.total);
+
+    unsigned char* base = (unsigned char*)ws;
+    RenderParams rp;
+    memset(&rp, 0, sizeof rp);
+    rp.tri_planes = w->d_planes, rp.tri_rgb = w->d_rgb, rp.T = (int)w->T, rp.horizon = w->horizon;
+    rp.eye_py = e->d_py, rp.eye_quat = e->d_quat, rp.eye_w = e->d_w;
+    rp.N = (int)e->N, rp.S = e->S, rp.R = (int)e->R;
+    rp.P = (int)P, rp.H = (int)H;
+    rp.pos = pos, rp.yaw = yaw, rp.vquat = vquat, rp.init_c = init_c;
+    rp.sun = (const SunConst*)(base + pl.off_sun);
+    rp.sun_per_view = (flags & ISY_FLAG_SUN_PER_VIEW) ? 1 : 0;
+    rp.sky = sp, rp.flags = flags, rp.out = *out;
+    rp.queue = (unsigned int*)(base + pl.off_queue);
+    rp.status = (int*)(base + pl.off_status);
+    rp.slab_vis = (int*)(base + pl.off_vis);
+    rp.slab_entry = (Entry*)(base + pl.off_entry);
+    rp.slab_exact = (Exact*)(base + pl.off_exact);
+    rp.slab_cap = pl.slab_cap, rp.splits = pl.splits, rp.items = (int)(P * pl.splits);
+
+    CUDA_TRY(cudaMemsetAsync(base, 0, 512, st));
+    if (sp.kind == ISY_SKY_PEREZ) {
+        int n = rp.sun_per_view ? (int)(P * H) : 1;
+        sun_setup_kernel<<<(n + 127) / 128, 128, 0, st>>>(sun, n, sp, (SunConst*)(base + pl.off_sun));
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    size_t smem = (size_t)kSmemEntries * sizeof(Entry);
+    if (flags & ISY_FLAG_OUT_F64) {
+        CUDA_TRY(cudaFuncSetAttribute(render_brute_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        render_brute_kernel<true><<<pl.grid, kThreads, smem, st>>>(rp);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(render_brute_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        render_brute_kernel<false><<<pl.grid, kThreads, smem, st>>>(rp);
+    }
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ISY_OK;
+}
+
+// read back the sticky status word of a workspace (synchronises the stream)
+int check_status(void* ws, cudaStream_t st) {
+    int status = 0;
+    CUDA_TRY(cudaMemcpyAsync(&status, (unsigned char*)ws + 256, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (status == ISY_ERR_OVERFLOW)
+        return fail(ISY_ERR_OVERFLOW, "isy_render: a position sees more triangle copies than the workspace slab holds");
+    return status ? fail(status, "isy_render: device-side error %d", status) : ISY_OK;
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+};
+
+}  // namespace
+
+extern "C" {
+
+size_t isy_render_workspace_bytes(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
+    if (!w || !e || P < 0 || H <= 0) return 0;
+    DeviceGuard g(w->device);
+    return make_plan(w, e, P, H).total;
+}
+
+int isy_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, const double* pos_dev,
+               const double* yaw_dev, const double* view_quat_dev, const double* sun_dev, const isy_sky_params* sky,
+               uint32_t flags, const isy_outputs* out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!w) return fail(ISY_ERR_INVALID, "isy_render: null world");
+    DeviceGuard g(w->device);
+    if (!g.ok) return fail(ISY_ERR_CUDA, "isy_render: cannot select CUDA device %d (no CPU fallback)", w->device);
+    return launch_render(w, e, P, H, pos_dev, yaw_dev, view_quat_dev, sun_dev, nullptr, sky, flags, out_dev,
+                         workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+int isy_workspace_status(void* workspace_dev, void* stream) { return check_status(workspace_dev, (cudaStream_t)stream); }
+
+int isy_render_host(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, const double* pos_host,
+                    const double* yaw_host, const double* view_quat_host, const double* sun_host,
+                    const isy_sky_params* sky, uint32_t flags, const isy_outputs* out_host) {
+    if (!w || !e || !pos_host || !out_host || P < 0 || H <= 0) return fail(ISY_ERR_INVALID, "isy_render_host: bad argument");
+    DeviceGuard g(w->device);
+    if (!g.ok) return fail(ISY_ERR_CUDA, "isy_render_host: cannot select CUDA device %d (no CPU fallback)", w->device);
+    if (P == 0) return ISY_OK;
+    const size_t esz = (flags & ISY_FLAG_OUT_F64) ? 8 : 4;
+    const int64_t R = e->R, N = e->N;
+    const bool sun_pv = flags & ISY_FLAG_SUN_PER_VIEW;
+
+    // positions are processed in chunks so that compute of chunk c+1 overlaps the D2H of chunk c
+    const size_t bytes_per_pos = (size_t)H * ((out_host->rgb ? 3 * N * esz : 0) + (out_host->hit ? R * 4 : 0) +
+                                              (out_host->depth ? R * esz : 0) +
+                                              ((out_host->Y ? 1 : 0) + (out_host->dop ? 1 : 0) + (out_host->aop ? 1 : 0)) * N * esz);
+    int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(P, (int64_t)((256ull << 20) / std::max<size_t>(bytes_per_pos, 1))));
+    if (chunk < P) chunk = std::max<int64_t>(chunk, std::min<int64_t>(P, 2 * device_sms(w->device)));
+
+    cudaStream_t s_comp, s_copy;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+    struct Slot {
+        DevBuf<unsigned char> rgb, hit, depth, Y, dop, aop, ws;
+        cudaEvent_t done = nullptr, copied = nullptr;
+    } slot[2];
+    DevBuf<double> d_pos, d_yaw, d_vq, d_sun;
+    int rc = ISY_OK;
+    auto cleanup = [&]() {
+        for (auto& s : slot) {
+            if (s.done) cudaEventDestroy(s.done);
+            if (s.copied) cudaEventDestroy(s.copied);
+        }
+        cudaStreamDestroy(s_comp);
+        cudaStreamDestroy(s_copy);
+    };
+#define TRY_CLEAN(expr)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess) {                                                                         \
+            cleanup();                                                                                    \
+            return fail(ISY_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                                 \
+    } while (0)
+
+    TRY_CLEAN(d_pos.alloc((size_t)P * 3));
+    TRY_CLEAN(cudaMemcpyAsync(d_pos.p, pos_host, (size_t)P * 3 * 8, cudaMemcpyHostToDevice, s_comp));
+    if (yaw_host) {
+        TRY_CLEAN(d_yaw.alloc((size_t)P * H));
+        TRY_CLEAN(cudaMemcpyAsync(d_yaw.p, yaw_host, (size_t)P * H * 8, cudaMemcpyHostToDevice, s_comp));
+    }
+    if (view_quat_host) {
+        TRY_CLEAN(d_vq.alloc((size_t)P * H * 4));
+        TRY_CLEAN(cudaMemcpyAsync(d_vq.p, view_quat_host, (size_t)P * H * 4 * 8, cudaMemcpyHostToDevice, s_comp));
+    }
+    if (sun_host) {
+        size_t n = sun_pv ? (size_t)P * H * 2 : 2;
+        TRY_CLEAN(d_sun.alloc(n));
+        TRY_CLEAN(cudaMemcpyAsync(d_sun.p, sun_host, n * 8, cudaMemcpyHostToDevice, s_comp));
+    }
+    const size_t ws_bytes = isy_render_workspace_bytes(w, e, chunk, H);
+    const int nslots = chunk < P ? 2 : 1;
+    for (int i = 0; i < nslots; ++i) {
+        Slot& s = slot[i];
+        size_t V = (size_t)chunk * H;
+        if (out_host->rgb) TRY_CLEAN(s.rgb.alloc(V * N * 3 * esz));
+        if (out_host->hit) TRY_CLEAN(s.hit.alloc(V * R * 4));
+        if (out_host->depth) TRY_CLEAN(s.depth.alloc(V * R * esz));
+        if (out_host->Y) TRY_CLEAN(s.Y.alloc(V * N * esz));
+        if (out_host->dop) TRY_CLEAN(s.dop.alloc(V * N * esz));
+        if (out_host->aop) TRY_CLEAN(s.aop.alloc(V * N * esz));
+        TRY_CLEAN(s.ws.alloc(ws_bytes));
+        TRY_CLEAN(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        TRY_CLEAN(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    }
+
+    int ci = 0;
+    for (int64_t p0 = 0; p0 < P && rc == ISY_OK; p0 += chunk, ++ci) {
+        Slot& s = slot[ci % nslots];
+        int64_t pc = std::min(chunk, P - p0);
+        size_t v0 = (size_t)p0 * H, V = (size_t)pc * H;
+        if (ci >= nslots) TRY_CLEAN(cudaStreamWaitEvent(s_comp, s.copied, 0));   // slot buffers free again
+        isy_outputs o;
+        o.rgb = s.rgb.p, o.hit = (int32_t*)s.hit.p, o.depth = s.depth.p, o.Y = s.Y.p, o.dop = s.dop.p, o.aop = s.aop.p;
+        rc = launch_render(w, e, pc, H, d_pos.p + 3 * p0, d_yaw.p ? d_yaw.p + v0 : nullptr,
+                           d_vq.p ? d_vq.p + 4 * v0 : nullptr, d_sun.p ? (sun_pv ? d_sun.p + 2 * v0 : d_sun.p) : nullptr,
+                           nullptr, sky, flags, &o, s.ws.p, ws_bytes, s_comp);
+        if (rc != ISY_OK) break;
+        TRY_CLEAN(cudaEventRecord(s.done, s_comp));
+        TRY_CLEAN(cudaStreamWaitEvent(s_copy, s.done, 0));
+        auto d2h = [&](void* dst, const void* src, size_t off, size_t bytes) {
+            return cudaMemcpyAsync((unsigned char*)dst + off, src, bytes, cudaMemcpyDeviceToHost, s_copy);
+        };
+        if (out_host->rgb) TRY_CLEAN(d2h(out_host->rgb, s.rgb.p, v0 * N * 3 * esz, V * N * 3 * esz));
+        if (out_host->hit) TRY_CLEAN(d2h(out_host->hit, s.hit.p, v0 * R * 4, V * R * 4));
+        if (out_host->depth) TRY_CLEAN(d2h(out_host->depth, s.depth.p, v0 * R * esz, V * R * esz));
+        if (out_host->Y) TRY_CLEAN(d2h(out_host->Y, s.Y.p, v0 * N * esz, V * N * esz));
+        if (out_host->dop) TRY_CLEAN(d2h(out_host->dop, s.dop.p, v0 * N * esz, V * N * esz));
+        if (out_host->aop) TRY_CLEAN(d2h(out_host->aop, s.aop.p, v0 * N * esz, V * N * esz));
+        TRY_CLEAN(cudaEventRecord(s.copied, s_copy));
+    }
+    if (rc == ISY_OK) {
+        TRY_CLEAN(cudaStreamSynchronize(s_copy));
+        for (int i = 0; i < nslots && rc == ISY_OK; ++i) rc = check_status(slot[i].ws.p, s_comp);
+    } else {
+        cudaStreamSynchronize(s_comp);
+        cudaStreamSynchronize(s_copy);
+    }
+    cleanup();
+    return rc;
+#undef TRY_CLEAN
+}
+
+int isy_world_call_host(const isy_world* w, const double* pos3_host, const double* ray_quat_host, int64_t N,
+                        const double* init_c_host, double* rgb_host, int32_t* hit_host, double* depth_host) {
+    if (!w || !pos3_host || !ray_quat_host || N < 0) return fail(ISY_ERR_INVALID, "isy_world_call_host: bad argument");
+    if (N == 0) return ISY_OK;
+    isy_eye* eye = nullptr;
+    int rc = isy_eye_create(ray_quat_host, nullptr, N, 1, w->device, &eye);
+    if (rc != ISY_OK) return rc;
+    DeviceGuard g(w->device);
+    DevBuf<double> d_pos, d_init, d_rgb, d_depth;
+    DevBuf<int32_t> d_hit;
+    DevBuf<unsigned char> ws;
+    size_t ws_bytes = isy_render_workspace_bytes(w, eye, 1, 1);
+    auto done = [&](int code) {
+        isy_eye_destroy(eye);
+        return code;
+    };
+#define TRY_EYE(expr)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return done(fail(ISY_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__)); \
+    } while (0)
+    TRY_EYE(d_pos.alloc(3));
+    TRY_EYE(cudaMemcpy(d_pos.p, pos3_host, 24, cudaMemcpyHostToDevice));
+    if (init_c_host) {
+        TRY_EYE(d_init.alloc(N));
+        TRY_EYE(cudaMemcpy(d_init.p, init_c_host, N * 8, cudaMemcpyHostToDevice));
+    }
+    isy_outputs o;
+    memset(&o, 0, sizeof o);
+    if (rgb_host) {
+        TRY_EYE(d_rgb.alloc(N * 3));
+        o.rgb = d_rgb.p;
+    }
+    if (hit_host) {
+        TRY_EYE(d_hit.alloc(N));
+        o.hit = d_hit.p;
+    }
+    if (depth_host) {
+        TRY_EYE(d_depth.alloc(N));
+        o.depth = d_depth.p;
+    }
+    TRY_EYE(ws.alloc(ws_bytes));
+    rc = launch_render(w, eye, 1, 1, d_pos.p, nullptr, nullptr, nullptr, d_init.p, nullptr, ISY_FLAG_OUT_F64, &o, ws.p,
+                       ws_bytes, 0);
+    if (rc != ISY_OK) return done(rc);
+    rc = check_status(ws.p, 0);
+    if (rc != ISY_OK) return done(rc);
+    if (rgb_host) TRY_EYE(cudaMemcpy(rgb_host, d_rgb.p, N * 24, cudaMemcpyDeviceToHost));
+    if (hit_host) TRY_EYE(cudaMemcpy(hit_host, d_hit.p, N * 4, cudaMemcpyDeviceToHost));
+    if (depth_host) TRY_EYE(cudaMemcpy(depth_host, d_depth.p, N * 8, cudaMemcpyDeviceToHost));
+    return done(ISY_OK);
+#undef TRY_EYE
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int isy_sky_call_host(const isy_sky_params* sky, double theta_s, double phi_s, const double* ray_quat_host, int64_t N,
+                      const uint8_t* eta_host, int device, double* Y_host, double* dop_host, double* aop_host,
+                      double* theta_host, double* phi_host) {
+    if (!sky || !ray_quat_host || !Y_host || !dop_host || !aop_host || N < 0)
+        return fail(ISY_ERR_INVALID, "isy_sky_call_host: bad argument");
+    if (sky->kind != ISY_SKY_UNIFORM && sky->kind != ISY_SKY_PEREZ)
+        return fail(ISY_ERR_INVALID, "isy_sky_call_host: sky kind must be UNIFORM or PEREZ");
+    if (N == 0) return ISY_OK;
+    DeviceGuard g(device);
+    if (!g.ok) return fail(ISY_ERR_CUDA, "isy_sky_call_host: cannot select CUDA device %d (no CPU fallback)", device);
+    DevBuf<double> d_q, d_out, d_sun;
+    DevBuf<SunConst> d_sc;
+    DevBuf<uint8_t> d_eta;
+    if (eta_host) {
+        CUDA_TRY(d_eta.alloc((size_t)N));
+        CUDA_TRY(cudaMemcpy(d_eta.p, eta_host, (size_t)N, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(d_q.alloc((size_t)N * 4));
+    CUDA_TRY(d_out.alloc((size_t)N * 5));
+    CUDA_TRY(d_sun.alloc(2));
+    CUDA_TRY(d_sc.alloc(1));
+    CUDA_TRY(cudaMemcpy(d_q.p, ray_quat_host, (size_t)N * 32, cudaMemcpyHostToDevice));
+    if (sky->kind == ISY_SKY_PEREZ) {
+        double s[2] = {theta_s, phi_s};
+        CUDA_TRY(cudaMemcpy(d_sun.p, s, 16, cudaMemcpyHostToDevice));
+        sun_setup_kernel<<<1, 32>>>(d_sun.p, 1, *sky, d_sc.p);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    double *dY = d_out.p, *dP = dY + N, *dA = dP + N, *dT = dA + N, *dF = dT + N;
+    sky_dirs_kernel<<<(unsigned)((N + 255) / 256), 256>>>(d_q.p, N, *sky, d_sc.p, d_eta.p, dY, dP, dA, dT, dF);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(Y_host, dY, (size_t)N * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(dop_host, dP, (size_t)N * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(aop_host, dA, (size_t)N * 8, cudaMemcpyDeviceToHost));
+    if (theta_host) CUDA_TRY(cudaMemcpy(theta_host, dT, (size_t)N * 8, cudaMemcpyDeviceToHost));
+    if (phi_host) CUDA_TRY(cudaMemcpy(phi_host, dF, (size_t)N * 8, cudaMemcpyDeviceToHost));
+    return ISY_OK;
+}
+
+int isy_spectrum_influence_host(const double* v_host, int64_t n, const double* irgbu_host, int64_t rows, int device,
+                                double* sum_host, double* channels_host) {
+    if (!v_host || !irgbu_host || (!sum_host && !channels_host) || n < 0 || rows <= 0)
+        return fail(ISY_ERR_INVALID, "isy_spectrum_influence_host: bad argument");
+    if (n % rows) return fail(ISY_ERR_INVALID, "isy_spectrum_influence_host: %lld values cannot be tiled by %lld irgbu rows",
+                              (long long)n, (long long)rows);
+    if (n == 0) return ISY_OK;
+    DeviceGuard g(device);
+    if (!g.ok) return fail(ISY_ERR_CUDA, "isy_spectrum_influence_host: cannot select CUDA device %d (no CPU fallback)", device);
+    DevBuf<double> d_v, d_w, d_o, d_c;
+    CUDA_TRY(d_v.alloc((size_t)n));
+    if (sum_host) CUDA_TRY(d_o.alloc((size_t)n));
+    if (channels_host) CUDA_TRY(d_c.alloc((size_t)n * 5));
+    CUDA_TRY(d_w.alloc((size_t)rows * 5));
+    CUDA_TRY(cudaMemcpy(d_v.p, v_host, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_w.p, irgbu_host, (size_t)rows * 40, cudaMemcpyHostToDevice));
+    spectrum_kernel<<<1, 1024>>>(d_v.p, n, d_w.p, rows, d_o.p, d_c.p);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (sum_host) CUDA_TRY(cudaMemcpy(sum_host, d_o.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    if (channels_host) CUDA_TRY(cudaMemcpy(channels_host, d_c.p, (size_t)n * 40, cudaMemcpyDeviceToHost));
+    return ISY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,207 @@
+// Shared definitions of the sm_100a view renderer: layouts, exact (reference-order) fp64
+// helpers and the fp32 edge-function filter.  Reference = InvertSy env/world.py, env/sky.py.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/isy_b200.h"
+
+namespace isy {
+
+constexpr double kPi = 3.141592653589793238462643383279502884;
+constexpr double kHalfPi = kPi / 2;     // np.pi / 2
+constexpr double kTwoPi = 2 * kPi;      // 2 * np.pi
+constexpr double kEps = 2.220446049250313e-16;  // invertsy/__helpers.py:10
+
+// ------------------------------------------------------------------------------------------
+// One painted copy of a visible triangle, as seen from one position (world.py:109-120).
+// `Entry` is the fp32 filter record staged in shared memory (48 B, three LDS.128 per test,
+// broadcast to the warp); `Exact` is the fp64 record read only by the rare exact re-check.
+//
+//   edge k of the reference's same-side test (world.py:482-526), k = 0: B->C (ref A),
+//   1: A->C (ref B), 2: A->B (ref C):
+//       inside  <=>  for all k   cross2(u_k, p - a_k) * o_k >= 0
+//   Entry holds E_k(p) = (A_k p_theta + B_k p_phi + C_k), the same cross product multiplied by
+//   sign(o_k) and scaled so |A_k| + |B_k| = 1; then |E_k(fp32) - E_k(exact)| < kEdgeEps for every
+//   query in [-pi/2, pi/2] x (-pi, pi] and the sign of E_k decides the test unless |E_k| <= kEdgeEps.
+// ------------------------------------------------------------------------------------------
+struct __align__(16) Entry {
+    float A0, B0, C0, A1;
+    float B1, C1, A2, B2;
+    float C2;
+    int32_t tri;       // triangle index in the world
+    int32_t dist_lo;   // min-vertex distance (world.py:97), fp64 bits
+    int32_t dist_hi;
+};
+static_assert(sizeof(Entry) == 48, "Entry must be 48 bytes");
+
+struct Exact {
+    double th[3];  // vertex pitch-space angle  (world.py:110)
+    double ph[3];  // vertex azimuth, seam-shifted for this copy (world.py:109, :117-120)
+    double o[3];   // cross2(u_k, ref_k - a_k) as the reference computes it
+};
+
+// rounding budget of the fp32 evaluation of a normalised edge function ("fp32
+// filter bound"): with u = 2^-24, |A|+|B| = 1, |p_theta| <= pi/2, |p_phi| <= pi, |C| <= 2pi:
+// coefficient rounding 3pi*u + query rounding pi*u + two FMA roundings (3pi + 3.5pi)*u < 2.0e-6
+constexpr float kEdgeEps = 3.0e-6f;
+
+// per-view sun constants (sky.py:304-321, 501-521), computed once per view by sun_setup_kernel
+struct SunConst {
+    double sx, sy, sz;   // unit vector towards the sun: (sin ths cos phs, sin ths sin phs, cos ths)
+    double i00;          // L(0, theta_s)                       sky.py:309
+    double K;            // i_00 * i_90 / (i_00 - i_90 + eps)   sky.py:312 (grouped as written there)
+    double i90;
+    double Yz;           // zenith luminance                    sky.py:501-510
+    double Mp;           // max degree of polarisation          sky.py:513-521
+};
+
+struct RenderParams {
+    // world (SoA planes: x0 y0 z0 x1 y1 z1 x2 y2 z2, each T floats) and colours T*3
+    const float* tri_planes;
+    const float* tri_rgb;
+    int T;
+    double horizon;
+    // eye
+    const double* eye_py;    // [R][2] eye-frame (pitch, yaw)
+    const double* eye_quat;  // [R][4]
+    const float* eye_w;      // [R]
+    int N, S, R;
+    // views
+    int P, H;
+    const double* pos;       // [P][3]
+    const double* yaw;       // [P][H] or null
+    const double* vquat;     // [P][H][4] or null
+    const double* init_c;    // [B][R] external background luminance (world.py:79-82) or null
+    const SunConst* sun;     // [1] or [B]
+    int sun_per_view;
+    isy_sky_params sky;
+    uint32_t flags;
+    isy_outputs out;
+    // workspace
+    unsigned int* queue;     // dynamic work counter
+    int* status;             // sticky error flag
+    int* slab_vis;           // [grid][slab_cap] visible triangle ids
+    Entry* slab_entry;       // [grid][slab_cap]
+    Exact* slab_exact;       // [grid][slab_cap]
+    int slab_cap;
+    int splits;              // CTAs sharing one position (each redoes the cull, takes a ray slice)
+    int items;               // P * splits
+};
+
+// ---- exact fp64 arithmetic in the reference's order (no FMA contraction) ----
+__device__ __forceinline__ double cross2_rn(double u0, double u1, double v0, double v1) {
+    // np.cross on 2-vectors: u0*v1 - u1*v0, each product rounded (world.py:526)
+    return __dsub_rn(__dmul_rn(u0, v1), __dmul_rn(u1, v0));
+}
+
+__device__ __forceinline__ double norm2_rn(double x, double y, double z) {
+    // np.linalg.norm(axis=2) before the sqrt: (x*x + y*y) + z*z (world.py:97)
+    return __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+}
+
+__device__ __forceinline__ bool inside_exact(const Exact& t, double p, double y) {
+    // same_side_technique (world.py:482-503) on one painted copy
+    double e0 = cross2_rn(t.th[2] - t.th[1], t.ph[2] - t.ph[1], p - t.th[1], y - t.ph[1]);
+    if (!(__dmul_rn(e0, t.o[0]) >= 0)) return false;
+    double e1 = cross2_rn(t.th[2] - t.th[0], t.ph[2] - t.ph[0], p - t.th[0], y - t.ph[0]);
+    if (!(__dmul_rn(e1, t.o[1]) >= 0)) return false;
+    double e2 = cross2_rn(t.th[1] - t.th[0], t.ph[1] - t.ph[0], p - t.th[0], y - t.ph[0]);
+    return __dmul_rn(e2, t.o[2]) >= 0;
+}
+
+__device__ __forceinline__ void edge_coeffs(double a_th, double a_ph, double b_th, double b_ph, double o, float& A,
+                                            float& B, float& C) {
+    double u_th = b_th - a_th, u_ph = b_ph - a_ph;
+    double n = fabs(u_th) + fabs(u_ph);
+    if (o != o) {           // NaN reference cross: the reference's `>= 0` is False for every point
+        A = 0.f, B = 0.f, C = -1.f;
+        return;
+    }
+    if (o == 0.0 || !(n > 0.0)) {  // degenerate: product is +-0 -> test passes for every point (world.py:526)
+        A = 0.f, B = 0.f, C = 1.f;
+        return;
+    }
+    double s = (o > 0.0 ? 1.0 : -1.0) / n;
+    // cross2(u, p - a) = u_th (p_ph - a_ph) - u_ph (p_th - a_th)
+    A = (float)(-u_ph * s);
+    B = (float)(u_th * s);
+    C = (float)((u_ph * a_th - u_th * a_ph) * s);
+}
+
+__device__ __forceinline__ void finish_copy(const double th[3], const double ph[3], double dist, int tri, Entry& e,
+                                            Exact& x) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        x.th[k] = th[k];
+        x.ph[k] = ph[k];
+    }
+    x.o[0] = cross2_rn(th[2] - th[1], ph[2] - ph[1], th[0] - th[1], ph[0] - ph[1]);
+    x.o[1] = cross2_rn(th[2] - th[0], ph[2] - ph[0], th[1] - th[0], ph[1] - ph[0]);
+    x.o[2] = cross2_rn(th[1] - th[0], ph[1] - ph[0], th[2] - th[0], ph[2] - ph[0]);
+    edge_coeffs(th[1], ph[1], th[2], ph[2], x.o[0], e.A0, e.B0, e.C0);
+    edge_coeffs(th[0], ph[0], th[2], ph[2], x.o[1], e.A1, e.B1, e.C1);
+    edge_coeffs(th[0], ph[0], th[1], ph[1], x.o[2], e.A2, e.B2, e.C2);
+    e.tri = tri;
+    e.dist_lo = __double2loint(dist);
+    e.dist_hi = __double2hiint(dist);
+}
+
+// wrap an angle to (-pi, pi] (the range of SciPy's as_euler yaw)
+__device__ __forceinline__ double wrap_yaw(double y) {
+    if (y > kPi || y <= -kPi) {
+        y = remainder(y, kTwoPi);  // [-pi, pi]
+        if (y <= -kPi) y += kTwoPi;
+    }
+    return y;
+}
+
+// (a + pi) % (2 pi) - pi with NumPy's floored modulo (sky.py:105, :324): result in [-pi, pi)
+__device__ __forceinline__ double wrap_pi_numpy(double a) {
+    double m = fmod(a + kPi, kTwoPi);
+    if (m < 0) m += kTwoPi;
+    return m - kPi;
+}
+
+// first column of the rotation matrix of unit quaternion (x,y,z,w) = ori.apply([1,0,0]) (sky.py:101)
+__device__ __forceinline__ void quat_dir(double x, double y, double z, double w, double& dx, double& dy, double& dz) {
+    dx = 1.0 - 2.0 * (y * y + z * z);
+    dy = 2.0 * (x * y + w * z);
+    dz = 2.0 * (x * z - w * y);
+}
+
+// ZYX Euler yaw/pitch of a direction (world.py:84): d = (cos p cos y, cos p sin y, -sin p)
+__device__ __forceinline__ void dir_pitch_yaw(double dx, double dy, double dz, double& pitch, double& yaw) {
+    yaw = atan2(dy, dx);
+    pitch = atan2(-dz, sqrt(dx * dx + dy * dy));
+}
+
+// Perez luminance L(chi, z) with cos(z) and cos(chi) supplied (sky.py:348-374)
+__device__ __forceinline__ double perez_f(double cos_z, bool above, double A, double B) {
+    return above ? 1.0 + A * exp(B / (cos_z + kEps)) : 0.0;
+}
+__device__ __forceinline__ double perez_phi(double chi, double cos_chi, double C, double D, double E) {
+    return 1.0 + C * exp(D * chi) + E * (cos_chi * cos_chi);
+}
+
+// Sky.__call__ for one direction (sky.py:304-334); d = unit view direction, theta = zenith angle
+__device__ __forceinline__ void sky_eval(const isy_sky_params& sp, const SunConst& sc, double dx, double dy, double dz,
+                                         double theta, double& Y, double& P, double& A, bool masked = false) {
+    double cg = dz * sc.sz + (dx * sc.sx + dy * sc.sy);      // cos(gamma), sky.py:304-305
+    cg = fmin(fmax(cg, -1.0), 1.0);
+    double gamma = acos(cg);
+    double cos_t = dz;
+    double f = perez_f(cos_t, theta < kHalfPi, sp.A, sp.B);
+    double i_prez = f * perez_phi(gamma, cg, sp.C, sp.D, sp.E);                 // sky.py:308
+    double i = (1.0 / (i_prez + kEps) - 1.0 / (sc.i00 + kEps)) * sc.K;          // sky.py:312
+    Y = fmax(sc.Yz * i_prez / (sc.i00 + kEps), 0.0);                            // sky.py:313
+    double lp = fmax(1.0 - cg * cg, 0.0) / (1.0 + cg * cg);                     // sky.py:316
+    double p = 2.0 / kPi * sc.Mp * lp * (theta * cos_t + (kHalfPi - theta) * i);  // sky.py:317
+    P = fmin(fmax(p, 0.0), 1.0);
+    A = wrap_pi_numpy(atan2(dy - sc.sy, dx - sc.sx) + kHalfPi);                 // sky.py:320-324
+    if (masked) Y = 0.0, P = 0.0, A = CUDART_NAN;                               // sky.py:330-332 (eta)
+    if (gamma < kPi / 60) Y = 17.0;                                             // sky.py:334
+}
+
+}  // namespace isy

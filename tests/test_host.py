@@ -1,0 +1,141 @@
+"""CPU: host-side logic of the drop-in (loaders, view generators, eta mask, C-ABI surface, loud failure)."""
+import ast
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import isy_oracle as o
+from conftest import ROOT, golden
+
+
+def test_library_exports_every_declared_symbol():
+    from invertsy_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "isy_b200.h")).read()
+    declared = set(re.findall(r"\b(isy_[a-z_0-9]+)\s*\(", header))
+    declared -= {"isy_status", "isy_sky_kind"}
+    assert declared == set(_lib.EXPORTS)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _lib.lib().isy_abi_version() == 1
+    assert _lib.launch_count() >= 0
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "invertsy_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "isy_oracle" not in src and "c_oracle" not in src and "ref_loader" not in src, f
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_compute_fails_loudly_without_a_gpu():
+    from scipy.spatial.transform import Rotation as R
+    import invertsy_b200 as ib
+    from invertsy_b200._lib import IsyError
+    ori = R.from_euler('Z', [[0.], [1.]])
+    with pytest.raises(IsyError):
+        ib.Seville2009()(np.zeros((1, 3)), ori)
+    with pytest.raises(IsyError):
+        ib.Sky(1., 0.)(ori)
+    with pytest.raises(RuntimeError):
+        ib.Renderer(ib.Seville2009(), ib.EyeLayout.from_angles(*ib.fibonacci_lattice(8)))
+
+
+def test_world_call_error_behaviour_matches_reference():
+    import invertsy_b200 as ib
+    with pytest.raises(IndexError):          # world.py:80 -> np.shape(None)[0]
+        ib.Seville2009()(np.zeros((1, 3)), None)
+
+
+def test_sky_scalars_and_assertions():
+    import invertsy_b200 as ib
+    g = golden("sky")
+    sky = ib.Sky(np.deg2rad(60), np.pi)
+    assert np.array_equal([sky.A, sky.B, sky.C, sky.D, sky.E], g["coef"])
+    assert sky.tau_L == float(g["tau_L"]) and sky.Y_z == float(g["Y_z"]) and sky.M_p == float(g["M_p"])
+    with pytest.raises(AssertionError):
+        _ = sky.Y
+    with pytest.raises(AssertionError):
+        sky.tau_L = 0.5
+    sky.tau_L = 3.
+    assert abs(sky.tau_L - 3.) < 1e-12
+    assert np.allclose([sky.A, sky.B, sky.C, sky.D, sky.E], o.sky_coefficients(3.))
+    s2 = ib.Sky(30., 90., degrees=True)
+    assert abs(s2.theta_s - np.pi / 6) < 1e-15 and abs(s2.phi_s - np.pi / 2) < 1e-15
+    c = sky.copy()
+    assert abs(c.tau_L - sky.tau_L) < 1e-12 and c.theta_s == sky.theta_s
+
+
+def test_loaders_and_lattices():
+    import invertsy_b200 as ib
+    pol, col = ib.Seville2009.load_world()
+    assert pol.shape == (5000, 3, 3) and pol.dtype == np.float32 and col.shape == (5000, 3)
+    assert np.all(col[:, [0, 2]] == 0) and col[:, 1].min() > 0.06 and col[:, 1].max() < 0.98
+    sp, sc = ib.SimpleWorld.load_world()
+    assert sp.shape == (3222, 3, 3) and np.allclose(sc, [0.8, 1.0, 0.8])
+    routes = ib.Seville2009.load_routes(degrees=True)
+    assert len(routes["path"]) == 133 and routes["path"][0].shape == (812, 4)
+    assert np.allclose(routes["path"][0][0], [8.45, 6.30, 0.01, -139.653564], atol=1e-5)
+    rad = ib.Seville2009.load_routes()["path"][0]
+    assert np.allclose(np.rad2deg(rad[:, 3]), routes["path"][0][:, 3])
+    p, y = ib.fibonacci_lattice(1000)
+    p2, y2 = o.fibonacci_eye(1000)
+    assert np.array_equal(p, p2) and np.array_equal(y, y2)
+    q = ib.render.angles_to_quat(p, y)
+    q2 = o.eye_rotations(p, y).as_quat()
+    assert np.minimum(np.abs(q - q2).max(1), np.abs(q + q2).max(1)).max() < 1e-15
+
+
+def test_view_generators_follow_the_reference_iteration_order():
+    from invertsy_b200 import views
+    rows, cols, oris = 7, 5, 16
+    pos, yaw = views.grid_views(rows, cols, oris)
+    assert pos.shape == (rows * cols, 3) and yaw.shape == (rows * cols, oris)
+    for j, (row, col, ori) in enumerate(np.ndindex(rows, cols, oris)):     # simulation.py:2620, 2677
+        p, h = divmod(j, oris)
+        assert pos[p, 0] == np.float32(col * 10.) / np.float32(cols)
+        assert pos[p, 1] == np.float32(row * 10.) / np.float32(rows)
+        two_pi = np.float32(360.)
+        assert yaw[p, h] == (np.float32(ori) * two_pi / np.float32(oris) + two_pi / 2) % two_pi - two_pi / 2
+    assert yaw.min() >= -180 and yaw.max() < 180
+    import invertsy_b200 as ib
+    route = ib.Seville2009.load_routes(degrees=True)["path"][0][::40]
+    L, K, H = route.shape[0], 5, 8
+    pos, yaw = views.parallel_views(route, H, K, 0.02)
+    span = route[-1, :2] - route[0, :2]
+    unit = span / np.linalg.norm(span)
+    disp = np.array([-unit[1], unit[0]])
+    for j in range(L * K * H):                                              # simulation.py:2683-2701
+        m, k, ori = (j // H) % L, j // (L * H), j % H
+        r = 0.02 * float((k % 2 - (k + 1) % 2) * ((k + 1) // 2))
+        p, h = divmod(j, H)
+        assert np.allclose(pos[p], [route[m, 0] + r * disp[0], route[m, 1] + r * disp[1], route[m, 2]], atol=0, rtol=0)
+        d_yaw = views.ori2yaw(ori, H)
+        assert yaw[p, h] == (route[m, 3] + d_yaw + 180) % 360 - 180
+    # sharding: contiguous, disjoint, complete
+    for n, ws in [(40000, 8), (13, 4), (3, 8)]:
+        blocks = [views.shard_positions(n, r, ws) for r in range(ws)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(ws - 1))
+        sizes = [b - a for a, b in blocks]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_eta_mask_semantics():
+    from invertsy_b200.env.occlusion import add_noise
+    assert add_noise(noise=0., shape=(5, 3)).shape == () and not add_noise(noise=0., shape=(5, 3))
+    c = np.ones((5, 3))
+    c[add_noise(noise=0., shape=c.shape)] = 0.
+    assert c.sum() == 15
+    for kw in [dict(noise=.4, shape=(10, 3)), dict(noise=.4, shape=(10,)), dict(noise=np.array([1, 0, 1, 0]), shape=(4,)),
+               dict(noise=np.array([1, 0]), shape=(4,))]:
+        a = add_noise(rng=np.random.RandomState(3), **kw)
+        b = o.add_noise(rng=np.random.RandomState(3), **kw)
+        assert np.array_equal(a, b) and a.dtype == b.dtype
