@@ -140,7 +140,7 @@ def test_batched_render_matches_reference_goldens(ib, seville, omm1000):
     assert np.array_equal(out["rgb"], g["rgb"], equal_nan=True)
     # same views through full quaternions
     from scipy.spatial.transform import Rotation as R
-    q = R.from_euler('Z', poses[:, 3], degrees=True).as_quat()[:, None, :]
+    q = R.from_euler('Z', poses[:, 3:4], degrees=True).as_quat()[:, None, :]
     out2 = _render_np(r, pos=poses[:, :3], quat=q, outputs=("rgb", "hit"))
     assert np.array_equal(out2["hit"], g["hit"])
 
