@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--e2e-positions", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--brute-force", action="store_true")
+    ap.add_argument("--sky", default="perez", choices=["perez", "uniform", "none"],
+                    help="diagnostic only: the headline workload is 'perez'")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -224,7 +226,9 @@ def main():
     world = ib.Seville2009(device=local_rank)
     pitch, yaw_e = ib.fibonacci_lattice(N_OMM)
     eye = ib.EyeLayout.from_angles(pitch, yaw_e)
-    sky = ib.Sky(SUN[0], SUN[1])
+    sky = {"perez": ib.Sky(SUN[0], SUN[1]), "uniform": ib.UniformSky(10.), "none": None}[args.sky]
+    if args.sky != "perez":
+        config["workload"] += " [DIAGNOSTIC sky=%s]" % args.sky
     r = ib.Renderer(world, eye, sky=sky, device=local_rank)
 
     pos, yaw = grid_workload(rank, world_size, args.rows, args.cols, args.oris)
@@ -233,7 +237,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     pos_d = torch.as_tensor(pos, device=dev)
     yaw_d = torch.as_tensor(yaw, device=dev)
-    names = ("rgb", "hit", "depth", "Y", "dop", "aop")
+    names = ("rgb", "hit", "depth", "Y", "dop", "aop") if sky is not None else ("rgb", "hit", "depth")
     out = {}
 
     def step():
@@ -280,7 +284,7 @@ def main():
     # ---------------- e2e: host buffers through the C-ABI host entry point ----------------
     Pe = min(args.e2e_positions, P)
     sel = np.linspace(0, P - 1, Pe).astype(np.int64)
-    e_names = ("rgb", "Y", "dop", "aop")
+    e_names = ("rgb", "Y", "dop", "aop") if sky is not None else ("rgb",)
     pos_h = torch.as_tensor(pos[sel]).pin_memory()
     yaw_h = torch.as_tensor(yaw[sel]).pin_memory()
     host_out = {}

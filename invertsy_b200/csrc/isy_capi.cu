@@ -66,6 +66,7 @@ struct isy_eye {
     int64_t R;
     double* d_quat;  // R*4
     double* d_py;    // R*2
+    double* d_trig;  // R*4
     float* d_w;      // R
 };
 
@@ -110,16 +111,17 @@ int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int3
     if (N * S > (1ll << 30)) return fail(ISY_ERR_INVALID, "isy_eye_create: too many rays");
     DeviceGuard g(device);
     if (!g.ok) return fail(ISY_ERR_CUDA, "isy_eye_create: cannot select CUDA device %d (no CPU fallback)", device);
-    isy_eye* e = new isy_eye{device, N, S, N * S, nullptr, nullptr, nullptr};
+    isy_eye* e = new isy_eye{device, N, S, N * S, nullptr, nullptr, nullptr, nullptr};
     size_t R = (size_t)e->R;
     CUDA_TRY(cudaMalloc(&e->d_quat, R * 4 * sizeof(double)));
     CUDA_TRY(cudaMalloc(&e->d_py, R * 2 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&e->d_trig, R * 4 * sizeof(double)));
     CUDA_TRY(cudaMalloc(&e->d_w, R * sizeof(float)));
     CUDA_TRY(cudaMemcpy(e->d_quat, omm_quat, R * 4 * sizeof(double), cudaMemcpyHostToDevice));
     std::vector<float> w(R, 1.0f / (float)S);
     if (weights) std::copy(weights, weights + R, w.begin());
     CUDA_TRY(cudaMemcpy(e->d_w, w.data(), R * sizeof(float), cudaMemcpyHostToDevice));
-    eye_setup_kernel<<<(unsigned)((R + 255) / 256), 256>>>(e->d_quat, e->d_py, (int)R);
+    eye_setup_kernel<<<(unsigned)((R + 255) / 256), 256>>>(e->d_quat, e->d_py, e->d_trig, (int)R);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
@@ -132,6 +134,7 @@ int isy_eye_destroy(isy_eye* e) {
     DeviceGuard g(e->device);
     cudaFree(e->d_quat);
     cudaFree(e->d_py);
+    cudaFree(e->d_trig);
     cudaFree(e->d_w);
     delete e;
     return ISY_OK;
@@ -147,7 +150,7 @@ struct Plan {
     int grid;
     int splits;
     int slab_cap;
-    size_t off_queue, off_status, off_sun, off_vis, off_entry, off_exact, total;
+    size_t off_queue, off_status, off_sun, off_ftheta, off_vis, off_entry, off_exact, total;
 };
 
 int device_sms(int device) {
@@ -165,8 +168,8 @@ Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
     Plan pl;
     int sms = device_sms(w->device);
     int64_t rays = H * e->R;
-    int64_t passes = (rays + kPassRays - 1) / kPassRays;
-    int max_ctas = sms;  // one persistent CTA per SM (72 KB tile + 512 threads)
+    int64_t passes = (rays + kThreads - 1) / kThreads;
+    int max_ctas = sms;  // one persistent CTA per SM (~190 KB of shared memory, 512 threads)
     int64_t splits = 1;
     if (P < max_ctas) splits = std::min<int64_t>(passes, (max_ctas + P - 1) / std::max<int64_t>(P, 1));
     pl.splits = (int)std::max<int64_t>(splits, 1);
@@ -177,6 +180,7 @@ Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
     pl.off_queue = off, off += 256;
     pl.off_status = off, off += 256;
     pl.off_sun = off, off += align_up((size_t)std::max<int64_t>(P * H, 1) * sizeof(SunConst));
+    pl.off_ftheta = off, off += align_up((size_t)e->R * sizeof(double));
     pl.off_vis = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(int));
     pl.off_entry = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(Entry));
     pl.off_exact = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(Exact));
@@ -205,7 +209,8 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
     RenderParams rp;
     memset(&rp, 0, sizeof rp);
     rp.tri_planes = w->d_planes, rp.tri_rgb = w->d_rgb, rp.T = (int)w->T, rp.horizon = w->horizon;
-    rp.eye_py = e->d_py, rp.eye_quat = e->d_quat, rp.eye_w = e->d_w;
+    rp.eye_py = e->d_py, rp.eye_quat = e->d_quat, rp.eye_w = e->d_w, rp.eye_trig = e->d_trig;
+    rp.eye_ftheta = (const double*)(base + pl.off_ftheta);
     rp.N = (int)e->N, rp.S = e->S, rp.R = (int)e->R;
     rp.P = (int)P, rp.H = (int)H;
     rp.pos = pos, rp.yaw = yaw, rp.vquat = vquat, rp.init_c = init_c;
@@ -225,14 +230,20 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
         sun_setup_kernel<<<(n + 127) / 128, 128, 0, st>>>(sun, n, sp, (SunConst*)(base + pl.off_sun));
         g_launches++;
         CUDA_TRY(cudaGetLastError());
+        if (!vquat) {
+            eye_sky_kernel<<<(unsigned)((e->R + 255) / 256), 256, 0, st>>>(e->d_py, e->d_trig, (int)e->R, sp,
+                                                                         (double*)(base + pl.off_ftheta));
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
     }
-    size_t smem = (size_t)kSmemEntries * sizeof(Entry);
+    size_t smem = sizeof(SmemLayout);
     if (flags & ISY_FLAG_OUT_F64) {
-        CUDA_TRY(cudaFuncSetAttribute(render_brute_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        render_brute_kernel<true><<<pl.grid, kThreads, smem, st>>>(rp);
+        CUDA_TRY(cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        render_kernel<true><<<pl.grid, kThreads, smem, st>>>(rp);
     } else {
-        CUDA_TRY(cudaFuncSetAttribute(render_brute_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        render_brute_kernel<false><<<pl.grid, kThreads, smem, st>>>(rp);
+        CUDA_TRY(cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        render_kernel<false><<<pl.grid, kThreads, smem, st>>>(rp);
     }
     g_launches++;
     CUDA_TRY(cudaGetLastError());

@@ -65,6 +65,8 @@ struct RenderParams {
     double horizon;
     // eye
     const double* eye_py;    // [R][2] eye-frame (pitch, yaw)
+    const double* eye_trig;  // [R][4] sin pitch, cos pitch, sin yaw, cos yaw (eye frame)
+    const double* eye_ftheta;// [R]    Perez gradation f(theta) of each eye ray for this call's sky (workspace)
     const double* eye_quat;  // [R][4]
     const float* eye_w;      // [R]
     int N, S, R;
@@ -186,14 +188,16 @@ __device__ __forceinline__ double perez_phi(double chi, double cos_chi, double C
 }
 
 // Sky.__call__ for one direction (sky.py:304-334); d = unit view direction, theta = zenith angle
+// f_theta = perez_f(cos theta, theta < pi/2) is passed in: it depends on the elevation only and is
+// tabulated per eye ray for yaw-only views.
 __device__ __forceinline__ void sky_eval(const isy_sky_params& sp, const SunConst& sc, double dx, double dy, double dz,
-                                         double theta, double& Y, double& P, double& A, bool masked = false) {
+                                         double theta, double f_theta, double& Y, double& P, double& A,
+                                         bool masked = false) {
     double cg = dz * sc.sz + (dx * sc.sx + dy * sc.sy);      // cos(gamma), sky.py:304-305
     cg = fmin(fmax(cg, -1.0), 1.0);
     double gamma = acos(cg);
     double cos_t = dz;
-    double f = perez_f(cos_t, theta < kHalfPi, sp.A, sp.B);
-    double i_prez = f * perez_phi(gamma, cg, sp.C, sp.D, sp.E);                 // sky.py:308
+    double i_prez = f_theta * perez_phi(gamma, cg, sp.C, sp.D, sp.E);           // sky.py:308
     double i = (1.0 / (i_prez + kEps) - 1.0 / (sc.i00 + kEps)) * sc.K;          // sky.py:312
     Y = fmax(sc.Yz * i_prez / (sc.i00 + kEps), 0.0);                            // sky.py:313
     double lp = fmax(1.0 - cg * cg, 0.0) / (1.0 + cg * cg);                     // sky.py:316

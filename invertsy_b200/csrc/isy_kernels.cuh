@@ -1,24 +1,45 @@
 // Kernels of the sm_100a view renderer (persistent, one CTA per position work item).
 //
 //   phase A1  cull      : min-vertex distance of every world triangle to the eye, fp64,
-//                         reference order (world.py:94-98)                       -> slab_vis
+//                         reference order (world.py:94-98)                      -> visible list
 //   phase A2  project   : vertex (theta, phi) by atan2, seam rule, reference crosses,
-//                         normalised fp32 edge functions (world.py:109-120, 482-526) -> slab
-//   phase B   rays      : every ray of every orientation at this position against the entry
-//                         tile staged in shared memory; fp32 filter + exact fp64 re-check near
+//                         normalised fp32 edge functions (world.py:109-120, 482-526)
+//                                                                -> entry tile in shared memory
+//   phase A3  bin       : conservative rasterisation of the projected copies into a
+//                         (theta, phi) grid over the vegetation band (count / scan / fill)
+//   phase B   rays      : every ray of every orientation at this position looks up its bin and
+//                         tests only that bin's copies: fp32 filter + exact fp64 re-check near
 //                         edges; argmin of distance over containing copies == the painter's
 //                         far->near overwrite (world.py:106-123); ground / background rule
 //                         (world.py:79-90); analytic sky per ray (sky.py:304-334); cone
 //                         average over the S samples of an ommatidium; ONE write of the view.
+//
+// ISY_FLAG_BRUTE_FORCE (and any position whose copies do not fit the shared-memory budget)
+// skips A3 and streams every copy past every ray instead; results are identical.
 #pragma once
 #include "isy_common.cuh"
 
 namespace isy {
 
-constexpr int kThreads = 512;        // CTA size
-constexpr int kRPT = 4;              // rays per thread per pass (register-blocked against the smem tile)
-constexpr int kPassRays = kThreads * kRPT;
-constexpr int kSmemEntries = 1536;   // entries per shared-memory tile (72 KB)
+constexpr int kThreads = 512;         // CTA size (16 warps), one persistent CTA per SM
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxE = 1280;           // projected copies resident in shared memory (60 KB)
+constexpr int kBinRows = 32;          // finest angular grid over the vegetation band
+constexpr int kBinCols = 128;         // ... and over azimuth [-pi, pi]
+constexpr int kBins = kBinRows * kBinCols;
+constexpr int kListCap = 24576;       // candidate list entries (u16, 48 KB)
+constexpr int kMaxH = 128;            // headings whose sin/cos are cached per position
+constexpr float kBinMargin = 1e-4f;   // rad; >> every fp32 rounding in the bin arithmetic
+constexpr float kBinReject = -1e-5f;  // a bin is dropped only if an edge function is below this on all of it
+
+struct SmemLayout {
+    Entry tile[kMaxE];
+    float4 bbox[kMaxE];               // (theta_lo, theta_hi, phi_lo, phi_hi) of each copy, margin included
+    unsigned int bin_off[kBins + 4];  // exclusive offsets into list (counts during the count pass)
+    unsigned int bin_cur[kBins];      // fill cursors
+    unsigned short list[kListCap];
+    double head_sin[kMaxH], head_cos[kMaxH];
+};
 
 struct RayOut {
     double r, g, b;
@@ -30,8 +51,9 @@ __device__ __forceinline__ void store_val(void* base, size_t idx, double v) {
     reinterpret_cast<T*>(base)[idx] = (T)v;
 }
 
-// eye-frame (pitch, yaw) from the ommatidia quaternions, once per eye
-__global__ void eye_setup_kernel(const double* __restrict__ quat, double* __restrict__ py, int R) {
+// eye-frame (pitch, yaw) and their sines / cosines from the ommatidia quaternions, once per eye
+__global__ void eye_setup_kernel(const double* __restrict__ quat, double* __restrict__ py, double* __restrict__ trig,
+                                 int R) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     double dx, dy, dz, p, y;
@@ -39,6 +61,20 @@ __global__ void eye_setup_kernel(const double* __restrict__ quat, double* __rest
     dir_pitch_yaw(dx, dy, dz, p, y);
     py[2 * r + 0] = p;
     py[2 * r + 1] = y;
+    double s, c;
+    sincos(p, &s, &c);
+    trig[4 * r + 0] = s, trig[4 * r + 1] = c;
+    sincos(y, &s, &c);
+    trig[4 * r + 2] = s, trig[4 * r + 3] = c;
+}
+
+// gradation term f(theta) of the Perez function per eye ray (depends on pitch only for yaw-only views)
+__global__ void eye_sky_kernel(const double* __restrict__ py, const double* __restrict__ trig, int R,
+                               isy_sky_params sp, double* __restrict__ f_theta) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    double theta = py[2 * r] + kHalfPi;
+    f_theta[r] = perez_f(-trig[4 * r + 0], theta < kHalfPi, sp.A, sp.B);   // cos(theta) = -sin(pitch)
 }
 
 // per-view sun constants (sky.py:309-312, 320-321, 501-521)
@@ -67,7 +103,8 @@ __global__ void sun_setup_kernel(const double* __restrict__ sun, int n, isy_sky_
 }
 
 // ------------------------------------------------------------------------------------------
-// phase A: cull + project one position into this CTA's slab. Returns the entry count.
+// phase A: cull + project one position. Entries go to the CTA's slab (always) and to the
+// shared-memory tile (first kMaxE). Returns the number of copies E.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void load_vertices(const float* __restrict__ planes, int T, int t, double px, double py,
                                               double pz, double v[3][3]) {
@@ -79,8 +116,31 @@ __device__ __forceinline__ void load_vertices(const float* __restrict__ planes, 
     }
 }
 
-__device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* entries, Exact* exacts, int* s_count,
-                                int* s_nent) {
+__device__ __forceinline__ int float_key(float f) {   // order-preserving int key for atomicMin/Max
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__device__ __forceinline__ void emit_copy(const double th[3], const double ph[3], double dist, int t, int slot,
+                                          Entry* entries, Exact* exacts, SmemLayout& sm, int* s_band) {
+    Entry e;
+    finish_copy(th, ph, dist, t, e, exacts[slot]);
+    entries[slot] = e;
+    if (slot < kMaxE) {
+        sm.tile[slot] = e;
+        float tlo = (float)fmin(th[0], fmin(th[1], th[2])) - kBinMargin;
+        float thi = (float)fmax(th[0], fmax(th[1], th[2])) + kBinMargin;
+        float plo = (float)fmin(ph[0], fmin(ph[1], ph[2])) - kBinMargin;
+        float phi = (float)fmax(ph[0], fmax(ph[1], ph[2])) + kBinMargin;
+        sm.bbox[slot] = make_float4(tlo, thi, plo, phi);
+        atomicMin(&s_band[0], float_key(tlo));
+        atomicMax(&s_band[1], float_key(thi));
+    }
+}
+
+__device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* entries, Exact* exacts,
+                                SmemLayout& sm, int* s_count, int* s_nent, int* s_band) {
     const int tid = threadIdx.x, lane = tid & 31;
     const double px = rp.pos[3 * p + 0], py = rp.pos[3 * p + 1], pz = rp.pos[3 * p + 2];
     const double h = rp.horizon;
@@ -89,6 +149,8 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
     if (tid == 0) {
         *s_count = 0;
         *s_nent = 0;
+        s_band[0] = float_key(CUDART_INF_F);
+        s_band[1] = float_key(-CUDART_INF_F);
     }
     __syncthreads();
 
@@ -152,10 +214,10 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
                     p1[k] = ph[k] < 0 ? ph[k] + kTwoPi : ph[k];                           // :118
                     p2[k] = ph[k] > 0 ? ph[k] - kTwoPi : ph[k];                           // :119
                 }
-                finish_copy(th, p1, dist, t, entries[slot], exacts[slot]);
-                finish_copy(th, p2, dist, t, entries[slot + 1], exacts[slot + 1]);
+                emit_copy(th, p1, dist, t, slot, entries, exacts, sm, s_band);
+                emit_copy(th, p2, dist, t, slot + 1, entries, exacts, sm, s_band);
             } else {
-                finish_copy(th, ph, dist, t, entries[slot], exacts[slot]);
+                emit_copy(th, ph, dist, t, slot, entries, exacts, sm, s_band);
             }
         }
     }
@@ -169,6 +231,119 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
 }
 
 // ------------------------------------------------------------------------------------------
+// phase A3: angular bins
+// ------------------------------------------------------------------------------------------
+struct BinGrid {
+    float th_lo, th_hi, inv_dth, dth;
+    float inv_dph, dph;
+    int rows, cols;
+};
+
+__device__ __forceinline__ bool bin_accepts(const Entry& e, float t0, float t1, float p0, float p1) {
+    // largest value of each edge function on the rectangle [t0,t1] x [p0,p1]
+    float m0 = fmaf(e.A0, e.A0 > 0.f ? t1 : t0, fmaf(e.B0, e.B0 > 0.f ? p1 : p0, e.C0));
+    float m1 = fmaf(e.A1, e.A1 > 0.f ? t1 : t0, fmaf(e.B1, e.B1 > 0.f ? p1 : p0, e.C1));
+    float m2 = fmaf(e.A2, e.A2 > 0.f ? t1 : t0, fmaf(e.B2, e.B2 > 0.f ? p1 : p0, e.C2));
+    return fminf(m0, fminf(m1, m2)) >= kBinReject;
+}
+
+// one warp per copy, lanes over the bins of its bounding box; kFill = false counts, true fills
+template <bool kFill>
+__device__ __forceinline__ void bin_pass(SmemLayout& sm, const BinGrid& g, int E) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = warp; e < E; e += kWarps) {
+        const float4 bb = sm.bbox[e];
+        int r0 = max((int)floorf((bb.x - g.th_lo) * g.inv_dth), 0);
+        int r1 = min((int)floorf((bb.y - g.th_lo) * g.inv_dth), g.rows - 1);
+        int c0 = max((int)floorf((bb.z + (float)kPi) * g.inv_dph), 0);
+        int c1 = min((int)floorf((bb.w + (float)kPi) * g.inv_dph), g.cols - 1);
+        if (r0 > r1 || c0 > c1) continue;
+        const Entry ent = sm.tile[e];
+        const int w = c1 - c0 + 1, n = (r1 - r0 + 1) * w;
+        for (int i = lane; i < n; i += 32) {
+            int r = r0 + i / w, c = c0 + i % w;
+            float t0 = g.th_lo + r * g.dth - kBinMargin, t1 = g.th_lo + (r + 1) * g.dth + kBinMargin;
+            float p0 = -(float)kPi + c * g.dph - kBinMargin, p1 = -(float)kPi + (c + 1) * g.dph + kBinMargin;
+            if (!bin_accepts(ent, t0, t1, p0, p1)) continue;
+            int b = r * g.cols + c;
+            if (kFill) {
+                unsigned pos = atomicAdd(&sm.bin_cur[b], 1u);
+                sm.list[pos] = (unsigned short)e;
+            } else {
+                atomicAdd(&sm.bin_off[b], 1u);
+            }
+        }
+    }
+}
+
+// exclusive scan of bin_off[0..nb) in place (nb multiple of kThreads); returns the total
+__device__ unsigned int block_scan_bins(SmemLayout& sm, int nb, unsigned int* s_warp) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = nb / kThreads;     // 8 (fine) or 2 (coarse)
+    unsigned int local[kBins / kThreads];
+    unsigned int sum = 0;
+    for (int i = 0; i < per; ++i) {
+        local[i] = sm.bin_off[tid * per + i];
+        sum += local[i];
+    }
+    unsigned int inc = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned int wbase = 0, total = 0;
+    for (int w = 0; w < kWarps; ++w) {
+        unsigned int v = s_warp[w];
+        if (w < warp) wbase += v;
+        total += v;
+    }
+    unsigned int run = wbase + inc - sum;
+    for (int i = 0; i < per; ++i) {
+        sm.bin_off[tid * per + i] = run;
+        sm.bin_cur[tid * per + i] = run;
+        run += local[i];
+    }
+    if (tid == kThreads - 1) sm.bin_off[nb] = run;
+    __syncthreads();
+    return total;
+}
+
+// builds the bins for the E copies in sm.tile; false if they do not fit the list budget
+__device__ bool build_bins(SmemLayout& sm, BinGrid& g, int E, const int* s_band, unsigned int* s_warp) {
+    g.th_lo = key_float(s_band[0]);
+    g.th_hi = key_float(s_band[1]);
+    if (!(g.th_hi > g.th_lo)) {   // no copies: an empty single-row grid
+        g.th_lo = 0.f, g.th_hi = 0.f;
+    }
+    g.th_lo = fmaxf(g.th_lo, -(float)kHalfPi - 1e-3f);
+    g.th_hi = fminf(g.th_hi, (float)kHalfPi + 1e-3f);
+    for (int level = 0; level < 2; ++level) {
+        g.rows = kBinRows >> level;
+        g.cols = kBinCols >> level;
+        float span = fmaxf(g.th_hi - g.th_lo, 1e-3f);
+        g.dth = span / g.rows;
+        g.inv_dth = g.rows / span;
+        g.dph = (float)kTwoPi / g.cols;
+        g.inv_dph = g.cols / (float)kTwoPi;
+        const int nb = g.rows * g.cols;
+        for (int i = threadIdx.x; i < nb; i += kThreads) sm.bin_off[i] = 0;
+        __syncthreads();
+        bin_pass<false>(sm, g, E);
+        __syncthreads();
+        unsigned int total = block_scan_bins(sm, nb, s_warp);
+        if (total <= (unsigned)kListCap) {
+            bin_pass<true>(sm, g, E);
+            __syncthreads();
+            return true;
+        }
+        __syncthreads();
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------
 // phase B helpers
 // ------------------------------------------------------------------------------------------
 struct Ray {
@@ -178,28 +353,21 @@ struct Ray {
     int hit;
 };
 
-__device__ __forceinline__ void test_tile(Ray (&ray)[kRPT], const Entry* __restrict__ tile, int n,
-                                          const Exact* __restrict__ exacts) {
-#pragma unroll 2
-    for (int j = 0; j < n; ++j) {
-        const float4 a = reinterpret_cast<const float4*>(tile + j)[0];
-        const float4 b = reinterpret_cast<const float4*>(tile + j)[1];
-        const float4 c = reinterpret_cast<const float4*>(tile + j)[2];
-#pragma unroll
-        for (int k = 0; k < kRPT; ++k) {
-            float e0 = fmaf(a.x, ray[k].fp, fmaf(a.y, ray[k].fy, a.z));
-            float e1 = fmaf(a.w, ray[k].fp, fmaf(b.x, ray[k].fy, b.y));
-            float e2 = fmaf(b.z, ray[k].fp, fmaf(b.w, ray[k].fy, c.x));
-            float m = fminf(e0, fminf(e1, e2));
-            if (m >= -kEdgeEps) {   // rare: inside, or within the rounding band of an edge
-                double dist = __hiloint2double(__float_as_int(c.w), __float_as_int(c.z));
-                int tri = __float_as_int(c.y);
-                bool closer = dist < ray[k].best || (dist == ray[k].best && tri < ray[k].hit);
-                if (closer && (m > kEdgeEps || inside_exact(exacts[j], ray[k].pitch, ray[k].yaw))) {
-                    ray[k].best = dist;
-                    ray[k].hit = tri;
-                }
-            }
+__device__ __forceinline__ void test_entry(Ray& ray, const Entry* __restrict__ ent, const Exact* __restrict__ exact) {
+    const float4 a = reinterpret_cast<const float4*>(ent)[0];
+    const float4 b = reinterpret_cast<const float4*>(ent)[1];
+    const float4 c = reinterpret_cast<const float4*>(ent)[2];
+    float e0 = fmaf(a.x, ray.fp, fmaf(a.y, ray.fy, a.z));
+    float e1 = fmaf(a.w, ray.fp, fmaf(b.x, ray.fy, b.y));
+    float e2 = fmaf(b.z, ray.fp, fmaf(b.w, ray.fy, c.x));
+    float m = fminf(e0, fminf(e1, e2));
+    if (m >= -kEdgeEps) {   // inside, or within the rounding band of an edge
+        double dist = __hiloint2double(__float_as_int(c.w), __float_as_int(c.z));
+        int tri = __float_as_int(c.y);
+        bool closer = dist < ray.best || (dist == ray.best && tri < ray.hit);
+        if (closer && (m > kEdgeEps || inside_exact(*exact, ray.pitch, ray.yaw))) {
+            ray.best = dist;
+            ray.hit = tri;
         }
     }
 }
@@ -248,22 +416,24 @@ __device__ __forceinline__ void write_view(const RenderParams& rp, size_t b, int
 }
 
 // ------------------------------------------------------------------------------------------
-// the render kernel (brute-force variant: every ray against every visible copy)
+// the render kernel
 // ------------------------------------------------------------------------------------------
 template <bool kF64>
-__global__ void __launch_bounds__(kThreads, 1) render_brute_kernel(const RenderParams rp) {
+__global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams rp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Entry* tile = reinterpret_cast<Entry*>(smem_raw);
-    __shared__ int s_count, s_nent;
-    __shared__ unsigned int s_item;
+    SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
+    __shared__ int s_count, s_nent, s_band[2];
+    __shared__ unsigned int s_item, s_warp[kWarps];
 
     const int tid = threadIdx.x;
     int* vis = rp.slab_vis + (size_t)blockIdx.x * rp.slab_cap;
     Entry* entries = rp.slab_entry + (size_t)blockIdx.x * rp.slab_cap;
     Exact* exacts = rp.slab_exact + (size_t)blockIdx.x * rp.slab_cap;
     const int raysPerPos = rp.H * rp.R;
+    const int raysPadded = (raysPerPos + kThreads - 1) / kThreads * kThreads;
     const bool want_sky = rp.sky.kind != ISY_SKY_NONE;
     const bool perez = rp.sky.kind == ISY_SKY_PEREZ;
+    const bool cache_heads = !rp.vquat && rp.yaw && perez && rp.H <= kMaxH;
 
     for (;;) {
         __syncthreads();
@@ -273,111 +443,107 @@ __global__ void __launch_bounds__(kThreads, 1) render_brute_kernel(const RenderP
         if (item >= (unsigned)rp.items) break;
         const int p = item / rp.splits, split = item % rp.splits;
 
-        const int E = cull_and_project(rp, p, vis, entries, exacts, &s_count, &s_nent);
-        const int nchunks = (E + kSmemEntries - 1) / kSmemEntries;
-        if (nchunks <= 1) {
-            // common case: the whole projected world of this position lives in shared memory
-            const float4* src = reinterpret_cast<const float4*>(entries);
-            float4* dst = reinterpret_cast<float4*>(tile);
-            for (int i = tid; i < E * 3; i += kThreads) dst[i] = src[i];
-            __syncthreads();
-        }
+        if (cache_heads && tid < rp.H) sincos(rp.yaw[(size_t)p * rp.H + tid], &sm.head_sin[tid], &sm.head_cos[tid]);
+        const int E = cull_and_project(rp, p, vis, entries, exacts, sm, &s_count, &s_nent, s_band);
+        BinGrid grid;
+        bool binned = false;
+        if (!(rp.flags & ISY_FLAG_BRUTE_FORCE) && E <= kMaxE) binned = build_bins(sm, grid, E, s_band, s_warp);
+        const int nchunks = binned ? 1 : (E + kMaxE - 1) / kMaxE;
 
-        for (int pass = split * kPassRays; pass < raysPerPos; pass += rp.splits * kPassRays) {
-            Ray ray[kRPT];
-            int rr[kRPT], hh[kRPT];
-            double ddx[kRPT], ddy[kRPT], ddz[kRPT];
-#pragma unroll
-            for (int k = 0; k < kRPT; ++k) {
-                int g = pass + k * kThreads + tid;
-                bool valid = g < raysPerPos;
-                int gg = valid ? g : 0;
-                int h = gg / rp.R, r = gg - h * rp.R;
-                rr[k] = valid ? r : -1;
-                hh[k] = h;
-                size_t b = (size_t)p * rp.H + h;
-                double pitch, yaw, dx = 0, dy = 0, dz = 0;
-                if (rp.vquat) {
-                    const double* qv = rp.vquat + 4 * b;
-                    const double* qo = rp.eye_quat + 4 * (size_t)r;
-                    double x1 = qv[0], y1 = qv[1], z1 = qv[2], w1 = qv[3];
-                    double x2 = qo[0], y2 = qo[1], z2 = qo[2], w2 = qo[3];
-                    double w = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2;
-                    double x = w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2;
-                    double y = w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2;
-                    double z = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2;
-                    quat_dir(x, y, z, w, dx, dy, dz);
-                    dir_pitch_yaw(dx, dy, dz, pitch, yaw);
-                } else {
-                    pitch = rp.eye_py[2 * (size_t)r + 0];
-                    yaw = wrap_yaw(rp.eye_py[2 * (size_t)r + 1] + (rp.yaw ? rp.yaw[b] : 0.0));
-                    if (perez) {
-                        double sp_, cp, sy, cy;
-                        sincos(pitch, &sp_, &cp);
-                        sincos(yaw, &sy, &cy);
-                        dx = cp * cy, dy = cp * sy, dz = -sp_;
+        for (int g0 = split * kThreads; g0 < raysPadded; g0 += rp.splits * kThreads) {
+            const int g = g0 + tid;
+            const bool valid = g < raysPerPos;
+            const int gg = valid ? g : 0;
+            const int h = gg / rp.R, r = gg - h * rp.R;
+            const size_t b = (size_t)p * rp.H + h;
+            Ray ray;
+            double dx = 0, dy = 0, dz = 0, f_theta = 0;
+            if (rp.vquat) {
+                const double* qv = rp.vquat + 4 * b;
+                const double* qo = rp.eye_quat + 4 * (size_t)r;
+                double x1 = qv[0], y1 = qv[1], z1 = qv[2], w1 = qv[3];
+                double x2 = qo[0], y2 = qo[1], z2 = qo[2], w2 = qo[3];
+                double w = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2;
+                double x = w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2;
+                double y = w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2;
+                double z = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2;
+                quat_dir(x, y, z, w, dx, dy, dz);
+                dir_pitch_yaw(dx, dy, dz, ray.pitch, ray.yaw);
+                if (perez) f_theta = perez_f(dz, ray.pitch + kHalfPi < kHalfPi, rp.sky.A, rp.sky.B);
+            } else {
+                const double heading = rp.yaw ? rp.yaw[b] : 0.0;
+                ray.pitch = rp.eye_py[2 * (size_t)r + 0];
+                ray.yaw = wrap_yaw(rp.eye_py[2 * (size_t)r + 1] + heading);
+                if (perez) {
+                    const double4 t4 = *reinterpret_cast<const double4*>(rp.eye_trig + 4 * (size_t)r);
+                    double hs, hc;
+                    if (cache_heads) {
+                        hs = sm.head_sin[h], hc = sm.head_cos[h];
+                    } else {
+                        sincos(heading, &hs, &hc);
+                    }
+                    // sin/cos(yaw_e + heading) by the addition formulas
+                    double sy = t4.z * hc + t4.w * hs, cy = t4.w * hc - t4.z * hs;
+                    dx = t4.y * cy, dy = t4.y * sy, dz = -t4.x;
+                    f_theta = rp.eye_ftheta[r];
+                }
+            }
+            ray.fp = (float)ray.pitch;
+            ray.fy = (float)ray.yaw;
+            ray.best = CUDART_INF;
+            ray.hit = -1;
+
+            if (binned) {
+                if (ray.fp >= grid.th_lo && ray.fp <= grid.th_hi) {
+                    int row = min((int)((ray.fp - grid.th_lo) * grid.inv_dth), grid.rows - 1);
+                    int col = min(max((int)((ray.fy + (float)kPi) * grid.inv_dph), 0), grid.cols - 1);
+                    int bin = row * grid.cols + col;
+                    unsigned i0 = sm.bin_off[bin], i1 = sm.bin_off[bin + 1];
+                    for (unsigned i = i0; i < i1; ++i) {
+                        int e = sm.list[i];
+                        test_entry(ray, &sm.tile[e], &exacts[e]);
                     }
                 }
-                ddx[k] = dx, ddy[k] = dy, ddz[k] = dz;
-                ray[k].pitch = pitch;
-                ray[k].yaw = yaw;
-                ray[k].fp = (float)pitch;
-                ray[k].fy = (float)yaw;
-                ray[k].best = CUDART_INF;
-                ray[k].hit = -1;
-            }
-
-            if (nchunks <= 1) {
-                test_tile(ray, tile, E, exacts);
             } else {
                 for (int c = 0; c < nchunks; ++c) {
-                    int n = min(kSmemEntries, E - c * kSmemEntries);
-                    __syncthreads();
-                    const float4* src = reinterpret_cast<const float4*>(entries + (size_t)c * kSmemEntries);
-                    float4* dst = reinterpret_cast<float4*>(tile);
-                    for (int i = tid; i < n * 3; i += kThreads) dst[i] = src[i];
-                    __syncthreads();
-                    test_tile(ray, tile, n, exacts + (size_t)c * kSmemEntries);
+                    int n = min(kMaxE, E - c * kMaxE);
+                    if (nchunks > 1) {   // (a single chunk is already resident: emit_copy filled sm.tile)
+                        __syncthreads();
+                        const float4* src = reinterpret_cast<const float4*>(entries + (size_t)c * kMaxE);
+                        float4* dst = reinterpret_cast<float4*>(sm.tile);
+                        for (int i = tid; i < n * 3; i += kThreads) dst[i] = src[i];
+                        __syncthreads();
+                    }
+                    for (int j = 0; j < n; ++j) test_entry(ray, &sm.tile[j], &exacts[(size_t)c * kMaxE + j]);
                 }
             }
 
-#pragma unroll
-            for (int k = 0; k < kRPT; ++k) {
-                const bool valid = rr[k] >= 0;
-                const int r = valid ? rr[k] : 0;
-                const size_t b = (size_t)p * rp.H + hh[k];
-                RayOut o;
-                o.Y = 0, o.P = 0, o.A = CUDART_NAN;
-                if (perez) {
-                    const SunConst sc = rp.sun[rp.sun_per_view ? b : 0];
-                    sky_eval(rp.sky, sc, ddx[k], ddy[k], ddz[k], ray[k].pitch + kHalfPi, o.Y, o.P, o.A);
-                } else if (want_sky) {
-                    o.Y = rp.sky.luminance;   // UniformSky: y = luminance, p = 0, a = nan (sky.py:77-79)
-                }
-                // world colour (world.py:79-90, :123)
-                double r_ = CUDART_NAN, g_ = CUDART_NAN, b_ = CUDART_NAN;
-                const bool from_sky = (rp.flags & ISY_FLAG_INIT_FROM_SKY) && want_sky;
-                if (rp.init_c || from_sky) {
-                    double lum = rp.init_c ? rp.init_c[b * (size_t)rp.R + r] : o.Y;
-                    r_ = fmin(fmax(19.0 * lum + 13.0, 0.0), 255.0);      // luminance2skycolour, world.py:479
-                    g_ = fmin(fmax(19.0 * lum + 135.0, 0.0), 255.0);
-                    b_ = fmin(fmax(19.0 * lum + 201.0, 0.0), 255.0);
-                }
-                if (ray[k].pitch >= 0) r_ = 229.0 / 255.0, g_ = 183.0 / 255.0, b_ = 90.0 / 255.0;   // :90
-                if (ray[k].hit >= 0) {
-                    const float* col = rp.tri_rgb + 3 * (size_t)ray[k].hit;
-                    r_ = __ldg(col + 0), g_ = __ldg(col + 1), b_ = __ldg(col + 2);
-                }
-                o.r = r_, o.g = g_, o.b = b_;
-                write_view<kF64>(rp, b, r, valid, ray[k].hit, ray[k].best, o);
+            RayOut o;
+            o.Y = 0, o.P = 0, o.A = CUDART_NAN;
+            if (perez) {
+                const SunConst sc = rp.sun[rp.sun_per_view ? b : 0];
+                sky_eval(rp.sky, sc, dx, dy, dz, ray.pitch + kHalfPi, f_theta, o.Y, o.P, o.A);
+            } else if (want_sky) {
+                o.Y = rp.sky.luminance;   // UniformSky: y = luminance, p = 0, a = nan (sky.py:77-79)
             }
+            // world colour (world.py:79-90, :123)
+            o.r = CUDART_NAN, o.g = CUDART_NAN, o.b = CUDART_NAN;
+            const bool from_sky = (rp.flags & ISY_FLAG_INIT_FROM_SKY) && want_sky;
+            if (rp.init_c || from_sky) {
+                double lum = rp.init_c ? rp.init_c[b * (size_t)rp.R + r] : o.Y;
+                o.r = fmin(fmax(19.0 * lum + 13.0, 0.0), 255.0);      // luminance2skycolour, world.py:479
+                o.g = fmin(fmax(19.0 * lum + 135.0, 0.0), 255.0);
+                o.b = fmin(fmax(19.0 * lum + 201.0, 0.0), 255.0);
+            }
+            if (ray.pitch >= 0) o.r = 229.0 / 255.0, o.g = 183.0 / 255.0, o.b = 90.0 / 255.0;   // :90
+            if (ray.hit >= 0) {
+                const float* col = rp.tri_rgb + 3 * (size_t)ray.hit;
+                o.r = __ldg(col + 0), o.g = __ldg(col + 1), o.b = __ldg(col + 2);
+            }
+            write_view<kF64>(rp, b, r, valid, ray.hit, ray.best, o);
         }
     }
 }
-
-}  // namespace isy
-
-namespace isy {
 
 // ------------------------------------------------------------------------------------------
 // Sky.__call__ / UniformSky.__call__ on explicit ray orientations (sky.py:99-113, 269-334)
@@ -397,7 +563,10 @@ __global__ void sky_dirs_kernel(const double* __restrict__ quat, int64_t n, isy_
     if (phi_out) phi_out[i] = phi;
     const bool masked = eta && eta[i];
     double y = masked ? 0.0 : sp.luminance, p = 0.0, a = CUDART_NAN;   // UniformSky: sky.py:77-84
-    if (sp.kind == ISY_SKY_PEREZ) sky_eval(sp, sun[0], dx, dy, dz, theta, y, p, a, masked);
+    if (sp.kind == ISY_SKY_PEREZ) {
+        double f_theta = perez_f(dz, theta < kHalfPi, sp.A, sp.B);
+        sky_eval(sp, sun[0], dx, dy, dz, theta, f_theta, y, p, a, masked);
+    }
     Y[i] = y, P[i] = p, A[i] = a;
 }
 

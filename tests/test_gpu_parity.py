@@ -260,3 +260,41 @@ def test_empty_world_and_determinism(ib, sparse, omm1000):
     ground = (np.array(o.GROUND_COLOUR) / 255.).astype(np.float32)
     assert np.array_equal(a["rgb"][0][pitch >= 0], np.tile(ground, ((pitch >= 0).sum(), 1)))
     assert np.all(np.isnan(a["rgb"][0][pitch < 0]))
+
+
+def test_binned_equals_brute_force(ib, seville, sparse, omm1000):
+    """the angular bins only skip work: every output equals the test-everything path bit for bit"""
+    rng = np.random.RandomState(23)
+    pitch, yaw = o.fibonacci_eye(4000)
+    eye = ib.EyeLayout.from_angles(pitch, yaw)
+    for world in (seville, sparse):
+        r = ib.Renderer(world, eye, sky=ib.Sky(0.9, 0.3))
+        P, H = 40, 5
+        pos = np.c_[rng.uniform(0, 10, P), rng.uniform(0, 10, P), np.full(P, 0.01)]
+        yaw_rad = rng.uniform(-np.pi, np.pi, (P, H))
+        names = ("rgb", "hit", "depth", "Y", "dop", "aop")
+        a = _render_np(r, pos=pos, yaw=yaw_rad, outputs=names)
+        b = _render_np(r, pos=pos, yaw=yaw_rad, outputs=names, brute_force=True)
+        for n in names:
+            assert np.array_equal(a[n], b[n], equal_nan=True), n
+
+
+def test_dense_synthetic_world_overflows_the_tile_and_stays_exact(ib):
+    """more projected copies than the shared-memory tile holds -> chunked fallback, same answers"""
+    rng = np.random.RandomState(99)
+    T = 4000
+    base = np.c_[rng.uniform(4, 6, T), rng.uniform(4, 6, T), np.zeros(T)]
+    tri = np.stack([base + np.c_[rng.uniform(-.05, .05, T), rng.uniform(-.05, .05, T), np.zeros(T)],
+                    base + np.c_[rng.uniform(-.05, .05, T), rng.uniform(-.05, .05, T), np.zeros(T)],
+                    base + np.c_[rng.uniform(-.02, .02, T), rng.uniform(-.02, .02, T), rng.uniform(.05, .6, T)]],
+                   axis=1).astype(np.float32)
+    col = np.c_[np.zeros(T), rng.uniform(.1, .9, T), np.zeros(T)].astype(np.float32)
+    world = ib.WorldBase(tri, col, horizon=2.)
+    pitch, yaw = o.fibonacci_eye(3000)
+    r = ib.Renderer(world, ib.EyeLayout.from_angles(pitch, yaw))
+    pos = np.array([[5., 5., 0.01], [4.2, 5.7, 0.01], [9.5, 9.5, 0.01]])
+    yaw_rad = np.array([[0.3, -2.0], [1.0, 3.0], [0., 0.5]])
+    out = _render_np(r, pos=pos, yaw=yaw_rad, outputs=("hit",))
+    ref = _oracle_views(tri, pos, yaw_rad, pitch, yaw)
+    assert (out["hit"] != ref).sum() == 0
+    assert (ref[:2] >= 0).mean() > 0.2 and np.all(ref[4:] == -1)
