@@ -278,6 +278,9 @@ def main():
         elapsed_ms = float(t.item())
     value = world_size * B * args.steps / (elapsed_ms / 1e3)
 
+    pc = r.phase_cycles().astype(np.float64)
+    phase = {"project_frac": pc[0] / pc[:3].sum(), "bin_frac": pc[1] / pc[:3].sum(), "rays_frac": pc[2] / pc[:3].sum(),
+             "cycles_per_position": pc[:3].sum() / max(pc[3], 1)}
     # sanity on the last step's result (cheap, outside the timed region)
     hit_frac = float((out["hit"][: 36 * 64] >= 0).float().mean().item())
 
@@ -331,7 +334,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "views_per_step": int(Pe * H), "api": "Renderer.render_host -> isy_render_host"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "check": {"hit_fraction_first_rows": hit_frac}}
+                "check": {"hit_fraction_first_rows": hit_frac}, "phases": phase}
         print(json.dumps(line))
     if world_size > 1:
         dist.destroy_process_group()

@@ -127,6 +127,9 @@ int isy_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, const
 /* Synchronises `stream` and returns the sticky device-side status of the renders that used this
  * workspace (ISY_OK, or ISY_ERR_OVERFLOW when a position exceeded the slab).                    */
 int isy_workspace_status(void* workspace_dev, void* stream);
+/* Profiling aid: SM cycles summed over CTAs of the LAST render that used this workspace, spent in
+ * out4[0] cull+projection, out4[1] bin build, out4[2] ray phase; out4[3] = positions processed.  */
+int isy_workspace_phase_cycles(void* workspace_dev, void* stream, uint64_t* out4);
 
 /* Same call with HOST buffers: stages inputs H2D, renders, copies the selected outputs D2H in
  * chunks overlapped with compute (pinned staging owned by the library) and returns after the

@@ -19,7 +19,8 @@ EXPORTS = (
     "isy_abi_version", "isy_last_error", "isy_launch_count",
     "isy_world_create", "isy_world_destroy", "isy_world_triangles",
     "isy_eye_create", "isy_eye_destroy", "isy_eye_rays",
-    "isy_render_workspace_bytes", "isy_render", "isy_workspace_status", "isy_render_host",
+    "isy_render_workspace_bytes", "isy_render", "isy_workspace_status", "isy_workspace_phase_cycles",
+    "isy_render_host",
     "isy_world_call_host", "isy_sky_call_host", "isy_spectrum_influence_host",
 )
 
@@ -70,6 +71,8 @@ def lib():
     L.isy_render.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, ctypes.POINTER(SkyParams), ctypes.c_uint32,
                              ctypes.POINTER(Outputs), vp, ctypes.c_size_t, vp]
     L.isy_workspace_status.argtypes = [vp, vp]
+    L.isy_workspace_phase_cycles.argtypes = [vp, vp, vp]
+    L.isy_workspace_phase_cycles.restype = ctypes.c_int
     L.isy_render_host.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, ctypes.POINTER(SkyParams), ctypes.c_uint32,
                                   ctypes.POINTER(Outputs)]
     L.isy_world_call_host.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]

@@ -219,6 +219,7 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
     rp.sky = sp, rp.flags = flags, rp.out = *out;
     rp.queue = (unsigned int*)(base + pl.off_queue);
     rp.status = (int*)(base + pl.off_status);
+    rp.phase_cycles = (unsigned long long*)(base + pl.off_status + 64);
     rp.slab_vis = (int*)(base + pl.off_vis);
     rp.slab_entry = (Entry*)(base + pl.off_entry);
     rp.slab_exact = (Exact*)(base + pl.off_exact);
@@ -288,6 +289,14 @@ int isy_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, const
 }
 
 int isy_workspace_status(void* workspace_dev, void* stream) { return check_status(workspace_dev, (cudaStream_t)stream); }
+
+int isy_workspace_phase_cycles(void* workspace_dev, void* stream, uint64_t* out4) {
+    if (!workspace_dev || !out4) return fail(ISY_ERR_INVALID, "isy_workspace_phase_cycles: bad argument");
+    CUDA_TRY(cudaMemcpyAsync(out4, (unsigned char*)workspace_dev + 256 + 64, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return ISY_OK;
+}
 
 int isy_render_host(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, const double* pos_host,
                     const double* yaw_host, const double* view_quat_host, const double* sun_host,

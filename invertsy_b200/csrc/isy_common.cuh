@@ -53,6 +53,7 @@ struct SunConst {
     double i00;          // L(0, theta_s)                       sky.py:309
     double K;            // i_00 * i_90 / (i_00 - i_90 + eps)   sky.py:312 (grouped as written there)
     double i90;
+    double inv_i00;      // 1 / (i_00 + eps)
     double Yz;           // zenith luminance                    sky.py:501-510
     double Mp;           // max degree of polarisation          sky.py:513-521
 };
@@ -84,6 +85,7 @@ struct RenderParams {
     // workspace
     unsigned int* queue;     // dynamic work counter
     int* status;             // sticky error flag
+    unsigned long long* phase_cycles;  // [8] summed SM cycles per phase (thread 0 of every CTA), profiling aid
     int* slab_vis;           // [grid][slab_cap] visible triangle ids
     Entry* slab_entry;       // [grid][slab_cap]
     Exact* slab_exact;       // [grid][slab_cap]
@@ -152,17 +154,32 @@ __device__ __forceinline__ void finish_copy(const double th[3], const double ph[
 
 // wrap an angle to (-pi, pi] (the range of SciPy's as_euler yaw)
 __device__ __forceinline__ double wrap_yaw(double y) {
-    if (y > kPi || y <= -kPi) {
-        y = remainder(y, kTwoPi);  // [-pi, pi]
-        if (y <= -kPi) y += kTwoPi;
+    if (y > kPi) {
+        y -= kTwoPi;                               // exact for y in (pi, 3pi] (Sterbenz)
+        if (y > kPi) {                             // far out of range: rare, general path
+            y = remainder(y, kTwoPi);
+            if (y <= -kPi) y += kTwoPi;
+        }
+    } else if (y <= -kPi) {
+        y += kTwoPi;
+        if (y <= -kPi) {
+            y = remainder(y, kTwoPi);
+            if (y <= -kPi) y += kTwoPi;
+        }
     }
     return y;
 }
 
-// (a + pi) % (2 pi) - pi with NumPy's floored modulo (sky.py:105, :324): result in [-pi, pi)
+// (a + pi) % (2 pi) - pi with NumPy's floored modulo (sky.py:105, :324): result in [-pi, pi).
+// Callers pass a in (-3pi, 3pi), where the modulo is one conditional shift of the rounded sum.
 __device__ __forceinline__ double wrap_pi_numpy(double a) {
-    double m = fmod(a + kPi, kTwoPi);
-    if (m < 0) m += kTwoPi;
+    double m = a + kPi;
+    if (m >= kTwoPi) m -= kTwoPi;
+    else if (m < 0) m += kTwoPi;
+    if (m >= kTwoPi || m < 0) {                    // not reached for |a| < 3pi; keeps the function total
+        m = fmod(m, kTwoPi);
+        if (m < 0) m += kTwoPi;
+    }
     return m - kPi;
 }
 
@@ -187,23 +204,70 @@ __device__ __forceinline__ double perez_phi(double chi, double cos_chi, double C
     return 1.0 + C * exp(D * chi) + E * (cos_chi * cos_chi);
 }
 
-// Sky.__call__ for one direction (sky.py:304-334); d = unit view direction, theta = zenith angle
+// acos(c) to ~1e-12 for the sky's angular distance: float acosf seed + one Newton step on
+// f(g) = cos g - c with cos(seed) from an fp64 even polynomial (the seed is an exact fp32 value);
+// next to 0 and pi, where the step is ill-conditioned, the library acos is used.
+__device__ __forceinline__ double acos_newton(double c) {
+    const float cf = (float)c;
+    const float s0 = sqrtf(fmaxf(1.0f - cf * cf, 0.0f));
+    if (s0 < 0.06f) return acos(c);
+    const float g0 = acosf(cf);
+    double x = (double)g0;
+    const bool flip = x > kHalfPi;
+    if (flip) x = kPi - x;
+    const double x2 = x * x;
+    double q = -1.5619206968586226e-16;                 // -1/18!
+    q = fma(q, x2, 4.7794773323873853e-14);             //  1/16!
+    q = fma(q, x2, -1.1470745597729725e-11);            // -1/14!
+    q = fma(q, x2, 2.0876756987868099e-09);             //  1/12!
+    q = fma(q, x2, -2.7557319223985893e-07);            // -1/10!
+    q = fma(q, x2, 2.4801587301587302e-05);             //  1/8!
+    q = fma(q, x2, -1.3888888888888889e-03);            // -1/6!
+    q = fma(q, x2, 4.1666666666666664e-02);             //  1/4!
+    q = fma(q, x2, -0.5);
+    q = fma(q, x2, 1.0);                                // cos(x), |error| < 4e-15 on [0, pi/2]
+    const double cos_g0 = flip ? -q : q;
+    return (double)g0 + (cos_g0 - c) * (double)__frcp_rn(s0);
+}
+
+// Sky.__call__ for one direction (sky.py:304-334); d = unit view direction, theta = zenith angle.
 // f_theta = perez_f(cos theta, theta < pi/2) is passed in: it depends on the elevation only and is
 // tabulated per eye ray for yaw-only views.
+// kPrecise = true : every step in fp64 in the reference's order (double outputs, ~1e-13 of the reference)
+// kPrecise = false: float outputs. Luminance keeps the fp64 core (gamma, exp); the polarisation
+//                   finish (one atan2, two divisions) runs in fp32 on fp64-rounded operands, which
+//                   bounds the added error by ~1e-6 (DESIGN.md "sky error budget"), inside the 1e-5 bar.
+template <bool kPrecise>
 __device__ __forceinline__ void sky_eval(const isy_sky_params& sp, const SunConst& sc, double dx, double dy, double dz,
                                          double theta, double f_theta, double& Y, double& P, double& A,
                                          bool masked = false) {
     double cg = dz * sc.sz + (dx * sc.sx + dy * sc.sy);      // cos(gamma), sky.py:304-305
     cg = fmin(fmax(cg, -1.0), 1.0);
-    double gamma = acos(cg);
-    double cos_t = dz;
-    double i_prez = f_theta * perez_phi(gamma, cg, sp.C, sp.D, sp.E);           // sky.py:308
-    double i = (1.0 / (i_prez + kEps) - 1.0 / (sc.i00 + kEps)) * sc.K;          // sky.py:312
-    Y = fmax(sc.Yz * i_prez / (sc.i00 + kEps), 0.0);                            // sky.py:313
-    double lp = fmax(1.0 - cg * cg, 0.0) / (1.0 + cg * cg);                     // sky.py:316
-    double p = 2.0 / kPi * sc.Mp * lp * (theta * cos_t + (kHalfPi - theta) * i);  // sky.py:317
-    P = fmin(fmax(p, 0.0), 1.0);
-    A = wrap_pi_numpy(atan2(dy - sc.sy, dx - sc.sx) + kHalfPi);                 // sky.py:320-324
+    const double cos_t = dz;
+    double gamma;
+    if (kPrecise) {
+        gamma = acos(cg);
+        double i_prez = f_theta * perez_phi(gamma, cg, sp.C, sp.D, sp.E);           // sky.py:308
+        double i = (1.0 / (i_prez + kEps) - 1.0 / (sc.i00 + kEps)) * sc.K;          // sky.py:312
+        Y = fmax(sc.Yz * i_prez / (sc.i00 + kEps), 0.0);                            // sky.py:313
+        double lp = fmax(1.0 - cg * cg, 0.0) / (1.0 + cg * cg);                     // sky.py:316
+        double p = 2.0 / kPi * sc.Mp * lp * (theta * cos_t + (kHalfPi - theta) * i);  // sky.py:317
+        P = fmin(fmax(p, 0.0), 1.0);
+        A = wrap_pi_numpy(atan2(dy - sc.sy, dx - sc.sx) + kHalfPi);                 // sky.py:320-324
+    } else {
+        gamma = acos_newton(cg);
+        const double i_prez = f_theta * perez_phi(gamma, cg, sp.C, sp.D, sp.E);
+        Y = fmax(sc.Yz * i_prez * sc.inv_i00, 0.0);
+        const float cg2 = (float)(cg * cg);
+        const float lp = fmaxf(1.0f - cg2, 0.0f) / (1.0f + cg2);
+        const float i = (1.0f / ((float)i_prez + (float)kEps) - (float)sc.inv_i00) * (float)sc.K;
+        const float p = (float)(2.0 / kPi * sc.Mp) * lp *
+                        fmaf((float)(kHalfPi - theta), i, (float)(theta * cos_t));
+        P = (double)fminf(fmaxf(p, 0.0f), 1.0f);
+        float a = atan2f((float)(dy - sc.sy), (float)(dx - sc.sx)) + (float)kHalfPi;   // in (-pi/2, 3pi/2]
+        if (a >= (float)kPi) a -= (float)kTwoPi;
+        A = (double)a;
+    }
     if (masked) Y = 0.0, P = 0.0, A = CUDART_NAN;                               // sky.py:330-332 (eta)
     if (gamma < kPi / 60) Y = 17.0;                                             // sky.py:334
 }

@@ -96,6 +96,7 @@ __global__ void sun_setup_kernel(const double* __restrict__ sun, int n, isy_sky_
     double f90 = perez_f(cos(z90), z90 < kHalfPi, sp.A, sp.B);
     c.i90 = f90 * perez_phi(kHalfPi, cos(kHalfPi), sp.C, sp.D, sp.E);
     c.K = c.i00 * c.i90 / (c.i00 - c.i90 + kEps);
+    c.inv_i00 = 1.0 / (c.i00 + kEps);
     double chi = (4.0 / 9.0 - sp.tau_L / 120.0) * (kPi - 2 * (kHalfPi - ths));
     c.Yz = (4.0453 * sp.tau_L - 4.9710) * tan(chi) - 0.2155 * sp.tau_L + 2.4192;
     c.Mp = exp(-(sp.tau_L - sp.c1) / (sp.c2 + kEps));
@@ -260,8 +261,10 @@ __device__ __forceinline__ void bin_pass(SmemLayout& sm, const BinGrid& g, int E
         if (r0 > r1 || c0 > c1) continue;
         const Entry ent = sm.tile[e];
         const int w = c1 - c0 + 1, n = (r1 - r0 + 1) * w;
+        const float inv_w = 1.0f / (float)w;
         for (int i = lane; i < n; i += 32) {
-            int r = r0 + i / w, c = c0 + i % w;
+            const int q = (int)(((float)i + 0.5f) * inv_w);   // i / w, exact for i < 2^12
+            int r = r0 + q, c = c0 + (i - q * w);
             float t0 = g.th_lo + r * g.dth - kBinMargin, t1 = g.th_lo + (r + 1) * g.dth + kBinMargin;
             float p0 = -(float)kPi + c * g.dph - kBinMargin, p1 = -(float)kPi + (c + 1) * g.dph + kBinMargin;
             if (!bin_accepts(ent, t0, t1, p0, p1)) continue;
@@ -435,6 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
     const bool perez = rp.sky.kind == ISY_SKY_PEREZ;
     const bool cache_heads = !rp.vquat && rp.yaw && perez && rp.H <= kMaxH;
 
+    long long t_phase[4] = {0, 0, 0, 0};   // project, bin, rays, (spare): thread 0 only
     for (;;) {
         __syncthreads();
         if (tid == 0) s_item = atomicAdd(rp.queue, 1u);
@@ -442,19 +446,24 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
         const unsigned item = s_item;
         if (item >= (unsigned)rp.items) break;
         const int p = item / rp.splits, split = item % rp.splits;
+        long long t0 = clock64();
 
         if (cache_heads && tid < rp.H) sincos(rp.yaw[(size_t)p * rp.H + tid], &sm.head_sin[tid], &sm.head_cos[tid]);
         const int E = cull_and_project(rp, p, vis, entries, exacts, sm, &s_count, &s_nent, s_band);
+        long long t1 = clock64();
         BinGrid grid;
         bool binned = false;
         if (!(rp.flags & ISY_FLAG_BRUTE_FORCE) && E <= kMaxE) binned = build_bins(sm, grid, E, s_band, s_warp);
         const int nchunks = binned ? 1 : (E + kMaxE - 1) / kMaxE;
+        long long t2 = clock64();
 
-        for (int g0 = split * kThreads; g0 < raysPadded; g0 += rp.splits * kThreads) {
-            const int g = g0 + tid;
-            const bool valid = g < raysPerPos;
-            const int gg = valid ? g : 0;
-            const int h = gg / rp.R, r = gg - h * rp.R;
+        const int stride = rp.splits * kThreads;
+        const int stride_h = stride / rp.R, stride_r = stride - stride_h * rp.R;
+        int h = (split * kThreads + tid) / rp.R, r = (split * kThreads + tid) - h * rp.R;
+        for (int g0 = split * kThreads; g0 < raysPadded; g0 += stride, h += stride_h, r += stride_r) {
+            if (r >= rp.R) r -= rp.R, ++h;
+            const bool valid = g0 + tid < raysPerPos;
+            if (!valid) h = 0, r = 0;      // padding lanes of the last pass (never become valid again)
             const size_t b = (size_t)p * rp.H + h;
             Ray ray;
             double dx = 0, dy = 0, dz = 0, f_theta = 0;
@@ -522,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
             o.Y = 0, o.P = 0, o.A = CUDART_NAN;
             if (perez) {
                 const SunConst sc = rp.sun[rp.sun_per_view ? b : 0];
-                sky_eval(rp.sky, sc, dx, dy, dz, ray.pitch + kHalfPi, f_theta, o.Y, o.P, o.A);
+                sky_eval<kF64>(rp.sky, sc, dx, dy, dz, ray.pitch + kHalfPi, f_theta, o.Y, o.P, o.A);
             } else if (want_sky) {
                 o.Y = rp.sky.luminance;   // UniformSky: y = luminance, p = 0, a = nan (sky.py:77-79)
             }
@@ -542,6 +551,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
             }
             write_view<kF64>(rp, b, r, valid, ray.hit, ray.best, o);
         }
+        __syncthreads();
+        long long t3 = clock64();
+        t_phase[0] += t1 - t0, t_phase[1] += t2 - t1, t_phase[2] += t3 - t2, t_phase[3] += 1;
+    }
+    if (tid == 0) {
+        for (int k = 0; k < 4; ++k) atomicAdd(&rp.phase_cycles[k], (unsigned long long)t_phase[k]);
     }
 }
 
@@ -565,7 +580,7 @@ __global__ void sky_dirs_kernel(const double* __restrict__ quat, int64_t n, isy_
     double y = masked ? 0.0 : sp.luminance, p = 0.0, a = CUDART_NAN;   // UniformSky: sky.py:77-84
     if (sp.kind == ISY_SKY_PEREZ) {
         double f_theta = perez_f(dz, theta < kHalfPi, sp.A, sp.B);
-        sky_eval(sp, sun[0], dx, dy, dz, theta, f_theta, y, p, a, masked);
+        sky_eval<true>(sp, sun[0], dx, dy, dz, theta, f_theta, y, p, a, masked);
     }
     Y[i] = y, P[i] = p, A[i] = a;
 }

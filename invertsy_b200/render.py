@@ -212,6 +212,14 @@ class Renderer(object):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             _lib.check(_lib.lib().isy_workspace_status(self._workspace.data_ptr(), ctypes.c_void_p(stream)))
 
+    def phase_cycles(self):
+        """Profiling aid: (project, bin, rays, positions) SM-cycle sums of the last render()."""
+        out = np.zeros(4, dtype=np.uint64)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib().isy_workspace_phase_cycles(self._workspace.data_ptr(), ctypes.c_void_p(stream),
+                                                         _lib.ptr(out)))
+        return out
+
     def render_host(self, pos, yaw=None, quat=None, sun=None, outputs=("rgb", "Y", "dop", "aop"),
                     init_from_sky=False, f64=False, out=None, sky=None):
         """
