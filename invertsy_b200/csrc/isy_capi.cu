@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -68,6 +69,10 @@ struct isy_eye {
     double* d_py;    // R*2
     double* d_trig;  // R*4
     float* d_w;      // R
+    // rays sorted by pitch for the rasteriser
+    unsigned int* d_plut;        // kPitchLut + 1
+    void* d_sorted;              // R x {double yaw; float pitch; int ray}
+    int* d_pos_of;               // R
 };
 
 extern "C" {
@@ -111,7 +116,7 @@ int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int3
     if (N * S > (1ll << 30)) return fail(ISY_ERR_INVALID, "isy_eye_create: too many rays");
     DeviceGuard g(device);
     if (!g.ok) return fail(ISY_ERR_CUDA, "isy_eye_create: cannot select CUDA device %d (no CPU fallback)", device);
-    isy_eye* e = new isy_eye{device, N, S, N * S, nullptr, nullptr, nullptr, nullptr};
+    isy_eye* e = new isy_eye{device, N, S, N * S, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t R = (size_t)e->R;
     CUDA_TRY(cudaMalloc(&e->d_quat, R * 4 * sizeof(double)));
     CUDA_TRY(cudaMalloc(&e->d_py, R * 2 * sizeof(double)));
@@ -125,6 +130,39 @@ int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int3
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
+
+    // ---- rays sorted by pitch + look-up table pitch slot -> first sorted ray (rasteriser, yaw-only views) ----
+    {
+        std::vector<double> py(2 * R);
+        CUDA_TRY(cudaMemcpy(py.data(), e->d_py, 2 * R * sizeof(double), cudaMemcpyDeviceToHost));
+        struct SortedRay {
+            double yaw;
+            float pitch;
+            int32_t ray;
+        };
+        static_assert(sizeof(SortedRay) == 16, "SortedRay must be 16 bytes");
+        std::vector<SortedRay> sorted(R);
+        for (size_t r = 0; r < R; ++r) sorted[r] = SortedRay{py[2 * r + 1], (float)py[2 * r], (int32_t)r};
+        std::stable_sort(sorted.begin(), sorted.end(),
+                         [](const SortedRay& a, const SortedRay& b) { return a.pitch < b.pitch; });
+        std::vector<int> pos_of(R);
+        for (size_t j = 0; j < R; ++j) pos_of[sorted[j].ray] = (int)j;
+        const double pi = 3.141592653589793238462643383279502884;
+        std::vector<unsigned int> plut(kPitchLut + 1);
+        size_t j = 0;
+        for (int sl = 0; sl <= kPitchLut; ++sl) {
+            const float edge = (float)(-pi / 2 + sl * (pi / kPitchLut)) - 1e-5f;   // conservative slot start
+            while (j < R && sorted[j].pitch < edge) ++j;
+            plut[sl] = (unsigned int)j;
+        }
+        plut[kPitchLut] = (unsigned int)R;   // the end bound of every run
+        CUDA_TRY(cudaMalloc(&e->d_plut, (kPitchLut + 1) * sizeof(unsigned int)));
+        CUDA_TRY(cudaMalloc(&e->d_sorted, R * sizeof(SortedRay)));
+        CUDA_TRY(cudaMalloc(&e->d_pos_of, R * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(e->d_plut, plut.data(), (kPitchLut + 1) * sizeof(unsigned int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(e->d_sorted, sorted.data(), R * sizeof(SortedRay), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(e->d_pos_of, pos_of.data(), R * sizeof(int), cudaMemcpyHostToDevice));
+    }
     *out = e;
     return ISY_OK;
 }
@@ -136,6 +174,9 @@ int isy_eye_destroy(isy_eye* e) {
     cudaFree(e->d_py);
     cudaFree(e->d_trig);
     cudaFree(e->d_w);
+    cudaFree(e->d_plut);
+    cudaFree(e->d_sorted);
+    cudaFree(e->d_pos_of);
     delete e;
     return ISY_OK;
 }
@@ -149,8 +190,10 @@ namespace {
 struct Plan {
     int grid;
     int splits;
+    int Hg, ngroups;
     int slab_cap;
-    size_t off_queue, off_status, off_sun, off_ftheta, off_vis, off_entry, off_exact, total;
+    bool global_best;
+    size_t off_queue, off_status, off_sun, off_ftheta, off_vis, off_entry, off_exact, off_best, total;
 };
 
 int device_sms(int device) {
@@ -166,13 +209,16 @@ int device_sms(int device) {
 
 Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
     Plan pl;
-    int sms = device_sms(w->device);
-    int64_t rays = H * e->R;
-    int64_t passes = (rays + kThreads - 1) / kThreads;
-    int max_ctas = sms;  // one persistent CTA per SM (~190 KB of shared memory, 512 threads)
+    const int max_ctas = device_sms(w->device);  // one persistent CTA per SM (~210 KB of shared memory, 512 threads)
+    // headings per group: what the rasteriser's shared-memory winner buffer holds
+    pl.global_best = e->R > kBestCap || e->R > kGridRaysSmem;
+    int64_t hg_max = pl.global_best ? 1 : std::min<int64_t>(kBestCap / e->R, kMaxH);
     int64_t splits = 1;
-    if (P < max_ctas) splits = std::min<int64_t>(passes, (max_ctas + P - 1) / std::max<int64_t>(P, 1));
-    pl.splits = (int)std::max<int64_t>(splits, 1);
+    if (P < max_ctas) splits = std::min<int64_t>(H, (max_ctas + std::max<int64_t>(P, 1) - 1) / std::max<int64_t>(P, 1));
+    int64_t ngroups = std::max<int64_t>((H + hg_max - 1) / hg_max, splits);
+    pl.Hg = (int)((H + ngroups - 1) / ngroups);
+    pl.ngroups = (int)((H + pl.Hg - 1) / pl.Hg);
+    pl.splits = (int)std::max<int64_t>(1, std::min<int64_t>(splits, pl.ngroups));
     int64_t items = P * pl.splits;
     pl.grid = (int)std::max<int64_t>(1, std::min<int64_t>(items, max_ctas));
     pl.slab_cap = (int)std::min<int64_t>(2 * std::max<int64_t>(w->T, 1), 1 << 17);
@@ -184,6 +230,7 @@ Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
     pl.off_vis = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(int));
     pl.off_entry = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(Entry));
     pl.off_exact = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(Exact));
+    pl.off_best = off, off += pl.global_best ? align_up((size_t)pl.grid * e->R * sizeof(unsigned int)) : 0;
     pl.total = off;
     return pl;
 }
@@ -223,7 +270,10 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
     rp.slab_vis = (int*)(base + pl.off_vis);
     rp.slab_entry = (Entry*)(base + pl.off_entry);
     rp.slab_exact = (Exact*)(base + pl.off_exact);
+    rp.slab_best = pl.global_best ? (unsigned int*)(base + pl.off_best) : nullptr;
     rp.slab_cap = pl.slab_cap, rp.splits = pl.splits, rp.items = (int)(P * pl.splits);
+    rp.Hg = pl.Hg, rp.ngroups = pl.ngroups;
+    rp.grid_plut = e->d_plut, rp.grid_sorted = e->d_sorted, rp.grid_pos_of = e->d_pos_of;
 
     CUDA_TRY(cudaMemsetAsync(base, 0, 512, st));
     if (sp.kind == ISY_SKY_PEREZ) {

@@ -70,6 +70,10 @@ struct RenderParams {
     const double* eye_ftheta;// [R]    Perez gradation f(theta) of each eye ray for this call's sky (workspace)
     const double* eye_quat;  // [R][4]
     const float* eye_w;      // [R]
+    // the eye's rays sorted by pitch, for the rasteriser (null = not available)
+    const unsigned int* grid_plut;        // [kPitchLut + 1] first sorted ray at or above each pitch slot
+    const void* grid_sorted;              // [R] {double yaw; float pitch; int ray} in pitch order
+    const int* grid_pos_of;               // [R] sorted position of ray r
     int N, S, R;
     // views
     int P, H;
@@ -89,8 +93,10 @@ struct RenderParams {
     int* slab_vis;           // [grid][slab_cap] visible triangle ids
     Entry* slab_entry;       // [grid][slab_cap]
     Exact* slab_exact;       // [grid][slab_cap]
+    unsigned int* slab_best; // [grid][R] winner buffer in global memory when a heading does not fit smem, else null
     int slab_cap;
-    int splits;              // CTAs sharing one position (each redoes the cull, takes a ray slice)
+    int Hg, ngroups;         // headings per group, number of groups (H = sum of group sizes)
+    int splits;              // CTAs sharing one position (each redoes the cull, takes every splits-th group)
     int items;               // P * splits
 };
 

@@ -32,14 +32,36 @@ constexpr int kMaxH = 128;            // headings whose sin/cos are cached per p
 constexpr float kBinMargin = 1e-4f;   // rad; >> every fp32 rounding in the bin arithmetic
 constexpr float kBinReject = -1e-5f;  // a bin is dropped only if an edge function is below this on all of it
 
-struct SmemLayout {
-    Entry tile[kMaxE];
-    float4 bbox[kMaxE];               // (theta_lo, theta_hi, phi_lo, phi_hi) of each copy, margin included
+constexpr int kBestCap = 36864;       // (heading, ray) slots of the rasteriser's winner buffer (u16 ranks, 72 KB)
+constexpr int kGridRaysSmem = 1280;   // eyes up to this many rays keep their pitch-sorted ray table in shared memory
+constexpr int kPitchLut = 1024;       // slots of the pitch -> first sorted ray look-up table
+constexpr int kHeadLut = 256;         // slots of the azimuth -> first sorted heading look-up table
+
+struct SmemBins {
     unsigned int bin_off[kBins + 4];  // exclusive offsets into list (counts during the count pass)
     unsigned int bin_cur[kBins];      // fill cursors
     unsigned short list[kListCap];
-    double head_sin[kMaxH], head_cos[kMaxH];
 };
+
+struct SmemRaster {
+    unsigned short best[kBestCap];    // nearest containing copy (slot in tile) per (heading, sorted ray)
+    double2 sorted[kGridRaysSmem];    // the eye's rays in pitch order: {yaw, (pitch | ray)} (copied once per CTA)
+    unsigned int plut[kPitchLut + 4]; // first sorted ray at or above each pitch slot
+    float hsort[2 * kMaxH];           // wrapped headings of the group, ascending, then the same + 2 pi
+    unsigned char hperm[2 * kMaxH];   // heading index of each sorted slot
+    unsigned short hlut[kHeadLut];    // first sorted slot at or above each azimuth slot
+};
+
+struct SmemLayout {
+    Entry tile[kMaxE];
+    float4 bbox[kMaxE];               // (theta_lo, theta_hi, phi_lo, phi_hi) of each copy, margin included
+    double head_sin[kMaxH], head_cos[kMaxH], head_val[kMaxH];   // per heading of the current group
+    union {
+        SmemBins bins;
+        SmemRaster ras;
+    };
+};
+static_assert(sizeof(SmemLayout) <= 192 * 1024, "leave some of the 228 KB for L1");
 
 struct RayOut {
     double r, g, b;
@@ -270,10 +292,10 @@ __device__ __forceinline__ void bin_pass(SmemLayout& sm, const BinGrid& g, int E
             if (!bin_accepts(ent, t0, t1, p0, p1)) continue;
             int b = r * g.cols + c;
             if (kFill) {
-                unsigned pos = atomicAdd(&sm.bin_cur[b], 1u);
-                sm.list[pos] = (unsigned short)e;
+                unsigned pos = atomicAdd(&sm.bins.bin_cur[b], 1u);
+                sm.bins.list[pos] = (unsigned short)e;
             } else {
-                atomicAdd(&sm.bin_off[b], 1u);
+                atomicAdd(&sm.bins.bin_off[b], 1u);
             }
         }
     }
@@ -286,7 +308,7 @@ __device__ unsigned int block_scan_bins(SmemLayout& sm, int nb, unsigned int* s_
     unsigned int local[kBins / kThreads];
     unsigned int sum = 0;
     for (int i = 0; i < per; ++i) {
-        local[i] = sm.bin_off[tid * per + i];
+        local[i] = sm.bins.bin_off[tid * per + i];
         sum += local[i];
     }
     unsigned int inc = sum;
@@ -304,11 +326,11 @@ __device__ unsigned int block_scan_bins(SmemLayout& sm, int nb, unsigned int* s_
     }
     unsigned int run = wbase + inc - sum;
     for (int i = 0; i < per; ++i) {
-        sm.bin_off[tid * per + i] = run;
-        sm.bin_cur[tid * per + i] = run;
+        sm.bins.bin_off[tid * per + i] = run;
+        sm.bins.bin_cur[tid * per + i] = run;
         run += local[i];
     }
-    if (tid == kThreads - 1) sm.bin_off[nb] = run;
+    if (tid == kThreads - 1) sm.bins.bin_off[nb] = run;
     __syncthreads();
     return total;
 }
@@ -331,7 +353,7 @@ __device__ bool build_bins(SmemLayout& sm, BinGrid& g, int E, const int* s_band,
         g.dph = (float)kTwoPi / g.cols;
         g.inv_dph = g.cols / (float)kTwoPi;
         const int nb = g.rows * g.cols;
-        for (int i = threadIdx.x; i < nb; i += kThreads) sm.bin_off[i] = 0;
+        for (int i = threadIdx.x; i < nb; i += kThreads) sm.bins.bin_off[i] = 0;
         __syncthreads();
         bin_pass<false>(sm, g, E);
         __syncthreads();
@@ -419,8 +441,242 @@ __device__ __forceinline__ void write_view(const RenderParams& rp, size_t b, int
 }
 
 // ------------------------------------------------------------------------------------------
+// phase A3' + B' (yaw-only views): triangle-centric rasterisation over the eye's pitch-sorted rays.
+//
+// For a yaw-only view the query of ray r is (pitch_r, yaw_r + heading).  A projected copy with
+// bounding box [t0,t1] x [p0,p1] can only contain rays whose pitch lies in [t0,t1] -- a contiguous
+// run of the eye's rays sorted by pitch (static per eye, isy_eye_create) -- and, for such a ray,
+// only the headings h with yaw_r + h in [p0,p1]: a window of the group's sorted headings found
+// through a small look-up table.  One warp takes a copy, its lanes the rays of the pitch run;
+// each (ray, heading) that survives gets the fp32 edge test (+ exact re-check) and posts the
+// copy's distance rank with an atomic min into best[heading][sorted ray].
+// The work is proportional to (copies x rays in their pitch band) + (true candidate pairs) for
+// ALL headings of the position at once; nothing is built per position beyond the ranks.
+// ------------------------------------------------------------------------------------------
+constexpr unsigned int kNoCopy = 0xffffu;
+
+// is copy e (distance d, triangle tri) nearer than copy c? (ties: lower triangle index, then lower slot)
+__device__ __forceinline__ bool nearer(const Entry* tile, double d, int tri, unsigned int e, unsigned int c) {
+    const Entry& o = tile[c];
+    const double dc = __hiloint2double(o.dist_hi, o.dist_lo);
+    return d < dc || (d == dc && (tri < o.tri || (tri == o.tri && e < c)));
+}
+
+// best[idx] = nearer(e, best[idx]) ? e : best[idx], atomically (CAS on the 32-bit word holding the u16)
+__device__ __forceinline__ void post_copy_u16(unsigned short* best, unsigned int idx, const Entry* tile, double d, int tri,
+                                              unsigned int e) {
+    unsigned int* word = reinterpret_cast<unsigned int*>(best) + (idx >> 1);
+    const bool hi = idx & 1u;
+    unsigned int old = *reinterpret_cast<volatile unsigned int*>(word);
+    for (;;) {
+        const unsigned int cur = hi ? (old >> 16) : (old & 0xffffu);
+        if (cur != kNoCopy && !nearer(tile, d, tri, e, cur)) return;
+        const unsigned int nw = hi ? ((old & 0xffffu) | (e << 16)) : ((old & 0xffff0000u) | e);
+        const unsigned int prev = atomicCAS(word, old, nw);
+        if (prev == old) return;
+        old = prev;
+    }
+}
+
+__device__ __forceinline__ void post_copy_u32(unsigned int* slot, const Entry* tile, double d, int tri, unsigned int e) {
+    unsigned int old = *reinterpret_cast<volatile unsigned int*>(slot);
+    for (;;) {
+        if (old != kNoCopy && !nearer(tile, d, tri, e, old)) return;
+        const unsigned int prev = atomicCAS(slot, old, e);
+        if (prev == old) return;
+        old = prev;
+    }
+}
+
+// sorts the group's wrapped headings (head_val[0..Hcur)) and builds the azimuth look-up table
+__device__ void sort_headings(SmemLayout& sm, int Hcur) {
+    const int tid = threadIdx.x;
+    if (tid < Hcur) {
+        const float h = (float)sm.head_val[tid];
+        int pos = 0;
+        for (int k = 0; k < Hcur; ++k) {
+            const float hk = (float)sm.head_val[k];
+            pos += (hk < h) || (hk == h && k < tid);
+        }
+        sm.ras.hsort[pos] = h;
+        sm.ras.hsort[pos + Hcur] = h + (float)kTwoPi;
+        sm.ras.hperm[pos] = (unsigned char)tid;
+        sm.ras.hperm[pos + Hcur] = (unsigned char)tid;
+    }
+    __syncthreads();
+    if (tid < kHeadLut) {
+        const float start = -(float)kPi + tid * ((float)kTwoPi / kHeadLut) - 1e-4f;
+        int k = 0;
+        while (k < 2 * Hcur && sm.ras.hsort[k] < start) ++k;
+        sm.ras.hlut[tid] = (unsigned short)k;
+    }
+}
+
+// kSmem: the eye's sorted ray table and the winner buffer live in shared memory (u16 ranks);
+// otherwise both are in global memory (u32 ranks), for eyes too large for that.
+template <bool kSmem>
+__device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest, const Exact* exacts, int E,
+                              int Hcur, int* s_next) {
+    const int R = rp.R, lane = threadIdx.x & 31;
+    const double2* gsorted = reinterpret_cast<const double2*>(rp.grid_sorted);
+    const int H2 = 2 * Hcur;
+    for (;;) {
+        // copies differ a lot in size (a near blade spans hundreds of rays): warps pull them from a counter
+        int e = 0;
+        if (lane == 0) e = atomicAdd(s_next, 1);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= E) break;
+        const float4 bb = sm.bbox[e];
+        // azimuth window of the copy clipped to the query domain (-pi, pi]
+        const float glo = fmaxf(bb.z, -(float)kPi - kBinMargin), ghi = fminf(bb.w, (float)kPi + kBinMargin);
+        if (glo > ghi) continue;
+        const float width = ghi - glo + 2.f * kBinMargin;
+        const Entry ent = sm.tile[e];
+        const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
+        // run of pitch-sorted rays that covers [bb.x, bb.y] (a few extra rays at both ends)
+        const int s0 = min(max((int)floorf((bb.x + (float)kHalfPi) * (kPitchLut / (float)kPi)), 0), kPitchLut - 1);
+        const int s1 = min(max((int)floorf((bb.y + (float)kHalfPi) * (kPitchLut / (float)kPi)) + 2, 0), kPitchLut);
+        const unsigned jbeg = kSmem ? sm.ras.plut[s0] : __ldg(rp.grid_plut + s0);
+        const unsigned jend = kSmem ? sm.ras.plut[s1] : __ldg(rp.grid_plut + s1);
+        for (unsigned jb = jbeg; jb < jend; jb += 32) {      // warp-uniform trip count
+            __syncwarp();                                    // keep the lanes converged across iterations
+            const unsigned j = jb + lane;
+            double2 sr = make_double2(0.0, 0.0);
+            float fp = 2.f * (float)kPi;
+            if (j < jend) {
+                sr = kSmem ? sm.ras.sorted[j] : __ldg(gsorted + j);
+                fp = __int_as_float(__double2loint(sr.y));
+            }
+            int k = H2, kend = H2;
+            float upper = 0.f;
+            if (fp >= bb.x && fp <= bb.y) {
+                // headings h with yaw + h in [glo - m, ghi + m]  <=>  h in [lower, lower + width] on the circle
+                float lower = glo - kBinMargin - (float)sr.x;
+                if (lower < -(float)kPi) lower += (float)kTwoPi;
+                else if (lower >= (float)kPi) lower -= (float)kTwoPi;
+                const int ls = min(max((int)((lower + (float)kPi) * (kHeadLut / (float)kTwoPi)), 0), kHeadLut - 1);
+                k = sm.ras.hlut[ls];
+                while (k < H2 && sm.ras.hsort[k] < lower) ++k;
+                upper = lower + width;
+                kend = k;
+                while (kend < H2 && sm.ras.hsort[kend] <= upper) ++kend;
+            }
+            // lanes walk their heading windows in lock step (most windows hold 0 or 1 heading)
+            while (__any_sync(0xffffffffu, k < kend)) {
+                if (k < kend) {
+                    const int hh = sm.ras.hperm[k];
+                    double yg = sr.x + sm.head_val[hh];         // both in (-pi, pi]: one shift wraps
+                    if (yg > kPi) yg -= kTwoPi;
+                    else if (yg <= -kPi) yg += kTwoPi;
+                    const float fy = (float)yg;
+                    float e0 = fmaf(ent.A0, fp, fmaf(ent.B0, fy, ent.C0));
+                    float e1 = fmaf(ent.A1, fp, fmaf(ent.B1, fy, ent.C1));
+                    float e2 = fmaf(ent.A2, fp, fmaf(ent.B2, fy, ent.C2));
+                    float m = fminf(e0, fminf(e1, e2));
+                    if (m >= -kEdgeEps) {
+                        bool in = m > kEdgeEps;
+                        if (!in) {
+                            const int ray = __double2hiint(sr.y);
+                            in = inside_exact(exacts[e], rp.eye_py[2 * (size_t)ray], yg);
+                        }
+                        if (in) {
+                            if (kSmem) post_copy_u16(sm.ras.best, (unsigned)hh * R + j, sm.tile, dist, ent.tri, e);
+                            else post_copy_u32(&gbest[(size_t)hh * R + j], sm.tile, dist, ent.tri, e);
+                        }
+                    }
+                    ++k;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // the render kernel
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// final pass of the rasteriser path, float outputs, one sample per ommatidium: per ray pick the
+// winner from best[], shade, evaluate the sky and write the view (the only HBM traffic).
+// Warp units = (block of 32 consecutive rays) x (chunk of headings); a ray's eye data are loaded
+// once per unit and reused for all its headings; each store instruction covers 32 consecutive
+// rays of one view.
+// ------------------------------------------------------------------------------------------
+template <bool kSmem>
+__device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const unsigned int* gbest, int p, int h0,
+                                int Hcur) {
+    const int R = rp.R, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool perez = rp.sky.kind == ISY_SKY_PEREZ, uniform = rp.sky.kind == ISY_SKY_UNIFORM;
+    const bool from_sky = (rp.flags & ISY_FLAG_INIT_FROM_SKY) && (perez || uniform);
+    float* const o_rgb = reinterpret_cast<float*>(rp.out.rgb);
+    float* const o_depth = reinterpret_cast<float*>(rp.out.depth);
+    float* const o_Y = reinterpret_cast<float*>(rp.out.Y);
+    float* const o_P = reinterpret_cast<float*>(rp.out.dop);
+    float* const o_A = reinterpret_cast<float*>(rp.out.aop);
+    const float nanf_ = __int_as_float(0x7fc00000);
+    const int nb = (R + 31) >> 5;
+    int nch = min(Hcur, max(1, (2 * kWarps + nb - 1) / nb));
+    const int hper = (Hcur + nch - 1) / nch;
+    nch = (Hcur + hper - 1) / hper;
+    for (int u = warp; u < nb * nch; u += kWarps) {
+        const int rb = u / nch, hc = u - rb * nch;
+        const int r = rb * 32 + lane;
+        const bool valid = r < R;
+        const int rr = valid ? r : R - 1;
+        const double e_pitch = rp.eye_py[2 * (size_t)rr];
+        const bool ground = e_pitch >= 0;                               // world.py:90
+        double4 t4v = make_double4(0, 1, 0, 1);
+        double f_theta = 0;
+        if (perez) {
+            t4v = *reinterpret_cast<const double4*>(rp.eye_trig + 4 * (size_t)rr);
+            f_theta = rp.eye_ftheta[rr];
+        }
+        const int pos = __ldg(rp.grid_pos_of + rr);
+        const int hend = min(Hcur, (hc + 1) * hper);
+        for (int hh = hc * hper; hh < hend; ++hh) {
+            const size_t vbase = ((size_t)p * rp.H + h0 + hh) * (size_t)R;   // first ray of this view
+            const unsigned int id = kSmem ? (unsigned)sm.ras.best[hh * R + pos] : gbest[(size_t)hh * R + pos];
+            double Y = 0, P = 0, A = CUDART_NAN;
+            if (perez) {
+                const double hs = sm.head_sin[hh], hcs = sm.head_cos[hh];
+                const double sy = t4v.z * hcs + t4v.w * hs, cy = t4v.w * hcs - t4v.z * hs;   // yaw_e + heading
+                const SunConst sc = rp.sun[rp.sun_per_view ? (size_t)p * rp.H + h0 + hh : 0];
+                sky_eval<false>(rp.sky, sc, t4v.y * cy, t4v.y * sy, -t4v.x, e_pitch + kHalfPi, f_theta, Y, P, A);
+            } else if (uniform) {
+                Y = rp.sky.luminance;
+            }
+            float cr = nanf_, cg = nanf_, cb = nanf_, depth = nanf_;
+            int hit = -1;
+            if (from_sky) {                                              // luminance2skycolour, world.py:479
+                cr = (float)fmin(fmax(19.0 * Y + 13.0, 0.0), 255.0);
+                cg = (float)fmin(fmax(19.0 * Y + 135.0, 0.0), 255.0);
+                cb = (float)fmin(fmax(19.0 * Y + 201.0, 0.0), 255.0);
+            }
+            if (ground) cr = (float)(229.0 / 255.0), cg = (float)(183.0 / 255.0), cb = (float)(90.0 / 255.0);
+            if (id != kNoCopy) {
+                const Entry& w = sm.tile[id];
+                hit = w.tri;
+                depth = (float)__hiloint2double(w.dist_hi, w.dist_lo);
+                const float* col = rp.tri_rgb + 3 * (size_t)hit;
+                cr = __ldg(col + 0), cg = __ldg(col + 1), cb = __ldg(col + 2);
+            }
+            if (valid) {
+                const size_t i = vbase + r;
+                if (o_rgb) {
+                    float* q = o_rgb + 3 * i;
+                    q[0] = cr, q[1] = cg, q[2] = cb;
+                }
+                if (rp.out.hit) rp.out.hit[i] = hit;
+                if (o_depth) o_depth[i] = depth;
+                if (o_Y) o_Y[i] = (float)Y;
+                if (o_P) o_P[i] = (float)P;
+                if (o_A) o_A[i] = (float)A;
+            }
+        }
+    }
+}
+
+enum { kModeBrute = 0, kModeBins = 1, kModeRaster = 2 };
+
 template <bool kF64>
 __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams rp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -428,17 +684,19 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
     __shared__ int s_count, s_nent, s_band[2];
     __shared__ unsigned int s_item, s_warp[kWarps];
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int* vis = rp.slab_vis + (size_t)blockIdx.x * rp.slab_cap;
     Entry* entries = rp.slab_entry + (size_t)blockIdx.x * rp.slab_cap;
     Exact* exacts = rp.slab_exact + (size_t)blockIdx.x * rp.slab_cap;
-    const int raysPerPos = rp.H * rp.R;
-    const int raysPadded = (raysPerPos + kThreads - 1) / kThreads * kThreads;
+    unsigned int* gbest = rp.slab_best ? rp.slab_best + (size_t)blockIdx.x * rp.R : nullptr;
     const bool want_sky = rp.sky.kind != ISY_SKY_NONE;
     const bool perez = rp.sky.kind == ISY_SKY_PEREZ;
-    const bool cache_heads = !rp.vquat && rp.yaw && perez && rp.H <= kMaxH;
+    const bool yaw_only = !rp.vquat;
+    const bool raster_ok = yaw_only && rp.grid_sorted && !(rp.flags & ISY_FLAG_BRUTE_FORCE);
+    const bool smem_grid = raster_ok && !gbest;
+    bool grid_loaded = false;
 
-    long long t_phase[4] = {0, 0, 0, 0};   // project, bin, rays, (spare): thread 0 only
+    long long t_phase[4] = {0, 0, 0, 0};   // project, accel (bins / ranks + raster), final ray pass, positions
     for (;;) {
         __syncthreads();
         if (tid == 0) s_item = atomicAdd(rp.queue, 1u);
@@ -448,112 +706,171 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
         const int p = item / rp.splits, split = item % rp.splits;
         long long t0 = clock64();
 
-        if (cache_heads && tid < rp.H) sincos(rp.yaw[(size_t)p * rp.H + tid], &sm.head_sin[tid], &sm.head_cos[tid]);
         const int E = cull_and_project(rp, p, vis, entries, exacts, sm, &s_count, &s_nent, s_band);
         long long t1 = clock64();
+        int mode = kModeBrute;
         BinGrid grid;
-        bool binned = false;
-        if (!(rp.flags & ISY_FLAG_BRUTE_FORCE) && E <= kMaxE) binned = build_bins(sm, grid, E, s_band, s_warp);
-        const int nchunks = binned ? 1 : (E + kMaxE - 1) / kMaxE;
+        if (!(rp.flags & ISY_FLAG_BRUTE_FORCE) && E <= kMaxE) {
+            if (raster_ok) {
+                mode = kModeRaster;
+                if (smem_grid && !grid_loaded) {   // the bins path shares this memory: (re)load when needed
+                    for (int i = tid; i <= kPitchLut; i += kThreads) sm.ras.plut[i] = rp.grid_plut[i];
+                    for (int i = tid; i < rp.R; i += kThreads)
+                        sm.ras.sorted[i] = reinterpret_cast<const double2*>(rp.grid_sorted)[i];
+                    grid_loaded = true;
+                }
+            } else if (build_bins(sm, grid, E, s_band, s_warp)) {
+                mode = kModeBins;
+                grid_loaded = false;
+            }
+        }
         long long t2 = clock64();
 
-        const int stride = rp.splits * kThreads;
-        const int stride_h = stride / rp.R, stride_r = stride - stride_h * rp.R;
-        int h = (split * kThreads + tid) / rp.R, r = (split * kThreads + tid) - h * rp.R;
-        for (int g0 = split * kThreads; g0 < raysPadded; g0 += stride, h += stride_h, r += stride_r) {
-            if (r >= rp.R) r -= rp.R, ++h;
-            const bool valid = g0 + tid < raysPerPos;
-            if (!valid) h = 0, r = 0;      // padding lanes of the last pass (never become valid again)
-            const size_t b = (size_t)p * rp.H + h;
-            Ray ray;
-            double dx = 0, dy = 0, dz = 0, f_theta = 0;
-            if (rp.vquat) {
-                const double* qv = rp.vquat + 4 * b;
-                const double* qo = rp.eye_quat + 4 * (size_t)r;
-                double x1 = qv[0], y1 = qv[1], z1 = qv[2], w1 = qv[3];
-                double x2 = qo[0], y2 = qo[1], z2 = qo[2], w2 = qo[3];
-                double w = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2;
-                double x = w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2;
-                double y = w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2;
-                double z = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2;
-                quat_dir(x, y, z, w, dx, dy, dz);
-                dir_pitch_yaw(dx, dy, dz, ray.pitch, ray.yaw);
-                if (perez) f_theta = perez_f(dz, ray.pitch + kHalfPi < kHalfPi, rp.sky.A, rp.sky.B);
-            } else {
-                const double heading = rp.yaw ? rp.yaw[b] : 0.0;
-                ray.pitch = rp.eye_py[2 * (size_t)r + 0];
-                ray.yaw = wrap_yaw(rp.eye_py[2 * (size_t)r + 1] + heading);
-                if (perez) {
-                    const double4 t4 = *reinterpret_cast<const double4*>(rp.eye_trig + 4 * (size_t)r);
-                    double hs, hc;
-                    if (cache_heads) {
-                        hs = sm.head_sin[h], hc = sm.head_cos[h];
+        // headings are handled in groups of rp.Hg (the rasteriser's winner buffer holds one group)
+        for (int grp = split; grp < rp.ngroups; grp += rp.splits) {
+            const int h0 = grp * rp.Hg, Hcur = min(rp.Hg, rp.H - h0);
+            long long t3 = clock64();
+            __syncthreads();
+            if (yaw_only && tid < Hcur) {
+                const double hw = wrap_yaw(rp.yaw ? rp.yaw[(size_t)p * rp.H + h0 + tid] : 0.0);
+                sm.head_val[tid] = hw;
+                sincos(hw, &sm.head_sin[tid], &sm.head_cos[tid]);
+            }
+            if (mode == kModeRaster) {
+                if (smem_grid) {
+                    unsigned int* b32 = reinterpret_cast<unsigned int*>(sm.ras.best);
+                    for (int i = tid; i < (Hcur * rp.R + 1) / 2; i += kThreads) b32[i] = 0xffffffffu;
+                } else {
+                    for (int i = tid; i < Hcur * rp.R; i += kThreads) gbest[i] = kNoCopy;
+                }
+                __syncthreads();
+                if (tid == 0) s_count = 0;     // (the cull's counter is free again: next copy to rasterise)
+                sort_headings(sm, Hcur);
+                __syncthreads();
+                if (smem_grid) raster_copies<true>(rp, sm, gbest, exacts, E, Hcur, &s_count);
+                else raster_copies<false>(rp, sm, gbest, exacts, E, Hcur, &s_count);
+            }
+            __syncthreads();
+            long long t4 = clock64();
+            t_phase[1] += t4 - t3;
+
+            if (mode == kModeRaster && !kF64 && rp.S == 1 && !rp.init_c) {
+                if (smem_grid) final_pass_fast<true>(rp, sm, gbest, p, h0, Hcur);
+                else final_pass_fast<false>(rp, sm, gbest, p, h0, Hcur);
+                t_phase[2] += clock64() - t4;
+                continue;
+            }
+            // ---- generic final pass: warp units = (block of 32 consecutive rays) x (chunk of headings);
+            //      the eye data of a ray are loaded once per unit and reused for its headings
+            const int nb = (rp.R + 31) >> 5;
+            int nch = min(Hcur, max(1, (2 * kWarps + nb - 1) / nb));
+            const int hper = (Hcur + nch - 1) / nch;
+            nch = (Hcur + hper - 1) / hper;
+            for (int u = warp; u < nb * nch; u += kWarps) {
+                const int rb = u / nch, hc = u - rb * nch;
+                const int r = rb * 32 + lane;
+                const bool valid = r < rp.R;
+                const int rr = valid ? r : rp.R - 1;
+                double e_pitch = 0, e_yaw = 0, f_theta = 0;
+                double4 t4v = make_double4(0, 1, 0, 1);
+                int pos = 0;
+                if (yaw_only) {
+                    e_pitch = rp.eye_py[2 * (size_t)rr + 0];
+                    e_yaw = rp.eye_py[2 * (size_t)rr + 1];
+                    if (perez) {
+                        t4v = *reinterpret_cast<const double4*>(rp.eye_trig + 4 * (size_t)rr);
+                        f_theta = rp.eye_ftheta[rr];
+                    }
+                    if (mode == kModeRaster) pos = __ldg(rp.grid_pos_of + rr);
+                }
+                const int hend = min(Hcur, (hc + 1) * hper);
+                for (int hh = hc * hper; hh < hend; ++hh) {
+                    const size_t b = (size_t)p * rp.H + h0 + hh;
+                    Ray ray;
+                    double dx = 0, dy = 0, dz = 0;
+                    if (!yaw_only) {
+                        const double* qv = rp.vquat + 4 * b;
+                        const double* qo = rp.eye_quat + 4 * (size_t)rr;
+                        double x1 = qv[0], y1 = qv[1], z1 = qv[2], w1 = qv[3];
+                        double x2 = qo[0], y2 = qo[1], z2 = qo[2], w2 = qo[3];
+                        double w = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2;
+                        double x = w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2;
+                        double y = w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2;
+                        double z = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2;
+                        quat_dir(x, y, z, w, dx, dy, dz);
+                        dir_pitch_yaw(dx, dy, dz, ray.pitch, ray.yaw);
+                        if (perez) f_theta = perez_f(dz, ray.pitch + kHalfPi < kHalfPi, rp.sky.A, rp.sky.B);
                     } else {
-                        sincos(heading, &hs, &hc);
+                        ray.pitch = e_pitch;
+                        double yg = e_yaw + sm.head_val[hh];   // both in (-pi, pi]: one shift wraps
+                        if (yg > kPi) yg -= kTwoPi;
+                        else if (yg <= -kPi) yg += kTwoPi;
+                        ray.yaw = yg;
+                        if (perez) {
+                            const double hs = sm.head_sin[hh], hcs = sm.head_cos[hh];
+                            // sin/cos(yaw_e + heading) by the addition formulas
+                            double sy = t4v.z * hcs + t4v.w * hs, cy = t4v.w * hcs - t4v.z * hs;
+                            dx = t4v.y * cy, dy = t4v.y * sy, dz = -t4v.x;
+                        }
                     }
-                    // sin/cos(yaw_e + heading) by the addition formulas
-                    double sy = t4.z * hc + t4.w * hs, cy = t4.w * hc - t4.z * hs;
-                    dx = t4.y * cy, dy = t4.y * sy, dz = -t4.x;
-                    f_theta = rp.eye_ftheta[r];
-                }
-            }
-            ray.fp = (float)ray.pitch;
-            ray.fy = (float)ray.yaw;
-            ray.best = CUDART_INF;
-            ray.hit = -1;
+                    ray.fp = (float)ray.pitch;
+                    ray.fy = (float)ray.yaw;
+                    ray.best = CUDART_INF;
+                    ray.hit = -1;
 
-            if (binned) {
-                if (ray.fp >= grid.th_lo && ray.fp <= grid.th_hi) {
-                    int row = min((int)((ray.fp - grid.th_lo) * grid.inv_dth), grid.rows - 1);
-                    int col = min(max((int)((ray.fy + (float)kPi) * grid.inv_dph), 0), grid.cols - 1);
-                    int bin = row * grid.cols + col;
-                    unsigned i0 = sm.bin_off[bin], i1 = sm.bin_off[bin + 1];
-                    for (unsigned i = i0; i < i1; ++i) {
-                        int e = sm.list[i];
-                        test_entry(ray, &sm.tile[e], &exacts[e]);
+                    if (mode == kModeRaster) {
+                        const unsigned int rk = smem_grid ? (unsigned)sm.ras.best[hh * rp.R + pos]
+                                                          : gbest[(size_t)hh * rp.R + pos];
+                        if (rk != kNoCopy) {
+                            const Entry& w = sm.tile[rk];
+                            ray.hit = w.tri;
+                            ray.best = __hiloint2double(w.dist_hi, w.dist_lo);
+                        }
+                    } else if (mode == kModeBins) {
+                        if (ray.fp >= grid.th_lo && ray.fp <= grid.th_hi) {
+                            int row = min((int)((ray.fp - grid.th_lo) * grid.inv_dth), grid.rows - 1);
+                            int col = min(max((int)((ray.fy + (float)kPi) * grid.inv_dph), 0), grid.cols - 1);
+                            int bin = row * grid.cols + col;
+                            unsigned i0 = sm.bins.bin_off[bin], i1 = sm.bins.bin_off[bin + 1];
+                            for (unsigned i = i0; i < i1; ++i) {
+                                int e = sm.bins.list[i];
+                                test_entry(ray, &sm.tile[e], &exacts[e]);
+                            }
+                        }
+                    } else if (E <= kMaxE) {
+                        for (int j = 0; j < E; ++j) test_entry(ray, &sm.tile[j], &exacts[j]);
+                    } else {   // more copies than the tile holds: stream them from the slab
+                        for (int j = 0; j < E; ++j) test_entry(ray, &entries[j], &exacts[j]);
                     }
-                }
-            } else {
-                for (int c = 0; c < nchunks; ++c) {
-                    int n = min(kMaxE, E - c * kMaxE);
-                    if (nchunks > 1) {   // (a single chunk is already resident: emit_copy filled sm.tile)
-                        __syncthreads();
-                        const float4* src = reinterpret_cast<const float4*>(entries + (size_t)c * kMaxE);
-                        float4* dst = reinterpret_cast<float4*>(sm.tile);
-                        for (int i = tid; i < n * 3; i += kThreads) dst[i] = src[i];
-                        __syncthreads();
-                    }
-                    for (int j = 0; j < n; ++j) test_entry(ray, &sm.tile[j], &exacts[(size_t)c * kMaxE + j]);
-                }
-            }
 
-            RayOut o;
-            o.Y = 0, o.P = 0, o.A = CUDART_NAN;
-            if (perez) {
-                const SunConst sc = rp.sun[rp.sun_per_view ? b : 0];
-                sky_eval<kF64>(rp.sky, sc, dx, dy, dz, ray.pitch + kHalfPi, f_theta, o.Y, o.P, o.A);
-            } else if (want_sky) {
-                o.Y = rp.sky.luminance;   // UniformSky: y = luminance, p = 0, a = nan (sky.py:77-79)
+                    RayOut o;
+                    o.Y = 0, o.P = 0, o.A = CUDART_NAN;
+                    if (perez) {
+                        const SunConst sc = rp.sun[rp.sun_per_view ? b : 0];
+                        sky_eval<kF64>(rp.sky, sc, dx, dy, dz, ray.pitch + kHalfPi, f_theta, o.Y, o.P, o.A);
+                    } else if (want_sky) {
+                        o.Y = rp.sky.luminance;   // UniformSky: y = luminance, p = 0, a = nan (sky.py:77-79)
+                    }
+                    // world colour (world.py:79-90, :123)
+                    o.r = CUDART_NAN, o.g = CUDART_NAN, o.b = CUDART_NAN;
+                    const bool from_sky = (rp.flags & ISY_FLAG_INIT_FROM_SKY) && want_sky;
+                    if (rp.init_c || from_sky) {
+                        double lum = rp.init_c ? rp.init_c[b * (size_t)rp.R + rr] : o.Y;
+                        o.r = fmin(fmax(19.0 * lum + 13.0, 0.0), 255.0);      // luminance2skycolour, world.py:479
+                        o.g = fmin(fmax(19.0 * lum + 135.0, 0.0), 255.0);
+                        o.b = fmin(fmax(19.0 * lum + 201.0, 0.0), 255.0);
+                    }
+                    if (ray.pitch >= 0) o.r = 229.0 / 255.0, o.g = 183.0 / 255.0, o.b = 90.0 / 255.0;   // :90
+                    if (ray.hit >= 0) {
+                        const float* col = rp.tri_rgb + 3 * (size_t)ray.hit;
+                        o.r = __ldg(col + 0), o.g = __ldg(col + 1), o.b = __ldg(col + 2);
+                    }
+                    write_view<kF64>(rp, b, rr, valid, ray.hit, ray.best, o);
+                }
             }
-            // world colour (world.py:79-90, :123)
-            o.r = CUDART_NAN, o.g = CUDART_NAN, o.b = CUDART_NAN;
-            const bool from_sky = (rp.flags & ISY_FLAG_INIT_FROM_SKY) && want_sky;
-            if (rp.init_c || from_sky) {
-                double lum = rp.init_c ? rp.init_c[b * (size_t)rp.R + r] : o.Y;
-                o.r = fmin(fmax(19.0 * lum + 13.0, 0.0), 255.0);      // luminance2skycolour, world.py:479
-                o.g = fmin(fmax(19.0 * lum + 135.0, 0.0), 255.0);
-                o.b = fmin(fmax(19.0 * lum + 201.0, 0.0), 255.0);
-            }
-            if (ray.pitch >= 0) o.r = 229.0 / 255.0, o.g = 183.0 / 255.0, o.b = 90.0 / 255.0;   // :90
-            if (ray.hit >= 0) {
-                const float* col = rp.tri_rgb + 3 * (size_t)ray.hit;
-                o.r = __ldg(col + 0), o.g = __ldg(col + 1), o.b = __ldg(col + 2);
-            }
-            write_view<kF64>(rp, b, r, valid, ray.hit, ray.best, o);
+            t_phase[2] += clock64() - t4;
         }
-        __syncthreads();
-        long long t3 = clock64();
-        t_phase[0] += t1 - t0, t_phase[1] += t2 - t1, t_phase[2] += t3 - t2, t_phase[3] += 1;
+        t_phase[0] += t1 - t0, t_phase[1] += t2 - t1, t_phase[3] += 1;
     }
     if (tid == 0) {
         for (int k = 0; k < 4; ++k) atomicAdd(&rp.phase_cycles[k], (unsigned long long)t_phase[k]);

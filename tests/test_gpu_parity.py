@@ -277,6 +277,26 @@ def test_binned_equals_brute_force(ib, seville, sparse, omm1000):
         b = _render_np(r, pos=pos, yaw=yaw_rad, outputs=names, brute_force=True)
         for n in names:
             assert np.array_equal(a[n], b[n], equal_nan=True), n
+        # general (non yaw-only) eye orientations go through the per-position angular bins
+        from scipy.spatial.transform import Rotation as R
+        q = R.from_euler('ZYX', np.c_[yaw_rad.ravel(), rng.uniform(-.4, .4, P * H), rng.uniform(-.3, .3, P * H)])
+        q = q.as_quat().reshape(P, H, 4)
+        a = _render_np(r, pos=pos, quat=q, outputs=names)
+        b = _render_np(r, pos=pos, quat=q, outputs=names, brute_force=True)
+        for n in names:
+            assert np.array_equal(a[n], b[n], equal_nan=True), n
+
+
+def test_large_eye_uses_the_global_winner_buffer(ib, seville):
+    """more rays than the shared-memory winner buffer holds (R > 27648): one heading per group, global buffer"""
+    rng = np.random.RandomState(4)
+    pitch, yaw = o.fibonacci_eye(40000)
+    r = ib.Renderer(seville, ib.EyeLayout.from_angles(pitch, yaw))
+    pos = np.array([[3.3, 6.1, 0.01], [8.45, 6.30, 0.01]])
+    yaw_rad = rng.uniform(-np.pi, np.pi, (2, 3))
+    out = _render_np(r, pos=pos, yaw=yaw_rad, outputs=("hit",))
+    ref = _oracle_views(seville.polygons, pos, yaw_rad, pitch, yaw)
+    assert (out["hit"] != ref).sum() == 0
 
 
 def test_dense_synthetic_world_overflows_the_tile_and_stays_exact(ib):
