@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libisy_b200.so")
+LIB_PATH = os.environ.get("ISY_B200_LIB", os.path.join(HERE, "libisy_b200.so"))   # override: profiling builds
 
 ISY_OK, ISY_ERR_INVALID, ISY_ERR_CUDA, ISY_ERR_WORKSPACE, ISY_ERR_OVERFLOW = 0, -1, -2, -3, -4
 SKY_NONE, SKY_UNIFORM, SKY_PEREZ = 0, 1, 2

@@ -71,8 +71,9 @@ struct isy_eye {
     float* d_w;      // R
     // rays sorted by pitch for the rasteriser
     unsigned int* d_plut;        // kPitchLut + 1
-    void* d_sorted;              // R x {double yaw; float pitch; int ray}
-    int* d_pos_of;               // R
+    void* d_sorted;              // R x float2 (pitch, yaw), pitch order
+    int* d_pos_of;               // R: sorted position of ray r
+    int* d_sorted_ray;           // R: ray at sorted position j
 };
 
 extern "C" {
@@ -116,7 +117,7 @@ int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int3
     if (N * S > (1ll << 30)) return fail(ISY_ERR_INVALID, "isy_eye_create: too many rays");
     DeviceGuard g(device);
     if (!g.ok) return fail(ISY_ERR_CUDA, "isy_eye_create: cannot select CUDA device %d (no CPU fallback)", device);
-    isy_eye* e = new isy_eye{device, N, S, N * S, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    isy_eye* e = new isy_eye{device, N, S, N * S, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t R = (size_t)e->R;
     CUDA_TRY(cudaMalloc(&e->d_quat, R * 4 * sizeof(double)));
     CUDA_TRY(cudaMalloc(&e->d_py, R * 2 * sizeof(double)));
@@ -136,17 +137,21 @@ int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int3
         std::vector<double> py(2 * R);
         CUDA_TRY(cudaMemcpy(py.data(), e->d_py, 2 * R * sizeof(double), cudaMemcpyDeviceToHost));
         struct SortedRay {
-            double yaw;
-            float pitch;
+            float pitch, yaw;
             int32_t ray;
         };
-        static_assert(sizeof(SortedRay) == 16, "SortedRay must be 16 bytes");
         std::vector<SortedRay> sorted(R);
-        for (size_t r = 0; r < R; ++r) sorted[r] = SortedRay{py[2 * r + 1], (float)py[2 * r], (int32_t)r};
+        for (size_t r = 0; r < R; ++r) sorted[r] = SortedRay{(float)py[2 * r], (float)py[2 * r + 1], (int32_t)r};
         std::stable_sort(sorted.begin(), sorted.end(),
                          [](const SortedRay& a, const SortedRay& b) { return a.pitch < b.pitch; });
-        std::vector<int> pos_of(R);
-        for (size_t j = 0; j < R; ++j) pos_of[sorted[j].ray] = (int)j;
+        std::vector<int> pos_of(R), ray_of(R);
+        std::vector<float> hot(2 * R);
+        for (size_t j = 0; j < R; ++j) {
+            pos_of[sorted[j].ray] = (int)j;
+            ray_of[j] = sorted[j].ray;
+            hot[2 * j] = sorted[j].pitch;
+            hot[2 * j + 1] = sorted[j].yaw;
+        }
         const double pi = 3.141592653589793238462643383279502884;
         std::vector<unsigned int> plut(kPitchLut + 1);
         size_t j = 0;
@@ -157,10 +162,12 @@ int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int3
         }
         plut[kPitchLut] = (unsigned int)R;   // the end bound of every run
         CUDA_TRY(cudaMalloc(&e->d_plut, (kPitchLut + 1) * sizeof(unsigned int)));
-        CUDA_TRY(cudaMalloc(&e->d_sorted, R * sizeof(SortedRay)));
+        CUDA_TRY(cudaMalloc(&e->d_sorted, 2 * R * sizeof(float)));
         CUDA_TRY(cudaMalloc(&e->d_pos_of, R * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&e->d_sorted_ray, R * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(e->d_sorted_ray, ray_of.data(), R * sizeof(int), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(e->d_plut, plut.data(), (kPitchLut + 1) * sizeof(unsigned int), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(e->d_sorted, sorted.data(), R * sizeof(SortedRay), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(e->d_sorted, hot.data(), 2 * R * sizeof(float), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(e->d_pos_of, pos_of.data(), R * sizeof(int), cudaMemcpyHostToDevice));
     }
     *out = e;
@@ -177,6 +184,7 @@ int isy_eye_destroy(isy_eye* e) {
     cudaFree(e->d_plut);
     cudaFree(e->d_sorted);
     cudaFree(e->d_pos_of);
+    cudaFree(e->d_sorted_ray);
     delete e;
     return ISY_OK;
 }
@@ -193,7 +201,7 @@ struct Plan {
     int Hg, ngroups;
     int slab_cap;
     bool global_best;
-    size_t off_queue, off_status, off_sun, off_ftheta, off_vis, off_entry, off_exact, off_best, total;
+    size_t off_queue, off_status, off_sun, off_ftheta, off_gtab, off_vis, off_entry, off_exact, off_best, total;
 };
 
 int device_sms(int device) {
@@ -227,6 +235,7 @@ Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
     pl.off_status = off, off += 256;
     pl.off_sun = off, off += align_up((size_t)std::max<int64_t>(P * H, 1) * sizeof(SunConst));
     pl.off_ftheta = off, off += align_up((size_t)e->R * sizeof(double));
+    pl.off_gtab = off, off += align_up((size_t)2 * (kGTab + 1) * sizeof(double2));
     pl.off_vis = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(int));
     pl.off_entry = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(Entry));
     pl.off_exact = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(Exact));
@@ -258,6 +267,7 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
     rp.tri_planes = w->d_planes, rp.tri_rgb = w->d_rgb, rp.T = (int)w->T, rp.horizon = w->horizon;
     rp.eye_py = e->d_py, rp.eye_quat = e->d_quat, rp.eye_w = e->d_w, rp.eye_trig = e->d_trig;
     rp.eye_ftheta = (const double*)(base + pl.off_ftheta);
+    rp.sky_gtab = (const double2*)(base + pl.off_gtab);
     rp.N = (int)e->N, rp.S = e->S, rp.R = (int)e->R;
     rp.P = (int)P, rp.H = (int)H;
     rp.pos = pos, rp.yaw = yaw, rp.vquat = vquat, rp.init_c = init_c;
@@ -274,11 +284,15 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
     rp.slab_cap = pl.slab_cap, rp.splits = pl.splits, rp.items = (int)(P * pl.splits);
     rp.Hg = pl.Hg, rp.ngroups = pl.ngroups;
     rp.grid_plut = e->d_plut, rp.grid_sorted = e->d_sorted, rp.grid_pos_of = e->d_pos_of;
+    rp.grid_sorted_ray = e->d_sorted_ray;
 
     CUDA_TRY(cudaMemsetAsync(base, 0, 512, st));
     if (sp.kind == ISY_SKY_PEREZ) {
         int n = rp.sun_per_view ? (int)(P * H) : 1;
         sun_setup_kernel<<<(n + 127) / 128, 128, 0, st>>>(sun, n, sp, (SunConst*)(base + pl.off_sun));
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        sky_table_kernel<<<(2 * (kGTab + 1) + 127) / 128, 128, 0, st>>>(sp.D, (double2*)(base + pl.off_gtab));
         g_launches++;
         CUDA_TRY(cudaGetLastError());
         if (!vquat) {

@@ -44,8 +44,10 @@ struct Exact {
 
 // rounding budget of the fp32 evaluation of a normalised edge function ("fp32
 // filter bound"): with u = 2^-24, |A|+|B| = 1, |p_theta| <= pi/2, |p_phi| <= pi, |C| <= 2pi:
-// coefficient rounding 3pi*u + query rounding pi*u + two FMA roundings (3pi + 3.5pi)*u < 2.0e-6
-constexpr float kEdgeEps = 3.0e-6f;
+// coefficient rounding 3pi*u + query rounding pi*u + two FMA roundings (3pi + 3.5pi)*u < 2.0e-6.
+// The rasteriser forms the query azimuth in fp32 (yaw_f + heading_f, one wrap by the float 2pi): four more
+// roundings of at most 2^-24 * 2pi plus the float-2pi error 1.75e-7, < 1.1e-6 in total -> < 3.1e-6.
+constexpr float kEdgeEps = 4.0e-6f;
 
 // per-view sun constants (sky.py:304-321, 501-521), computed once per view by sun_setup_kernel
 struct SunConst {
@@ -72,7 +74,8 @@ struct RenderParams {
     const float* eye_w;      // [R]
     // the eye's rays sorted by pitch, for the rasteriser (null = not available)
     const unsigned int* grid_plut;        // [kPitchLut + 1] first sorted ray at or above each pitch slot
-    const void* grid_sorted;              // [R] {double yaw; float pitch; int ray} in pitch order
+    const void* grid_sorted;              // [R] float2 (pitch, yaw) of the rays in pitch order
+    const int* grid_sorted_ray;           // [R] ray index of each sorted position
     const int* grid_pos_of;               // [R] sorted position of ray r
     int N, S, R;
     // views
@@ -82,6 +85,7 @@ struct RenderParams {
     const double* vquat;     // [P][H][4] or null
     const double* init_c;    // [B][R] external background luminance (world.py:79-82) or null
     const SunConst* sun;     // [1] or [B]
+    const double2* sky_gtab; // [2][kGTab + 1] Hermite table of exp(D acos c) for this call's sky (workspace)
     int sun_per_view;
     isy_sky_params sky;
     uint32_t flags;
@@ -243,10 +247,33 @@ __device__ __forceinline__ double acos_newton(double c) {
 // kPrecise = false: float outputs. Luminance keeps the fp64 core (gamma, exp); the polarisation
 //                   finish (one atan2, two divisions) runs in fp32 on fp64-rounded operands, which
 //                   bounds the added error by ~1e-6 (DESIGN.md "sky error budget"), inside the 1e-5 bar.
+constexpr int kGTab = 256;   // intervals of the G(c) = exp(D acos c) table, per half (c >= 0, c < 0)
+
+// G(c) = exp(D * acos(c)), the only place the angular distance to the sun enters the luminance
+// (sky.py:308 via :372), from a cubic Hermite table in u = sqrt(1 - |c|): acos(1 - u^2) = 2 asin(u / sqrt 2)
+// is analytic on [0, 1], so 256 intervals give |error| < 1e-9 for any |D| < 4 (tests/test_oracle.py checks the
+// construction on the CPU, DESIGN.md "sky error budget").  tab[half][i] = {G(u_i), dG/du(u_i) * h}.
+__device__ __forceinline__ double g_table_eval(const double2* __restrict__ tab, double c) {
+    const double x = 1.0 - fabs(c);
+    double u = 0.0;
+    if (x > 1e-30) {   // sqrt(x): float rsqrt seed + one Newton step in fp64 (relative error ~1e-14)
+        const double r0 = (double)rsqrtf((float)x);
+        u = x * (r0 * (1.5 - 0.5 * x * r0 * r0));
+    }
+    const double um = u * (double)kGTab;
+    const int idx = min((int)um, kGTab - 1);
+    const double t = um - (double)idx;
+    const double2* tb = tab + (c < 0.0 ? kGTab + 1 : 0) + idx;
+    const double2 a = tb[0], b = tb[1];
+    const double c2 = 3.0 * (b.x - a.x) - 2.0 * a.y - b.y;
+    const double c3 = 2.0 * (a.x - b.x) + a.y + b.y;
+    return fma(t, fma(t, fma(t, c3, c2), a.y), a.x);
+}
+
 template <bool kPrecise>
 __device__ __forceinline__ void sky_eval(const isy_sky_params& sp, const SunConst& sc, double dx, double dy, double dz,
                                          double theta, double f_theta, double& Y, double& P, double& A,
-                                         bool masked = false) {
+                                         bool masked = false, const double2* __restrict__ gtab = nullptr) {
     double cg = dz * sc.sz + (dx * sc.sx + dy * sc.sy);      // cos(gamma), sky.py:304-305
     cg = fmin(fmax(cg, -1.0), 1.0);
     const double cos_t = dz;
@@ -261,8 +288,9 @@ __device__ __forceinline__ void sky_eval(const isy_sky_params& sp, const SunCons
         P = fmin(fmax(p, 0.0), 1.0);
         A = wrap_pi_numpy(atan2(dy - sc.sy, dx - sc.sx) + kHalfPi);                 // sky.py:320-324
     } else {
-        gamma = acos_newton(cg);
-        const double i_prez = f_theta * perez_phi(gamma, cg, sp.C, sp.D, sp.E);
+        // gamma itself is never needed: exp(D gamma) comes from the table, the sun disc is a test on cos(gamma)
+        gamma = cg > 0.99862953475457383 ? 0.0 : kPi;                    // cos(pi / 60)
+        const double i_prez = f_theta * (1.0 + sp.C * g_table_eval(gtab, cg) + sp.E * (cg * cg));
         Y = fmax(sc.Yz * i_prez * sc.inv_i00, 0.0);
         const float cg2 = (float)(cg * cg);
         const float lp = fmaxf(1.0f - cg2, 0.0f) / (1.0f + cg2);

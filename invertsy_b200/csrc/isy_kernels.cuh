@@ -23,7 +23,7 @@ namespace isy {
 
 constexpr int kThreads = 512;         // CTA size (16 warps), one persistent CTA per SM
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxE = 1280;           // projected copies resident in shared memory (60 KB)
+constexpr int kMaxE = 1152;           // projected copies resident in shared memory (54 KB)
 constexpr int kBinRows = 32;          // finest angular grid over the vegetation band
 constexpr int kBinCols = 128;         // ... and over azimuth [-pi, pi]
 constexpr int kBins = kBinRows * kBinCols;
@@ -35,7 +35,7 @@ constexpr float kBinReject = -1e-5f;  // a bin is dropped only if an edge functi
 constexpr int kBestCap = 36864;       // (heading, ray) slots of the rasteriser's winner buffer (u16 ranks, 72 KB)
 constexpr int kGridRaysSmem = 1280;   // eyes up to this many rays keep their pitch-sorted ray table in shared memory
 constexpr int kPitchLut = 1024;       // slots of the pitch -> first sorted ray look-up table
-constexpr int kHeadLut = 256;         // slots of the azimuth -> first sorted heading look-up table
+constexpr int kHeadLut = 1024;        // slots of the azimuth -> first sorted heading look-up table
 
 struct SmemBins {
     unsigned int bin_off[kBins + 4];  // exclusive offsets into list (counts during the count pass)
@@ -45,17 +45,19 @@ struct SmemBins {
 
 struct SmemRaster {
     unsigned short best[kBestCap];    // nearest containing copy (slot in tile) per (heading, sorted ray)
-    double2 sorted[kGridRaysSmem];    // the eye's rays in pitch order: {yaw, (pitch | ray)} (copied once per CTA)
+    float2 sorted[kGridRaysSmem];     // the eye's rays in pitch order: (pitch, yaw) as floats (copied once per CTA)
     unsigned int plut[kPitchLut + 4]; // first sorted ray at or above each pitch slot
     float hsort[2 * kMaxH];           // wrapped headings of the group, ascending, then the same + 2 pi
+    float hvalf[2 * kMaxH];           // the wrapped heading itself (no + 2 pi) of each sorted slot
     unsigned char hperm[2 * kMaxH];   // heading index of each sorted slot
-    unsigned short hlut[kHeadLut];    // first sorted slot at or above each azimuth slot
+    unsigned short hlut[kHeadLut];    // first sorted slot that can reach each azimuth slot
 };
 
 struct SmemLayout {
     Entry tile[kMaxE];
     float4 bbox[kMaxE];               // (theta_lo, theta_hi, phi_lo, phi_hi) of each copy, margin included
     double head_sin[kMaxH], head_cos[kMaxH], head_val[kMaxH];   // per heading of the current group
+    double2 gtab[2 * (kGTab + 1)];    // exp(D acos c) table of this call's sky (copied once per CTA)
     union {
         SmemBins bins;
         SmemRaster ras;
@@ -97,6 +99,25 @@ __global__ void eye_sky_kernel(const double* __restrict__ py, const double* __re
     if (r >= R) return;
     double theta = py[2 * r] + kHalfPi;
     f_theta[r] = perez_f(-trig[4 * r + 0], theta < kHalfPi, sp.A, sp.B);   // cos(theta) = -sin(pitch)
+}
+
+// Hermite table of G(c) = exp(D acos c) in u = sqrt(1 - |c|), see g_table_eval
+__global__ void sky_table_kernel(double D, double2* __restrict__ tab) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * (kGTab + 1)) return;
+    const int half = i / (kGTab + 1), k = i - half * (kGTab + 1);
+    const double h = 1.0 / kGTab, u = k * h;
+    const double g = 2.0 * asin(u * 0.70710678118654752440);       // acos(1 - u^2)
+    const double dg = 2.0 / sqrt(2.0 - u * u);                     // d gamma / du
+    double2 v;
+    if (half == 0) {
+        v.x = exp(D * g);
+        v.y = v.x * D * dg * h;
+    } else {                                                       // c < 0: gamma = pi - g
+        v.x = exp(D * (kPi - g));
+        v.y = -v.x * D * dg * h;
+    }
+    tab[i] = v;
 }
 
 // per-view sun constants (sky.py:309-312, 320-321, 501-521)
@@ -454,6 +475,7 @@ __device__ __forceinline__ void write_view(const RenderParams& rp, size_t b, int
 // ALL headings of the position at once; nothing is built per position beyond the ranks.
 // ------------------------------------------------------------------------------------------
 constexpr unsigned int kNoCopy = 0xffffu;
+constexpr int kRU = 4;                // rays per lane and iteration in the rasteriser
 
 // is copy e (distance d, triangle tri) nearer than copy c? (ties: lower triangle index, then lower slot)
 __device__ __forceinline__ bool nearer(const Entry* tile, double d, int tri, unsigned int e, unsigned int c) {
@@ -500,26 +522,34 @@ __device__ void sort_headings(SmemLayout& sm, int Hcur) {
         }
         sm.ras.hsort[pos] = h;
         sm.ras.hsort[pos + Hcur] = h + (float)kTwoPi;
+        sm.ras.hvalf[pos] = h;
+        sm.ras.hvalf[pos + Hcur] = h;
         sm.ras.hperm[pos] = (unsigned char)tid;
         sm.ras.hperm[pos + Hcur] = (unsigned char)tid;
     }
     __syncthreads();
-    if (tid < kHeadLut) {
-        const float start = -(float)kPi + tid * ((float)kTwoPi / kHeadLut) - 1e-4f;
+    for (int s = tid; s < kHeadLut; s += kThreads) {
+        // first sorted slot whose heading is not below this azimuth slot (minus a guard band):
+        // windows start their walk here; whatever they pick up below `lower` just fails the edge test
+        const float start = -(float)kPi + s * ((float)kTwoPi / kHeadLut) - 1e-4f;
         int k = 0;
         while (k < 2 * Hcur && sm.ras.hsort[k] < start) ++k;
-        sm.ras.hlut[tid] = (unsigned short)k;
+        sm.ras.hlut[s] = (unsigned short)k;
     }
 }
 
-// kSmem: the eye's sorted ray table and the winner buffer live in shared memory (u16 ranks);
-// otherwise both are in global memory (u32 ranks), for eyes too large for that.
+// kSmem: the eye's sorted ray table and the winner buffer live in shared memory (u16 slots);
+// otherwise both are in global memory (u32 slots), for eyes too large for that.
+// The hot path is fp32: query azimuth = fl(yaw_f + heading_f) wrapped in fp32; kEdgeEps covers that
+// rounding.  Rays that land within 3e-6 rad of the +-pi seam, and rays inside the rounding band of
+// an edge, redo the query in fp64 exactly as the reference composes it.
 template <bool kSmem>
 __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest, const Exact* exacts, int E,
                               int Hcur, int* s_next) {
     const int R = rp.R, lane = threadIdx.x & 31;
-    const double2* gsorted = reinterpret_cast<const double2*>(rp.grid_sorted);
+    const float2* gsorted = reinterpret_cast<const float2*>(rp.grid_sorted);
     const int H2 = 2 * Hcur;
+    const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
     for (;;) {
         // copies differ a lot in size (a near blade spans hundreds of rays): warps pull them from a counter
         int e = 0;
@@ -528,9 +558,9 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
         if (e >= E) break;
         const float4 bb = sm.bbox[e];
         // azimuth window of the copy clipped to the query domain (-pi, pi]
-        const float glo = fmaxf(bb.z, -(float)kPi - kBinMargin), ghi = fminf(bb.w, (float)kPi + kBinMargin);
+        const float glo = fmaxf(bb.z, -pi_f - kBinMargin) - kBinMargin, ghi = fminf(bb.w, pi_f + kBinMargin) + kBinMargin;
         if (glo > ghi) continue;
-        const float width = ghi - glo + 2.f * kBinMargin;
+        const float width = ghi - glo;
         const Entry ent = sm.tile[e];
         const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
         // run of pitch-sorted rays that covers [bb.x, bb.y] (a few extra rays at both ends)
@@ -538,62 +568,90 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
         const int s1 = min(max((int)floorf((bb.y + (float)kHalfPi) * (kPitchLut / (float)kPi)) + 2, 0), kPitchLut);
         const unsigned jbeg = kSmem ? sm.ras.plut[s0] : __ldg(rp.grid_plut + s0);
         const unsigned jend = kSmem ? sm.ras.plut[s1] : __ldg(rp.grid_plut + s1);
-        for (unsigned jb = jbeg; jb < jend; jb += 32) {      // warp-uniform trip count
-            __syncwarp();                                    // keep the lanes converged across iterations
-            const unsigned j = jb + lane;
-            double2 sr = make_double2(0.0, 0.0);
-            float fp = 2.f * (float)kPi;
-            if (j < jend) {
-                sr = kSmem ? sm.ras.sorted[j] : __ldg(gsorted + j);
-                fp = __int_as_float(__double2loint(sr.y));
+        // kRU rays per lane and iteration: their window walks and edge tests are independent
+        // instruction streams, which is what hides the shared-memory and branch latencies here
+        for (unsigned jb = jbeg; jb < jend; jb += 32 * kRU) {   // warp-uniform trip count
+            __syncwarp();                                       // keep the lanes converged across iterations
+            float2 py[kRU];
+            int k[kRU];
+            float upper[kRU];
+#pragma unroll
+            for (int u = 0; u < kRU; ++u) {
+                const unsigned j = jb + u * 32 + lane;
+                py[u] = make_float2(4.f, 0.f);                  // pitch 4 rad: outside every band
+                if (j < jend) py[u] = kSmem ? sm.ras.sorted[j] : __ldg(gsorted + j);
             }
-            int k = H2, kend = H2;
-            float upper = 0.f;
-            if (fp >= bb.x && fp <= bb.y) {
-                // headings h with yaw + h in [glo - m, ghi + m]  <=>  h in [lower, lower + width] on the circle
-                float lower = glo - kBinMargin - (float)sr.x;
-                if (lower < -(float)kPi) lower += (float)kTwoPi;
-                else if (lower >= (float)kPi) lower -= (float)kTwoPi;
-                const int ls = min(max((int)((lower + (float)kPi) * (kHeadLut / (float)kTwoPi)), 0), kHeadLut - 1);
-                k = sm.ras.hlut[ls];
-                while (k < H2 && sm.ras.hsort[k] < lower) ++k;
-                upper = lower + width;
-                kend = k;
-                while (kend < H2 && sm.ras.hsort[kend] <= upper) ++kend;
+#pragma unroll
+            for (int u = 0; u < kRU; ++u) {
+                // headings h with yaw + h in [glo, ghi]  <=>  h in [lower, lower + width] on the circle
+                float lower = glo - py[u].y;
+                if (lower < -pi_f) lower += twopi_f;
+                else if (lower >= pi_f) lower -= twopi_f;
+                const int ls = min(max((int)((lower + pi_f) * (kHeadLut / twopi_f)), 0), kHeadLut - 1);
+                const bool band = py[u].x >= bb.x && py[u].x <= bb.y;
+                k[u] = band ? (int)sm.ras.hlut[ls] : H2;
+                upper[u] = lower + width;
             }
             // lanes walk their heading windows in lock step (most windows hold 0 or 1 heading)
-            while (__any_sync(0xffffffffu, k < kend)) {
-                if (k < kend) {
-                    const int hh = sm.ras.hperm[k];
-                    double yg = sr.x + sm.head_val[hh];         // both in (-pi, pi]: one shift wraps
-                    if (yg > kPi) yg -= kTwoPi;
-                    else if (yg <= -kPi) yg += kTwoPi;
-                    const float fy = (float)yg;
-                    float e0 = fmaf(ent.A0, fp, fmaf(ent.B0, fy, ent.C0));
-                    float e1 = fmaf(ent.A1, fp, fmaf(ent.B1, fy, ent.C1));
-                    float e2 = fmaf(ent.A2, fp, fmaf(ent.B2, fy, ent.C2));
-                    float m = fminf(e0, fminf(e1, e2));
-                    if (m >= -kEdgeEps) {
-                        bool in = m > kEdgeEps;
-                        if (!in) {
-                            const int ray = __double2hiint(sr.y);
-                            in = inside_exact(exacts[e], rp.eye_py[2 * (size_t)ray], yg);
+            for (;;) {
+                bool act[kRU], any = false;
+                float hv[kRU];
+#pragma unroll
+                for (int u = 0; u < kRU; ++u) {
+                    const int kk = min(k[u], H2 - 1);
+                    act[u] = k[u] < H2 && sm.ras.hsort[kk] <= upper[u];
+                    hv[u] = sm.ras.hvalf[kk];
+                    any |= act[u];
+                }
+                if (!__any_sync(0xffffffffu, any)) break;
+                float fy[kRU], m[kRU];
+#pragma unroll
+                for (int u = 0; u < kRU; ++u) {                 // branch-free: the common case of every slot
+                    float f = py[u].y + hv[u];                  // both in (-pi, pi]: one shift wraps
+                    f = f > pi_f ? f - twopi_f : (f <= -pi_f ? f + twopi_f : f);
+                    fy[u] = f;
+                    const float e0 = fmaf(ent.A0, py[u].x, fmaf(ent.B0, f, ent.C0));
+                    const float e1 = fmaf(ent.A1, py[u].x, fmaf(ent.B1, f, ent.C1));
+                    const float e2 = fmaf(ent.A2, py[u].x, fmaf(ent.B2, f, ent.C2));
+                    m[u] = fminf(e0, fminf(e1, e2));
+                }
+#pragma unroll
+                for (int u = 0; u < kRU; ++u) {
+                    // slow part: a hit, the rounding band of an edge, or a query within 3e-6 rad of the seam
+                    const bool seam = fabsf(fy[u]) > 3.14159f;
+                    if (act[u] && (seam || m[u] >= -kEdgeEps)) {
+                        const unsigned j = jb + u * 32 + lane;
+                        const int hh = sm.ras.hperm[k[u]];
+                        bool in = m[u] > kEdgeEps && !seam;
+                        if (!in) {   // redo the query in fp64 exactly as the reference composes it
+                            const int ray = __ldg(rp.grid_sorted_ray + j);
+                            double yg = rp.eye_py[2 * (size_t)ray + 1] + sm.head_val[hh];
+                            if (yg > kPi) yg -= kTwoPi;
+                            else if (yg <= -kPi) yg += kTwoPi;
+                            if (seam) {
+                                const float f = (float)yg;
+                                const float e0 = fmaf(ent.A0, py[u].x, fmaf(ent.B0, f, ent.C0));
+                                const float e1 = fmaf(ent.A1, py[u].x, fmaf(ent.B1, f, ent.C1));
+                                const float e2 = fmaf(ent.A2, py[u].x, fmaf(ent.B2, f, ent.C2));
+                                const float mm = fminf(e0, fminf(e1, e2));
+                                in = mm > kEdgeEps;
+                                if (!in && mm >= -kEdgeEps) in = inside_exact(exacts[e], rp.eye_py[2 * (size_t)ray], yg);
+                            } else {
+                                in = inside_exact(exacts[e], rp.eye_py[2 * (size_t)ray], yg);
+                            }
                         }
                         if (in) {
                             if (kSmem) post_copy_u16(sm.ras.best, (unsigned)hh * R + j, sm.tile, dist, ent.tri, e);
                             else post_copy_u32(&gbest[(size_t)hh * R + j], sm.tile, dist, ent.tri, e);
                         }
                     }
-                    ++k;
+                    if (act[u]) ++k[u];
                 }
             }
         }
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// the render kernel
-// ------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------
 // final pass of the rasteriser path, float outputs, one sample per ommatidium: per ray pick the
 // winner from best[], shade, evaluate the sky and write the view (the only HBM traffic).
@@ -640,7 +698,7 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
                 const double hs = sm.head_sin[hh], hcs = sm.head_cos[hh];
                 const double sy = t4v.z * hcs + t4v.w * hs, cy = t4v.w * hcs - t4v.z * hs;   // yaw_e + heading
                 const SunConst sc = rp.sun[rp.sun_per_view ? (size_t)p * rp.H + h0 + hh : 0];
-                sky_eval<false>(rp.sky, sc, t4v.y * cy, t4v.y * sy, -t4v.x, e_pitch + kHalfPi, f_theta, Y, P, A);
+                sky_eval<false>(rp.sky, sc, t4v.y * cy, t4v.y * sy, -t4v.x, e_pitch + kHalfPi, f_theta, Y, P, A, false, sm.gtab);
             } else if (uniform) {
                 Y = rp.sky.luminance;
             }
@@ -696,7 +754,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
     const bool smem_grid = raster_ok && !gbest;
     bool grid_loaded = false;
 
-    long long t_phase[4] = {0, 0, 0, 0};   // project, accel (bins / ranks + raster), final ray pass, positions
+    if (perez) {
+        for (int i = tid; i < 2 * (kGTab + 1); i += kThreads) sm.gtab[i] = rp.sky_gtab[i];
+    }
+    long long t_phase[4] = {0, 0, 0, 0};   // project, accel (bins / raster), final ray pass, positions
     for (;;) {
         __syncthreads();
         if (tid == 0) s_item = atomicAdd(rp.queue, 1u);
@@ -716,7 +777,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                 if (smem_grid && !grid_loaded) {   // the bins path shares this memory: (re)load when needed
                     for (int i = tid; i <= kPitchLut; i += kThreads) sm.ras.plut[i] = rp.grid_plut[i];
                     for (int i = tid; i < rp.R; i += kThreads)
-                        sm.ras.sorted[i] = reinterpret_cast<const double2*>(rp.grid_sorted)[i];
+                        sm.ras.sorted[i] = reinterpret_cast<const float2*>(rp.grid_sorted)[i];
                     grid_loaded = true;
                 }
             } else if (build_bins(sm, grid, E, s_band, s_warp)) {
@@ -847,7 +908,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                     o.Y = 0, o.P = 0, o.A = CUDART_NAN;
                     if (perez) {
                         const SunConst sc = rp.sun[rp.sun_per_view ? b : 0];
-                        sky_eval<kF64>(rp.sky, sc, dx, dy, dz, ray.pitch + kHalfPi, f_theta, o.Y, o.P, o.A);
+                        sky_eval<kF64>(rp.sky, sc, dx, dy, dz, ray.pitch + kHalfPi, f_theta, o.Y, o.P, o.A, false, sm.gtab);
                     } else if (want_sky) {
                         o.Y = rp.sky.luminance;   // UniformSky: y = luminance, p = 0, a = nan (sky.py:77-79)
                     }
