@@ -46,8 +46,9 @@ struct Exact {
 // filter bound"): with u = 2^-24, |A|+|B| = 1, |p_theta| <= pi/2, |p_phi| <= pi, |C| <= 2pi:
 // coefficient rounding 3pi*u + query rounding pi*u + two FMA roundings (3pi + 3.5pi)*u < 2.0e-6.
 // The rasteriser forms the query azimuth in fp32 (yaw_f + heading_f, one wrap by the float 2pi): four more
-// roundings of at most 2^-24 * 2pi plus the float-2pi error 1.75e-7, < 1.1e-6 in total -> < 3.1e-6.
-constexpr float kEdgeEps = 4.0e-6f;
+// roundings of at most 2^-24 * 2pi plus the float-2pi error 1.75e-7, < 1.1e-6 in total -> < 3.1e-6;
+// evenly spaced headings are formed as fma(k, delta, h0), at most 7.5e-7 from the true heading (5e-7 admitted by the uniformity check) -> < 3.9e-6.
+constexpr float kEdgeEps = 5.0e-6f;
 
 // per-view sun constants (sky.py:304-321, 501-521), computed once per view by sun_setup_kernel
 struct SunConst {

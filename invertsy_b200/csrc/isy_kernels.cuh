@@ -19,9 +19,13 @@
 #pragma once
 #include "isy_common.cuh"
 
+#ifndef ISY_THREADS
+#define ISY_THREADS 512
+#endif
+
 namespace isy {
 
-constexpr int kThreads = 512;         // CTA size (16 warps), one persistent CTA per SM
+constexpr int kThreads = ISY_THREADS;  // CTA size, one persistent CTA per SM
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxE = 1152;           // projected copies resident in shared memory (54 KB)
 constexpr int kBinRows = 32;          // finest angular grid over the vegetation band
@@ -32,7 +36,7 @@ constexpr int kMaxH = 128;            // headings whose sin/cos are cached per p
 constexpr float kBinMargin = 1e-4f;   // rad; >> every fp32 rounding in the bin arithmetic
 constexpr float kBinReject = -1e-5f;  // a bin is dropped only if an edge function is below this on all of it
 
-constexpr int kBestCap = 36864;       // (heading, ray) slots of the rasteriser's winner buffer (u16 ranks, 72 KB)
+constexpr int kBestCap = 36864;       // (heading, ray) slots of the rasteriser's winner buffer (u16 copy slots, 72 KB)
 constexpr int kGridRaysSmem = 1280;   // eyes up to this many rays keep their pitch-sorted ray table in shared memory
 constexpr int kPitchLut = 1024;       // slots of the pitch -> first sorted ray look-up table
 constexpr int kHeadLut = 1024;        // slots of the azimuth -> first sorted heading look-up table
@@ -44,13 +48,15 @@ struct SmemBins {
 };
 
 struct SmemRaster {
-    unsigned short best[kBestCap];    // nearest containing copy (slot in tile) per (heading, sorted ray)
+    unsigned short best[kBestCap];    // nearest containing copy (slot in tile) per (sorted heading, sorted ray)
     float2 sorted[kGridRaysSmem];     // the eye's rays in pitch order: (pitch, yaw) as floats (copied once per CTA)
     unsigned int plut[kPitchLut + 4]; // first sorted ray at or above each pitch slot
     float hsort[2 * kMaxH];           // wrapped headings of the group, ascending, then the same + 2 pi
     float hvalf[2 * kMaxH];           // the wrapped heading itself (no + 2 pi) of each sorted slot
     unsigned char hperm[2 * kMaxH];   // heading index of each sorted slot
+    unsigned char hinv[kMaxH];        // sorted slot of each heading
     unsigned short hlut[kHeadLut];    // first sorted slot that can reach each azimuth slot
+    float uni[4];                     // {h0, delta, 1/delta, flag}: sorted headings are h0 + k*delta over the full circle
 };
 
 struct SmemLayout {
@@ -324,9 +330,10 @@ __device__ __forceinline__ void bin_pass(SmemLayout& sm, const BinGrid& g, int E
 
 // exclusive scan of bin_off[0..nb) in place (nb multiple of kThreads); returns the total
 __device__ unsigned int block_scan_bins(SmemLayout& sm, int nb, unsigned int* s_warp) {
+    constexpr int kScan = 512;         // threads that take part (kThreads >= 512)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = nb / kThreads;     // 8 (fine) or 2 (coarse)
-    unsigned int local[kBins / kThreads];
+    const int per = tid < kScan ? nb / kScan : 0;     // 8 (fine) or 2 (coarse)
+    unsigned int local[kBins / kScan];
     unsigned int sum = 0;
     for (int i = 0; i < per; ++i) {
         local[i] = sm.bins.bin_off[tid * per + i];
@@ -351,7 +358,7 @@ __device__ unsigned int block_scan_bins(SmemLayout& sm, int nb, unsigned int* s_
         sm.bins.bin_cur[tid * per + i] = run;
         run += local[i];
     }
-    if (tid == kThreads - 1) sm.bins.bin_off[nb] = run;
+    if (tid == kScan - 1) sm.bins.bin_off[nb] = run;
     __syncthreads();
     return total;
 }
@@ -526,8 +533,18 @@ __device__ void sort_headings(SmemLayout& sm, int Hcur) {
         sm.ras.hvalf[pos + Hcur] = h;
         sm.ras.hperm[pos] = (unsigned char)tid;
         sm.ras.hperm[pos + Hcur] = (unsigned char)tid;
+        sm.ras.hinv[tid] = (unsigned char)pos;
     }
     __syncthreads();
+    if (tid == 0) {
+        // evenly spaced headings over the full circle (every scan of the reference's simulations, and a
+        // single heading) let the window walk use arithmetic instead of the look-up table
+        const float h0 = sm.ras.hsort[0];
+        const float delta = (float)kTwoPi / (float)Hcur;
+        bool ok = true;
+        for (int k = 1; k < Hcur; ++k) ok = ok && fabsf(sm.ras.hsort[k] - (h0 + k * delta)) < 5e-7f;
+        sm.ras.uni[0] = h0, sm.ras.uni[1] = delta, sm.ras.uni[2] = 1.0f / delta, sm.ras.uni[3] = ok ? 1.f : 0.f;
+    }
     for (int s = tid; s < kHeadLut; s += kThreads) {
         // first sorted slot whose heading is not below this azimuth slot (minus a guard band):
         // windows start their walk here; whatever they pick up below `lower` just fails the edge test
@@ -543,13 +560,14 @@ __device__ void sort_headings(SmemLayout& sm, int Hcur) {
 // The hot path is fp32: query azimuth = fl(yaw_f + heading_f) wrapped in fp32; kEdgeEps covers that
 // rounding.  Rays that land within 3e-6 rad of the +-pi seam, and rays inside the rounding band of
 // an edge, redo the query in fp64 exactly as the reference composes it.
-template <bool kSmem>
+template <bool kSmem, bool kUniform>
 __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest, const Exact* exacts, int E,
                               int Hcur, int* s_next) {
     const int R = rp.R, lane = threadIdx.x & 31;
     const float2* gsorted = reinterpret_cast<const float2*>(rp.grid_sorted);
     const int H2 = 2 * Hcur;
     const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
+    const float uh0 = sm.ras.uni[0], udelta = sm.ras.uni[1], uinv = sm.ras.uni[2];
     for (;;) {
         // copies differ a lot in size (a near blade spans hundreds of rays): warps pull them from a counter
         int e = 0;
@@ -572,6 +590,9 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
         // instruction streams, which is what hides the shared-memory and branch latencies here
         for (unsigned jb = jbeg; jb < jend; jb += 32 * kRU) {   // warp-uniform trip count
             __syncwarp();                                       // keep the lanes converged across iterations
+#ifdef ISY_DBG_COUNT
+            if (lane == 0) atomicAdd(&rp.phase_cycles[4], 1ull);
+#endif
             float2 py[kRU];
             int k[kRU];
             float upper[kRU];
@@ -587,23 +608,43 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
                 float lower = glo - py[u].y;
                 if (lower < -pi_f) lower += twopi_f;
                 else if (lower >= pi_f) lower -= twopi_f;
-                const int ls = min(max((int)((lower + pi_f) * (kHeadLut / twopi_f)), 0), kHeadLut - 1);
                 const bool band = py[u].x >= bb.x && py[u].x <= bb.y;
-                k[u] = band ? (int)sm.ras.hlut[ls] : H2;
-                upper[u] = lower + width;
+                if (kUniform) {
+                    // headings are h0 + k*delta (k mod H): the window is the index range [k, upper]
+                    const float a = (lower - uh0) * uinv;
+                    k[u] = band ? (int)ceilf(a - 2e-4f) : 1;
+                    upper[u] = band ? floorf(fmaf(width, uinv, a) + 2e-4f) : 0.f;
+                } else {
+                    const int ls = min(max((int)((lower + pi_f) * (kHeadLut / twopi_f)), 0), kHeadLut - 1);
+                    k[u] = band ? (int)sm.ras.hlut[ls] : H2;
+                    upper[u] = lower + width;
+                }
             }
             // lanes walk their heading windows in lock step (most windows hold 0 or 1 heading)
             for (;;) {
                 bool act[kRU], any = false;
                 float hv[kRU];
+                int ks[kRU];    // sorted slot of the heading
 #pragma unroll
                 for (int u = 0; u < kRU; ++u) {
-                    const int kk = min(k[u], H2 - 1);
-                    act[u] = k[u] < H2 && sm.ras.hsort[kk] <= upper[u];
-                    hv[u] = sm.ras.hvalf[kk];
+                    if (kUniform) {
+                        act[u] = (float)k[u] <= upper[u];
+                        ks[u] = k[u] < 0 ? k[u] + Hcur : (k[u] >= Hcur ? k[u] - Hcur : k[u]);   // k in [-H, 2H)
+                        ks[u] = min(max(ks[u], 0), Hcur - 1);
+                        hv[u] = fmaf((float)ks[u], udelta, uh0);
+                    } else {
+                        const int kk = min(k[u], H2 - 1);
+                        act[u] = k[u] < H2 && sm.ras.hsort[kk] <= upper[u];
+                        hv[u] = sm.ras.hvalf[kk];
+                        ks[u] = kk >= Hcur ? kk - Hcur : kk;       // the + 2 pi copy is the same heading
+                    }
                     any |= act[u];
                 }
                 if (!__any_sync(0xffffffffu, any)) break;
+#ifdef ISY_DBG_COUNT
+                if (lane == 0) atomicAdd(&rp.phase_cycles[5], 1ull);
+                for (int u = 0; u < kRU; ++u) if (act[u]) atomicAdd(&rp.phase_cycles[6], 1ull);
+#endif
                 float fy[kRU], m[kRU];
 #pragma unroll
                 for (int u = 0; u < kRU; ++u) {                 // branch-free: the common case of every slot
@@ -617,34 +658,33 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
                 }
 #pragma unroll
                 for (int u = 0; u < kRU; ++u) {
-                    // slow part: a hit, the rounding band of an edge, or a query within 3e-6 rad of the seam
+                    const unsigned j = jb + u * 32 + lane;
                     const bool seam = fabsf(fy[u]) > 3.14159f;
-                    if (act[u] && (seam || m[u] >= -kEdgeEps)) {
-                        const unsigned j = jb + u * 32 + lane;
-                        const int hh = sm.ras.hperm[k[u]];
-                        bool in = m[u] > kEdgeEps && !seam;
-                        if (!in) {   // redo the query in fp64 exactly as the reference composes it
-                            const int ray = __ldg(rp.grid_sorted_ray + j);
-                            double yg = rp.eye_py[2 * (size_t)ray + 1] + sm.head_val[hh];
-                            if (yg > kPi) yg -= kTwoPi;
-                            else if (yg <= -kPi) yg += kTwoPi;
-                            if (seam) {
-                                const float f = (float)yg;
-                                const float e0 = fmaf(ent.A0, py[u].x, fmaf(ent.B0, f, ent.C0));
-                                const float e1 = fmaf(ent.A1, py[u].x, fmaf(ent.B1, f, ent.C1));
-                                const float e2 = fmaf(ent.A2, py[u].x, fmaf(ent.B2, f, ent.C2));
-                                const float mm = fminf(e0, fminf(e1, e2));
-                                in = mm > kEdgeEps;
-                                if (!in && mm >= -kEdgeEps) in = inside_exact(exacts[e], rp.eye_py[2 * (size_t)ray], yg);
-                            } else {
-                                in = inside_exact(exacts[e], rp.eye_py[2 * (size_t)ray], yg);
-                            }
-                        }
-                        if (in) {
-                            if (kSmem) post_copy_u16(sm.ras.best, (unsigned)hh * R + j, sm.tile, dist, ent.tri, e);
-                            else post_copy_u32(&gbest[(size_t)hh * R + j], sm.tile, dist, ent.tri, e);
-                        }
+                    bool in = act[u] && m[u] > kEdgeEps && !seam;
+                    // rare: the rounding band of an edge, or a query within 3e-6 rad of the seam ->
+                    // redo the query in fp64 exactly as the reference composes it
+                    if (act[u] && (seam || (m[u] >= -kEdgeEps && m[u] <= kEdgeEps))) {
+                        const int hh = sm.ras.hperm[ks[u]];
+                        const int ray = __ldg(rp.grid_sorted_ray + j);
+                        double yg = rp.eye_py[2 * (size_t)ray + 1] + sm.head_val[hh];
+                        if (yg > kPi) yg -= kTwoPi;
+                        else if (yg <= -kPi) yg += kTwoPi;
+                        const float f = (float)yg;
+                        const float e0 = fmaf(ent.A0, py[u].x, fmaf(ent.B0, f, ent.C0));
+                        const float e1 = fmaf(ent.A1, py[u].x, fmaf(ent.B1, f, ent.C1));
+                        const float e2 = fmaf(ent.A2, py[u].x, fmaf(ent.B2, f, ent.C2));
+                        const float mm = fminf(e0, fminf(e1, e2));
+                        in = mm > kEdgeEps;
+                        if (!in && mm >= -kEdgeEps) in = inside_exact(exacts[e], rp.eye_py[2 * (size_t)ray], yg);
                     }
+                    // rows of best[] are SORTED heading slots
+                    if (in) {
+                        if (kSmem) post_copy_u16(sm.ras.best, (unsigned)ks[u] * R + j, sm.tile, dist, ent.tri, e);
+                        else post_copy_u32(&gbest[(size_t)ks[u] * R + j], sm.tile, dist, ent.tri, e);
+                    }
+#ifdef ISY_DBG_COUNT
+                    if (in) atomicAdd(&rp.phase_cycles[7], 1ull);
+#endif
                     if (act[u]) ++k[u];
                 }
             }
@@ -660,7 +700,7 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
 // rays of one view.
 // ------------------------------------------------------------------------------------------
 template <bool kSmem>
-__device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const unsigned int* gbest, int p, int h0,
+__device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const unsigned int* gbest, int p, int grp,
                                 int Hcur) {
     const int R = rp.R, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool perez = rp.sky.kind == ISY_SKY_PEREZ, uniform = rp.sky.kind == ISY_SKY_UNIFORM;
@@ -691,13 +731,15 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
         const int pos = __ldg(rp.grid_pos_of + rr);
         const int hend = min(Hcur, (hc + 1) * hper);
         for (int hh = hc * hper; hh < hend; ++hh) {
-            const size_t vbase = ((size_t)p * rp.H + h0 + hh) * (size_t)R;   // first ray of this view
-            const unsigned int id = kSmem ? (unsigned)sm.ras.best[hh * R + pos] : gbest[(size_t)hh * R + pos];
+            const size_t view = (size_t)p * rp.H + grp + (size_t)hh * rp.ngroups;   // group = every ngroups-th heading
+            const size_t vbase = view * (size_t)R;                                  // first ray of this view
+            const int hs = sm.ras.hinv[hh];
+            const unsigned int id = kSmem ? (unsigned)sm.ras.best[hs * R + pos] : gbest[(size_t)hs * R + pos];
             double Y = 0, P = 0, A = CUDART_NAN;
             if (perez) {
                 const double hs = sm.head_sin[hh], hcs = sm.head_cos[hh];
                 const double sy = t4v.z * hcs + t4v.w * hs, cy = t4v.w * hcs - t4v.z * hs;   // yaw_e + heading
-                const SunConst sc = rp.sun[rp.sun_per_view ? (size_t)p * rp.H + h0 + hh : 0];
+                const SunConst sc = rp.sun[rp.sun_per_view ? view : 0];
                 sky_eval<false>(rp.sky, sc, t4v.y * cy, t4v.y * sy, -t4v.x, e_pitch + kHalfPi, f_theta, Y, P, A, false, sm.gtab);
             } else if (uniform) {
                 Y = rp.sky.luminance;
@@ -789,11 +831,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 
         // headings are handled in groups of rp.Hg (the rasteriser's winner buffer holds one group)
         for (int grp = split; grp < rp.ngroups; grp += rp.splits) {
-            const int h0 = grp * rp.Hg, Hcur = min(rp.Hg, rp.H - h0);
+            // group grp = headings grp, grp + ngroups, ...: an evenly spaced scan stays evenly spaced
+            const int Hcur = (rp.H - grp + rp.ngroups - 1) / rp.ngroups;
             long long t3 = clock64();
             __syncthreads();
             if (yaw_only && tid < Hcur) {
-                const double hw = wrap_yaw(rp.yaw ? rp.yaw[(size_t)p * rp.H + h0 + tid] : 0.0);
+                const double hw = wrap_yaw(rp.yaw ? rp.yaw[(size_t)p * rp.H + grp + (size_t)tid * rp.ngroups] : 0.0);
                 sm.head_val[tid] = hw;
                 sincos(hw, &sm.head_sin[tid], &sm.head_cos[tid]);
             }
@@ -808,16 +851,22 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                 if (tid == 0) s_count = 0;     // (the cull's counter is free again: next copy to rasterise)
                 sort_headings(sm, Hcur);
                 __syncthreads();
-                if (smem_grid) raster_copies<true>(rp, sm, gbest, exacts, E, Hcur, &s_count);
-                else raster_copies<false>(rp, sm, gbest, exacts, E, Hcur, &s_count);
+                const bool uniform = sm.ras.uni[3] != 0.f;
+                if (smem_grid) {
+                    if (uniform) raster_copies<true, true>(rp, sm, gbest, exacts, E, Hcur, &s_count);
+                    else raster_copies<true, false>(rp, sm, gbest, exacts, E, Hcur, &s_count);
+                } else {
+                    if (uniform) raster_copies<false, true>(rp, sm, gbest, exacts, E, Hcur, &s_count);
+                    else raster_copies<false, false>(rp, sm, gbest, exacts, E, Hcur, &s_count);
+                }
             }
             __syncthreads();
             long long t4 = clock64();
             t_phase[1] += t4 - t3;
 
             if (mode == kModeRaster && !kF64 && rp.S == 1 && !rp.init_c) {
-                if (smem_grid) final_pass_fast<true>(rp, sm, gbest, p, h0, Hcur);
-                else final_pass_fast<false>(rp, sm, gbest, p, h0, Hcur);
+                if (smem_grid) final_pass_fast<true>(rp, sm, gbest, p, grp, Hcur);
+                else final_pass_fast<false>(rp, sm, gbest, p, grp, Hcur);
                 t_phase[2] += clock64() - t4;
                 continue;
             }
@@ -846,7 +895,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                 }
                 const int hend = min(Hcur, (hc + 1) * hper);
                 for (int hh = hc * hper; hh < hend; ++hh) {
-                    const size_t b = (size_t)p * rp.H + h0 + hh;
+                    const size_t b = (size_t)p * rp.H + grp + (size_t)hh * rp.ngroups;
                     Ray ray;
                     double dx = 0, dy = 0, dz = 0;
                     if (!yaw_only) {
@@ -880,8 +929,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                     ray.hit = -1;
 
                     if (mode == kModeRaster) {
-                        const unsigned int rk = smem_grid ? (unsigned)sm.ras.best[hh * rp.R + pos]
-                                                          : gbest[(size_t)hh * rp.R + pos];
+                        const int hs = sm.ras.hinv[hh];
+                        const unsigned int rk = smem_grid ? (unsigned)sm.ras.best[hs * rp.R + pos]
+                                                          : gbest[(size_t)hs * rp.R + pos];
                         if (rk != kNoCopy) {
                             const Entry& w = sm.tile[rk];
                             ray.hit = w.tri;

@@ -202,6 +202,23 @@ def test_batched_many_headings_vs_c_oracle(ib, world, request):
     assert np.array_equal(rgb[hit >= 0], cols[hit[hit >= 0]])
 
 
+@pytest.mark.parametrize("H", [1, 2, 7, 18, 36, 40])
+def test_small_eye_irregular_and_regular_headings_vs_c_oracle(ib, seville, omm1000, H):
+    """1000-ray eye (shared-memory rasteriser): irregular headings walk the look-up table, evenly spaced
+    full-circle headings use the arithmetic window; more headings than one group holds are split"""
+    pitch, yaw, _ = omm1000
+    rng = np.random.RandomState(100 + H)
+    P = 6
+    pos = np.c_[rng.uniform(0.5, 9.5, P), rng.uniform(0.5, 9.5, P), np.full(P, 0.01)]
+    r = ib.Renderer(seville, ib.EyeLayout.from_angles(pitch, yaw))
+    irregular = rng.uniform(-np.pi, np.pi, (P, H))
+    regular = (rng.uniform(-np.pi, np.pi, (P, 1)) + np.arange(H)[None, :] * 2 * np.pi / H + np.pi) % (2 * np.pi) - np.pi
+    for yaw_rad in (irregular, regular):
+        out = _render_np(r, pos=pos, yaw=yaw_rad, outputs=("hit",))
+        ref = _oracle_views(seville.polygons, pos, yaw_rad, pitch, yaw)
+        assert (out["hit"] != ref).sum() == 0
+
+
 def test_cone_average_matches_numpy_composition(ib, seville):
     """S samples per ommatidium: GPU average == reference-rule per-sample values averaged in NumPy"""
     rng = np.random.RandomState(5)
