@@ -215,32 +215,6 @@ __device__ __forceinline__ double perez_phi(double chi, double cos_chi, double C
     return 1.0 + C * exp(D * chi) + E * (cos_chi * cos_chi);
 }
 
-// acos(c) to ~1e-12 for the sky's angular distance: float acosf seed + one Newton step on
-// f(g) = cos g - c with cos(seed) from an fp64 even polynomial (the seed is an exact fp32 value);
-// next to 0 and pi, where the step is ill-conditioned, the library acos is used.
-__device__ __forceinline__ double acos_newton(double c) {
-    const float cf = (float)c;
-    const float s0 = sqrtf(fmaxf(1.0f - cf * cf, 0.0f));
-    if (s0 < 0.06f) return acos(c);
-    const float g0 = acosf(cf);
-    double x = (double)g0;
-    const bool flip = x > kHalfPi;
-    if (flip) x = kPi - x;
-    const double x2 = x * x;
-    double q = -1.5619206968586226e-16;                 // -1/18!
-    q = fma(q, x2, 4.7794773323873853e-14);             //  1/16!
-    q = fma(q, x2, -1.1470745597729725e-11);            // -1/14!
-    q = fma(q, x2, 2.0876756987868099e-09);             //  1/12!
-    q = fma(q, x2, -2.7557319223985893e-07);            // -1/10!
-    q = fma(q, x2, 2.4801587301587302e-05);             //  1/8!
-    q = fma(q, x2, -1.3888888888888889e-03);            // -1/6!
-    q = fma(q, x2, 4.1666666666666664e-02);             //  1/4!
-    q = fma(q, x2, -0.5);
-    q = fma(q, x2, 1.0);                                // cos(x), |error| < 4e-15 on [0, pi/2]
-    const double cos_g0 = flip ? -q : q;
-    return (double)g0 + (cos_g0 - c) * (double)__frcp_rn(s0);
-}
-
 // Sky.__call__ for one direction (sky.py:304-334); d = unit view direction, theta = zenith angle.
 // f_theta = perez_f(cos theta, theta < pi/2) is passed in: it depends on the elevation only and is
 // tabulated per eye ray for yaw-only views.
