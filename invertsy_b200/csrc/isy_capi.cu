@@ -370,116 +370,127 @@ int isy_workspace_phase_cycles(void* workspace_dev, void* stream, uint64_t* out4
     return ISY_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// Persistent staging of the host-buffer path: two compute/copy slots (device arenas that only
+// grow), two streams and their events, one per device.  Calls on one device are serialised.
+struct HostCtx {
+    std::mutex mu;
+    bool init = false;
+    cudaStream_t s_comp = nullptr, s_copy = nullptr;
+    cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    void* arena[2] = {nullptr, nullptr};
+    size_t arena_bytes[2] = {0, 0};
+    void* in_arena = nullptr;
+    size_t in_bytes = 0;
+};
+HostCtx g_host_ctx[16];
+
+cudaError_t grow(void** p, size_t* have, size_t need) {
+    if (*have >= need) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr, *have = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e == cudaSuccess) *have = need;
+    return e;
+}
+
+}  // namespace
+
+extern "C" {
+
 int isy_render_host(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, const double* pos_host,
                     const double* yaw_host, const double* view_quat_host, const double* sun_host,
                     const isy_sky_params* sky, uint32_t flags, const isy_outputs* out_host) {
     if (!w || !e || !pos_host || !out_host || P < 0 || H <= 0) return fail(ISY_ERR_INVALID, "isy_render_host: bad argument");
+    if (w->device < 0 || w->device >= 16) return fail(ISY_ERR_INVALID, "isy_render_host: device index out of range");
     DeviceGuard g(w->device);
     if (!g.ok) return fail(ISY_ERR_CUDA, "isy_render_host: cannot select CUDA device %d (no CPU fallback)", w->device);
     if (P == 0) return ISY_OK;
+    HostCtx& cx = g_host_ctx[w->device];
+    std::lock_guard<std::mutex> lk(cx.mu);
+    if (!cx.init) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&cx.s_comp, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&cx.s_copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&cx.done[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&cx.copied[i], cudaEventDisableTiming));
+        }
+        cx.init = true;
+    }
     const size_t esz = (flags & ISY_FLAG_OUT_F64) ? 8 : 4;
     const int64_t R = e->R, N = e->N;
     const bool sun_pv = flags & ISY_FLAG_SUN_PER_VIEW;
 
-    // positions are processed in chunks so that compute of chunk c+1 overlaps the D2H of chunk c
-    const size_t bytes_per_pos = (size_t)H * ((out_host->rgb ? 3 * N * esz : 0) + (out_host->hit ? R * 4 : 0) +
-                                              (out_host->depth ? R * esz : 0) +
-                                              ((out_host->Y ? 1 : 0) + (out_host->dop ? 1 : 0) + (out_host->aop ? 1 : 0)) * N * esz);
-    int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(P, (int64_t)((256ull << 20) / std::max<size_t>(bytes_per_pos, 1))));
+    // positions are processed in chunks so that the compute of chunk c+1 overlaps the D2H of chunk c
+    const size_t per_view[6] = {out_host->rgb ? 3 * (size_t)N * esz : 0, out_host->hit ? (size_t)R * 4 : 0,
+                                out_host->depth ? (size_t)R * esz : 0, out_host->Y ? (size_t)N * esz : 0,
+                                out_host->dop ? (size_t)N * esz : 0, out_host->aop ? (size_t)N * esz : 0};
+    size_t bytes_per_pos = 0;
+    for (size_t b : per_view) bytes_per_pos += (size_t)H * b;
+    int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(P, (int64_t)((96ull << 20) / std::max<size_t>(bytes_per_pos, 1))));
     if (chunk < P) chunk = std::max<int64_t>(chunk, std::min<int64_t>(P, 2 * device_sms(w->device)));
-
-    cudaStream_t s_comp, s_copy;
-    CUDA_TRY(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-    struct Slot {
-        DevBuf<unsigned char> rgb, hit, depth, Y, dop, aop, ws;
-        cudaEvent_t done = nullptr, copied = nullptr;
-    } slot[2];
-    DevBuf<double> d_pos, d_yaw, d_vq, d_sun;
-    int rc = ISY_OK;
-    auto cleanup = [&]() {
-        for (auto& s : slot) {
-            if (s.done) cudaEventDestroy(s.done);
-            if (s.copied) cudaEventDestroy(s.copied);
-        }
-        cudaStreamDestroy(s_comp);
-        cudaStreamDestroy(s_copy);
-    };
-#define TRY_CLEAN(expr)                                                                                   \
-    do {                                                                                                  \
-        cudaError_t e__ = (expr);                                                                         \
-        if (e__ != cudaSuccess) {                                                                         \
-            cleanup();                                                                                    \
-            return fail(ISY_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
-        }                                                                                                 \
-    } while (0)
-
-    TRY_CLEAN(d_pos.alloc((size_t)P * 3));
-    TRY_CLEAN(cudaMemcpyAsync(d_pos.p, pos_host, (size_t)P * 3 * 8, cudaMemcpyHostToDevice, s_comp));
-    if (yaw_host) {
-        TRY_CLEAN(d_yaw.alloc((size_t)P * H));
-        TRY_CLEAN(cudaMemcpyAsync(d_yaw.p, yaw_host, (size_t)P * H * 8, cudaMemcpyHostToDevice, s_comp));
-    }
-    if (view_quat_host) {
-        TRY_CLEAN(d_vq.alloc((size_t)P * H * 4));
-        TRY_CLEAN(cudaMemcpyAsync(d_vq.p, view_quat_host, (size_t)P * H * 4 * 8, cudaMemcpyHostToDevice, s_comp));
-    }
-    if (sun_host) {
-        size_t n = sun_pv ? (size_t)P * H * 2 : 2;
-        TRY_CLEAN(d_sun.alloc(n));
-        TRY_CLEAN(cudaMemcpyAsync(d_sun.p, sun_host, n * 8, cudaMemcpyHostToDevice, s_comp));
-    }
-    const size_t ws_bytes = isy_render_workspace_bytes(w, e, chunk, H);
     const int nslots = chunk < P ? 2 : 1;
-    for (int i = 0; i < nslots; ++i) {
-        Slot& s = slot[i];
-        size_t V = (size_t)chunk * H;
-        if (out_host->rgb) TRY_CLEAN(s.rgb.alloc(V * N * 3 * esz));
-        if (out_host->hit) TRY_CLEAN(s.hit.alloc(V * R * 4));
-        if (out_host->depth) TRY_CLEAN(s.depth.alloc(V * R * esz));
-        if (out_host->Y) TRY_CLEAN(s.Y.alloc(V * N * esz));
-        if (out_host->dop) TRY_CLEAN(s.dop.alloc(V * N * esz));
-        if (out_host->aop) TRY_CLEAN(s.aop.alloc(V * N * esz));
-        TRY_CLEAN(s.ws.alloc(ws_bytes));
-        TRY_CLEAN(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-        TRY_CLEAN(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
-    }
 
-    int ci = 0;
+    // inputs: one small H2D each
+    const size_t n_pos = (size_t)P * 3, n_yaw = yaw_host ? (size_t)P * H : 0, n_vq = view_quat_host ? (size_t)P * H * 4 : 0;
+    const size_t n_sun = sun_host ? (sun_pv ? (size_t)P * H * 2 : 2) : 0;
+    CUDA_TRY(grow(&cx.in_arena, &cx.in_bytes, (n_pos + n_yaw + n_vq + n_sun + 8) * sizeof(double)));
+    double* d_pos = (double*)cx.in_arena;
+    double* d_yaw = n_yaw ? d_pos + n_pos : nullptr;
+    double* d_vq = n_vq ? d_pos + n_pos + n_yaw : nullptr;
+    double* d_sun = n_sun ? d_pos + n_pos + n_yaw + n_vq : nullptr;
+    CUDA_TRY(cudaMemcpyAsync(d_pos, pos_host, n_pos * 8, cudaMemcpyHostToDevice, cx.s_comp));
+    if (d_yaw) CUDA_TRY(cudaMemcpyAsync(d_yaw, yaw_host, n_yaw * 8, cudaMemcpyHostToDevice, cx.s_comp));
+    if (d_vq) CUDA_TRY(cudaMemcpyAsync(d_vq, view_quat_host, n_vq * 8, cudaMemcpyHostToDevice, cx.s_comp));
+    if (d_sun) CUDA_TRY(cudaMemcpyAsync(d_sun, sun_host, n_sun * 8, cudaMemcpyHostToDevice, cx.s_comp));
+
+    const size_t ws_bytes = align_up(isy_render_workspace_bytes(w, e, chunk, H));
+    size_t off[7];
+    size_t total = ws_bytes;
+    for (int k = 0; k < 6; ++k) {
+        off[k] = total;
+        total += align_up((size_t)chunk * H * per_view[k]);
+    }
+    off[6] = total;
+    for (int i = 0; i < nslots; ++i) CUDA_TRY(grow(&cx.arena[i], &cx.arena_bytes[i], total));
+
+    void* const host_ptr[6] = {out_host->rgb, out_host->hit, out_host->depth, out_host->Y, out_host->dop, out_host->aop};
+    int rc = ISY_OK, ci = 0;
     for (int64_t p0 = 0; p0 < P && rc == ISY_OK; p0 += chunk, ++ci) {
-        Slot& s = slot[ci % nslots];
-        int64_t pc = std::min(chunk, P - p0);
-        size_t v0 = (size_t)p0 * H, V = (size_t)pc * H;
-        if (ci >= nslots) TRY_CLEAN(cudaStreamWaitEvent(s_comp, s.copied, 0));   // slot buffers free again
+        const int sl = ci % nslots;
+        unsigned char* base = (unsigned char*)cx.arena[sl];
+        const int64_t pc = std::min(chunk, P - p0);
+        const size_t v0 = (size_t)p0 * H, V = (size_t)pc * H;
+        if (ci >= nslots) CUDA_TRY(cudaStreamWaitEvent(cx.s_comp, cx.copied[sl], 0));   // slot buffers free again
         isy_outputs o;
-        o.rgb = s.rgb.p, o.hit = (int32_t*)s.hit.p, o.depth = s.depth.p, o.Y = s.Y.p, o.dop = s.dop.p, o.aop = s.aop.p;
-        rc = launch_render(w, e, pc, H, d_pos.p + 3 * p0, d_yaw.p ? d_yaw.p + v0 : nullptr,
-                           d_vq.p ? d_vq.p + 4 * v0 : nullptr, d_sun.p ? (sun_pv ? d_sun.p + 2 * v0 : d_sun.p) : nullptr,
-                           nullptr, sky, flags, &o, s.ws.p, ws_bytes, s_comp);
+        o.rgb = per_view[0] ? base + off[0] : nullptr;
+        o.hit = per_view[1] ? (int32_t*)(base + off[1]) : nullptr;
+        o.depth = per_view[2] ? base + off[2] : nullptr;
+        o.Y = per_view[3] ? base + off[3] : nullptr;
+        o.dop = per_view[4] ? base + off[4] : nullptr;
+        o.aop = per_view[5] ? base + off[5] : nullptr;
+        rc = launch_render(w, e, pc, H, d_pos + 3 * p0, d_yaw ? d_yaw + v0 : nullptr, d_vq ? d_vq + 4 * v0 : nullptr,
+                           d_sun ? (sun_pv ? d_sun + 2 * v0 : d_sun) : nullptr, nullptr, sky, flags, &o, base, ws_bytes,
+                           cx.s_comp);
         if (rc != ISY_OK) break;
-        TRY_CLEAN(cudaEventRecord(s.done, s_comp));
-        TRY_CLEAN(cudaStreamWaitEvent(s_copy, s.done, 0));
-        auto d2h = [&](void* dst, const void* src, size_t off, size_t bytes) {
-            return cudaMemcpyAsync((unsigned char*)dst + off, src, bytes, cudaMemcpyDeviceToHost, s_copy);
-        };
-        if (out_host->rgb) TRY_CLEAN(d2h(out_host->rgb, s.rgb.p, v0 * N * 3 * esz, V * N * 3 * esz));
-        if (out_host->hit) TRY_CLEAN(d2h(out_host->hit, s.hit.p, v0 * R * 4, V * R * 4));
-        if (out_host->depth) TRY_CLEAN(d2h(out_host->depth, s.depth.p, v0 * R * esz, V * R * esz));
-        if (out_host->Y) TRY_CLEAN(d2h(out_host->Y, s.Y.p, v0 * N * esz, V * N * esz));
-        if (out_host->dop) TRY_CLEAN(d2h(out_host->dop, s.dop.p, v0 * N * esz, V * N * esz));
-        if (out_host->aop) TRY_CLEAN(d2h(out_host->aop, s.aop.p, v0 * N * esz, V * N * esz));
-        TRY_CLEAN(cudaEventRecord(s.copied, s_copy));
+        CUDA_TRY(cudaEventRecord(cx.done[sl], cx.s_comp));
+        CUDA_TRY(cudaStreamWaitEvent(cx.s_copy, cx.done[sl], 0));
+        for (int k = 0; k < 6; ++k) {
+            if (!per_view[k]) continue;
+            CUDA_TRY(cudaMemcpyAsync((unsigned char*)host_ptr[k] + v0 * per_view[k], base + off[k], V * per_view[k],
+                                     cudaMemcpyDeviceToHost, cx.s_copy));
+        }
+        CUDA_TRY(cudaEventRecord(cx.copied[sl], cx.s_copy));
     }
-    if (rc == ISY_OK) {
-        TRY_CLEAN(cudaStreamSynchronize(s_copy));
-        for (int i = 0; i < nslots && rc == ISY_OK; ++i) rc = check_status(slot[i].ws.p, s_comp);
-    } else {
-        cudaStreamSynchronize(s_comp);
-        cudaStreamSynchronize(s_copy);
-    }
-    cleanup();
+    cudaError_t e1 = cudaStreamSynchronize(cx.s_comp), e2 = cudaStreamSynchronize(cx.s_copy);
+    if (rc != ISY_OK) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+        return fail(ISY_ERR_CUDA, "isy_render_host: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    for (int i = 0; i < nslots && rc == ISY_OK; ++i) rc = check_status(cx.arena[i], cx.s_comp);
     return rc;
-#undef TRY_CLEAN
 }
 
 int isy_world_call_host(const isy_world* w, const double* pos3_host, const double* ray_quat_host, int64_t N,

@@ -1,0 +1,76 @@
+"""
+Multi-GPU rendering: one process per GPU (torchrun), views sharded by *position*.
+
+The path has no exchange step (every view is a pure function of its pose -- reference
+sim/simulation.py:2675-2701), so the data path needs no collective: each rank renders a contiguous
+block of positions with all their headings (the cull / projection of a position is shared by its
+headings, so a position never straddles ranks).  NCCL is used only to gather results -- per-view
+outputs or small per-view summaries such as a familiarity heat-map row -- onto one or all ranks.
+
+`render_fn(pos, yaw)` is any callable returning {name: tensor [B_local, ...]} -- normally
+``lambda p, y: renderer.render(p, y, outputs=...)`` -- which keeps this module testable on CPU with
+the gloo backend.
+"""
+import torch
+import torch.distributed as dist
+
+from .views import shard_positions
+
+
+def rank_and_world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard(pos, yaw, rank=None, world_size=None, group=None):
+    """This rank's block of positions: (pos[a:b], yaw[a:b], (a, b))."""
+    if rank is None or world_size is None:
+        rank, world_size = rank_and_world(group)
+    a, b = shard_positions(len(pos), rank, world_size)
+    return pos[a:b], yaw[a:b], (a, b)
+
+
+def gather_views(local, nb_positions, views_per_position, dst=None, group=None):
+    """
+    Concatenates per-rank results in position order.  `local` maps names to tensors whose first
+    dimension is this rank's view count; shards may differ by one position, so tensors are padded to
+    the largest shard for the collective and trimmed afterwards.  dst=None -> every rank gets the
+    full result (all_gather); otherwise only rank `dst` does (others get None).
+    """
+    rank, world = rank_and_world(group)
+    if world == 1:
+        return dict(local)
+    counts = [(shard_positions(nb_positions, r, world)[1] - shard_positions(nb_positions, r, world)[0])
+              * views_per_position for r in range(world)]
+    biggest = max(counts)
+    out = {}
+    for name, t in local.items():
+        if t.shape[0] != counts[rank]:
+            raise ValueError("%s holds %d views, this rank's shard has %d" % (name, t.shape[0], counts[rank]))
+        pad = t
+        if t.shape[0] < biggest:
+            pad = torch.cat([t, t.new_zeros((biggest - t.shape[0],) + tuple(t.shape[1:]))], dim=0)
+        pad = pad.contiguous()
+        if dst is None:
+            parts = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(parts, pad, group=group)
+        else:
+            parts = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+            dist.gather(pad, parts, dst=dst, group=group)
+        out[name] = None if parts is None else torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+    return out
+
+
+def render_sharded(render_fn, pos, yaw, reduce_fn=None, dst=None, group=None):
+    """
+    Renders this rank's positions and gathers.  `reduce_fn(outputs) -> {name: tensor [B_local, ...]}`
+    may shrink what travels (e.g. per-view mean luminance for a heat map) before the gather.
+    Returns (gathered dict or None on non-destination ranks, local dict, (a, b) position block).
+    """
+    p, y, block = shard(pos, yaw, group=group)
+    local = render_fn(p, y)          # also for an empty shard: the gather needs every rank's names and shapes
+    local = {k: v for k, v in local.items() if torch.is_tensor(v)}
+    small = reduce_fn(local) if reduce_fn is not None else local
+    views_per_position = yaw.shape[1] if getattr(yaw, "ndim", 1) > 1 else 1
+    return gather_views(small, len(pos), views_per_position, dst=dst, group=group), local, block

@@ -152,11 +152,12 @@ class Renderer(object):
         pos = self._dev(pos, (-1, 3))
         P = pos.shape[0]
         if quat is not None:
-            quat = self._dev(quat, (P, -1, 4))
-            H = quat.shape[1]
+            H = quat.shape[1] if getattr(quat, "ndim", 0) == 3 else 1
+            quat = self._dev(quat, (P, H, 4))
         else:
-            yaw = self._dev(np.zeros((P, 1)) if yaw is None else yaw, (P, -1))
-            H = yaw.shape[1]
+            yaw = np.zeros((P, 1)) if yaw is None else yaw
+            H = yaw.shape[1] if getattr(yaw, "ndim", 0) == 2 else 1
+            yaw = self._dev(yaw, (P, H))
         B = P * H
         flags = 0
         if sp.kind == _lib.SKY_PEREZ:
