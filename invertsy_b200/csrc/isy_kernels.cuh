@@ -64,6 +64,7 @@ struct SmemLayout {
     float4 bbox[kMaxE];               // (theta_lo, theta_hi, phi_lo, phi_hi) of each copy, margin included
     double head_sin[kMaxH], head_cos[kMaxH], head_val[kMaxH];   // per heading of the current group
     double2 gtab[2 * (kGTab + 1)];    // exp(D acos c) table of this call's sky (copied once per CTA)
+    SunConst sun0;                    // sun constants when all views share one sun (copied once per CTA)
     union {
         SmemBins bins;
         SmemRaster ras;
@@ -146,9 +147,11 @@ __global__ void sun_setup_kernel(const double* __restrict__ sun, int n, isy_sky_
     c.i90 = f90 * perez_phi(kHalfPi, cos(kHalfPi), sp.C, sp.D, sp.E);
     c.K = c.i00 * c.i90 / (c.i00 - c.i90 + kEps);
     c.inv_i00 = 1.0 / (c.i00 + kEps);
+    c.pad_ = 0.f;
     double chi = (4.0 / 9.0 - sp.tau_L / 120.0) * (kPi - 2 * (kHalfPi - ths));
     c.Yz = (4.0453 * sp.tau_L - 4.9710) * tan(chi) - 0.2155 * sp.tau_L + 2.4192;
     c.Mp = exp(-(sp.tau_L - sp.c1) / (sp.c2 + kEps));
+    c.inv_i00_f = (float)c.inv_i00, c.K_f = (float)c.K, c.Mp2_f = (float)(2.0 / kPi * c.Mp);
     out[b] = c;
 }
 
@@ -482,6 +485,15 @@ __device__ __forceinline__ void write_view(const RenderParams& rp, size_t b, int
 // ALL headings of the position at once; nothing is built per position beyond the ranks.
 // ------------------------------------------------------------------------------------------
 constexpr unsigned int kNoCopy = 0xffffu;
+
+// atomicAdd on a __shared__ int through an explicit shared-space instruction (a generic-address
+// atomic on shared memory is much slower)
+__device__ __forceinline__ int smem_atomic_add(int* p, int v) {
+    int old;
+    const unsigned int a = (unsigned int)__cvta_generic_to_shared(p);
+    asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+    return old;
+}
 constexpr int kRU = 4;                // rays per lane and iteration in the rasteriser
 
 // is copy e (distance d, triangle tri) nearer than copy c? (ties: lower triangle index, then lower slot)
@@ -571,7 +583,7 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
     for (;;) {
         // copies differ a lot in size (a near blade spans hundreds of rays): warps pull them from a counter
         int e = 0;
-        if (lane == 0) e = atomicAdd(s_next, 1);
+        if (lane == 0) e = smem_atomic_add(s_next, 1);
         e = __shfl_sync(0xffffffffu, e, 0);
         if (e >= E) break;
         const float4 bb = sm.bbox[e];
@@ -594,7 +606,7 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
             if (lane == 0) atomicAdd(&rp.phase_cycles[4], 1ull);
 #endif
             float2 py[kRU];
-            int k[kRU];
+            int k[kRU], ks[kRU];    // window cursor; sorted slot of the heading under the cursor
             float upper[kRU];
 #pragma unroll
             for (int u = 0; u < kRU; ++u) {
@@ -610,10 +622,13 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
                 else if (lower >= pi_f) lower -= twopi_f;
                 const bool band = py[u].x >= bb.x && py[u].x <= bb.y;
                 if (kUniform) {
-                    // headings are h0 + k*delta (k mod H): the window is the index range [k, upper]
+                    // headings are h0 + k*delta (k mod H): the window is the index range [k0, k1];
+                    // k[] counts the headings left in the window, ks[] is the sorted slot of the next one
                     const float a = (lower - uh0) * uinv;
-                    k[u] = band ? (int)ceilf(a - 2e-4f) : 1;
-                    upper[u] = band ? floorf(fmaf(width, uinv, a) + 2e-4f) : 0.f;
+                    const int k0 = (int)ceilf(a - 2e-4f), k1 = (int)floorf(fmaf(width, uinv, a) + 2e-4f);
+                    k[u] = band ? min(k1 - k0 + 1, Hcur) : 0;            // lower in [-pi, pi): k0 in [-H, H]
+                    ks[u] = k0 < 0 ? k0 + Hcur : (k0 >= Hcur ? k0 - Hcur : k0);
+                    upper[u] = 0.f;
                 } else {
                     const int ls = min(max((int)((lower + pi_f) * (kHeadLut / twopi_f)), 0), kHeadLut - 1);
                     k[u] = band ? (int)sm.ras.hlut[ls] : H2;
@@ -624,13 +639,10 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
             for (;;) {
                 bool act[kRU], any = false;
                 float hv[kRU];
-                int ks[kRU];    // sorted slot of the heading
 #pragma unroll
                 for (int u = 0; u < kRU; ++u) {
                     if (kUniform) {
-                        act[u] = (float)k[u] <= upper[u];
-                        ks[u] = k[u] < 0 ? k[u] + Hcur : (k[u] >= Hcur ? k[u] - Hcur : k[u]);   // k in [-H, 2H)
-                        ks[u] = min(max(ks[u], 0), Hcur - 1);
+                        act[u] = k[u] > 0;
                         hv[u] = fmaf((float)ks[u], udelta, uh0);
                     } else {
                         const int kk = min(k[u], H2 - 1);
@@ -685,7 +697,14 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
 #ifdef ISY_DBG_COUNT
                     if (in) atomicAdd(&rp.phase_cycles[7], 1ull);
 #endif
-                    if (act[u]) ++k[u];
+                    if (kUniform) {
+                        if (act[u]) {
+                            --k[u];
+                            ks[u] = ks[u] + 1 == Hcur ? 0 : ks[u] + 1;
+                        }
+                    } else if (act[u]) {
+                        ++k[u];
+                    }
                 }
             }
         }
@@ -730,6 +749,7 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
         }
         const int pos = __ldg(rp.grid_pos_of + rr);
         const int hend = min(Hcur, (hc + 1) * hper);
+
         for (int hh = hc * hper; hh < hend; ++hh) {
             const size_t view = (size_t)p * rp.H + grp + (size_t)hh * rp.ngroups;   // group = every ngroups-th heading
             const size_t vbase = view * (size_t)R;                                  // first ray of this view
@@ -739,7 +759,7 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
             if (perez) {
                 const double hs = sm.head_sin[hh], hcs = sm.head_cos[hh];
                 const double sy = t4v.z * hcs + t4v.w * hs, cy = t4v.w * hcs - t4v.z * hs;   // yaw_e + heading
-                const SunConst sc = rp.sun[rp.sun_per_view ? view : 0];
+                const SunConst& sc = rp.sun_per_view ? rp.sun[view] : sm.sun0;   // one sun: read from shared memory
                 sky_eval<false>(rp.sky, sc, t4v.y * cy, t4v.y * sy, -t4v.x, e_pitch + kHalfPi, f_theta, Y, P, A, false, sm.gtab);
             } else if (uniform) {
                 Y = rp.sky.luminance;
@@ -798,6 +818,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 
     if (perez) {
         for (int i = tid; i < 2 * (kGTab + 1); i += kThreads) sm.gtab[i] = rp.sky_gtab[i];
+        if (tid == 0) sm.sun0 = rp.sun[0];
     }
     long long t_phase[4] = {0, 0, 0, 0};   // project, accel (bins / raster), final ray pass, positions
     for (;;) {
