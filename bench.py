@@ -158,7 +158,7 @@ class ClockSampler(object):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=GRID_ROWS)
@@ -317,7 +317,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "kernel": "render kernel (1 launch/step)",
                 "kernel_ms": kernel_ms,
-                "issue": {"note": "SURVEY.md 8(d) brute-force-equivalent FP32 work; binning skips most of it",
+                "issue": {"note": "SURVEY.md 8(d) brute-force-equivalent FP32 work; the rasteriser skips most of it, so this may exceed the peak",
                           "achieved_tflops": alg_flop / (kernel_ms / 1e3) / 1e12, "peak_tflops": FP32_PEAK_TFLOPS}}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
@@ -329,7 +329,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 filter + f64 exact/sky", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (edge filter, polarisation) + f64 (projection, exact re-check, luminance)", "data": "synthetic",
                 "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "views_per_step": int(Pe * H), "api": "Renderer.render_host -> isy_render_host"},

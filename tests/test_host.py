@@ -139,3 +139,30 @@ def test_eta_mask_semantics():
         a = add_noise(rng=np.random.RandomState(3), **kw)
         b = o.add_noise(rng=np.random.RandomState(3), **kw)
         assert np.array_equal(a, b) and a.dtype == b.dtype
+
+
+def test_sky_table_construction_is_accurate_enough():
+    """G(c) = exp(D acos c) from a 2 x 257 cubic-Hermite table in u = sqrt(1 - |c|) (csrc: sky_table_kernel,
+    g_table_eval): the same construction in NumPy stays within 1e-9 of the exact value"""
+    M = 256
+    u = np.linspace(0, 1, M + 1)
+    h = 1.0 / M
+    rng = np.random.RandomState(0)
+    c = np.clip(np.concatenate([rng.uniform(-1, 1, 400000), 1 - 10 ** rng.uniform(-12, 0, 50000),
+                                -1 + 10 ** rng.uniform(-12, 0, 50000)]), -1, 1)
+    uu = np.sqrt(1 - np.abs(c))
+    idx = np.minimum((uu * M).astype(int), M - 1)
+    t = uu * M - idx
+    for D in (-3.5, -2.3359, -0.5, 1.0):
+        g = 2 * np.arcsin(u / np.sqrt(2))
+        dg = 2 / np.sqrt(2 - u * u)
+        tabs = [(np.exp(D * g), np.exp(D * g) * D * dg * h), (np.exp(D * (np.pi - g)), -np.exp(D * (np.pi - g)) * D * dg * h)]
+        out = np.empty_like(c)
+        for half, (f, d) in enumerate(tabs):
+            f0, f1, d0, d1 = f[idx], f[idx + 1], d[idx], d[idx + 1]
+            c2 = 3 * (f1 - f0) - 2 * d0 - d1
+            c3 = 2 * (f0 - f1) + d0 + d1
+            val = f0 + t * (d0 + t * (c2 + t * c3))
+            sel = (c < 0) == bool(half)
+            out[sel] = val[sel]
+        assert np.abs(out - np.exp(D * np.arccos(c))).max() < 1e-9
