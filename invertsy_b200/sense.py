@@ -1,0 +1,149 @@
+"""
+CompoundEye-compatible sensor on top of the GPU renderer.
+
+The reference takes its eye from the third-party package InvertPy (`from invertpy.sense import
+CompoundEye`, reference agent/agent.py:20, sim/simulation.py:24), which is neither vendored nor pinned;
+its acceptance-cone sampler and photoreceptor transform are therefore **unpinned** (SURVEY.md 0.3, 8c).
+This class keeps the *surface* the reference uses -- constructor keywords (agent.py:588,
+simulation.py:796, 2238, 2599, examples/create_familiarity_map_data.py:30), `eye(sky=, scene=,
+callback=)` returning `(nb_ommatidia, channels)` responses whose consumers take `.mean(axis=1)` and clip
+to [0, 1] (agent.py:744, 788; simulation.py:816, 838), and the attributes read elsewhere (`omm_ori`,
+`nb_ommatidia`, `ori`, `xyz`, `x/y/z`, `yaw_deg`, `responses`, `_xyz`, `_ori`) -- and defines the
+unpinned parts explicitly:
+
+  * acceptance cone: `nb_samples` (1, 2, 4, 8, 16, 32) directions per ommatidium: the axis, then rings
+    of points at 0.5 * omm_rho and omm_rho/... (see `cone_offsets`), Gaussian weights with
+    sigma = omm_rho / 2, normalised per ommatidium;
+  * responses (N, 3): the cone-averaged RGB of `scene` painted over the sky background, with the
+    background brought to the same 0..1 scale (sky colour / 255), multiplied by the R, G, B entries of
+    `c_sensitive` (IRGBU order) and by `omm_res`, clipped to [0, 1].
+
+Everything the eye computes per ray goes through `Renderer` (one fused launch per call or per batch).
+"""
+import numpy as np
+from scipy.spatial.transform import Rotation as R
+
+from .render import EyeLayout, Renderer, fibonacci_lattice
+
+
+def cone_offsets(nb_samples, rho):
+    """
+    Deterministic sample pattern of an acceptance cone of full angle `rho` around +x: returns
+    (pitch_off, yaw_off, weight), sample 0 on the axis, the others on a ring of radius rho/2 (and a
+    second ring at rho/4 from 16 samples up), Gaussian weights with sigma = rho/2.
+    """
+    if nb_samples == 1:
+        return np.zeros(1), np.zeros(1), np.ones(1)
+    k = np.arange(1, nb_samples)
+    rad = np.full(k.size, rho / 2.)
+    if nb_samples >= 16:
+        rad[k % 2 == 0] = rho / 4.
+    ang = 2 * np.pi * k / (nb_samples - 1) + (0.5 if nb_samples >= 16 else 0.) * (k % 2)
+    d_pitch = np.concatenate([[0.], rad * np.sin(ang)])
+    d_yaw = np.concatenate([[0.], rad * np.cos(ang)])
+    r2 = d_pitch ** 2 + d_yaw ** 2
+    w = np.exp(-r2 / (2 * (rho / 2.) ** 2)) if rho > 0 else np.ones(nb_samples)
+    return d_pitch, d_yaw, w / w.sum()
+
+
+class CompoundEye(object):
+    def __init__(self, nb_input=1000, omm_ori=None, omm_rho=np.deg2rad(5.), omm_res=1., omm_pol_op=0.,
+                 c_sensitive=(0., 0., 1., 0., 0.), noise=0., xyz=None, ori=None, nb_samples=1, dtype='float32',
+                 name="compound_eye", device=0):
+        if omm_ori is None:
+            pitch, yaw = fibonacci_lattice(nb_input)
+            omm_ori = R.from_euler('ZY', np.c_[yaw, pitch])
+        self._omm_ori = omm_ori
+        self.nb_ommatidia = len(omm_ori)
+        self.omm_rho = float(np.max(omm_rho))
+        self.omm_res = omm_res
+        self.omm_pol_op = omm_pol_op
+        self.c_sensitive = np.asarray(c_sensitive, dtype=np.float64).reshape(-1)
+        self.noise = noise
+        self.nb_samples = int(nb_samples)
+        self.dtype = dtype
+        self.name = name
+        self.device = device
+        self._xyz = np.zeros(3) if xyz is None else np.asarray(xyz, dtype=np.float64)
+        self._ori = R.from_euler('Z', 0.) if ori is None else ori
+        self.responses = np.zeros((self.nb_ommatidia, 3), dtype=dtype)
+        self._layout = None
+        self._renderers = {}
+
+    # ---- geometry ----
+    @property
+    def omm_ori(self):
+        return self._omm_ori
+
+    def _eye_layout(self):
+        if self._layout is None:
+            yaw, pitch, _ = self._omm_ori.as_euler('ZYX').T
+            dp, dy, w = cone_offsets(self.nb_samples, self.omm_rho)
+            p = np.clip(pitch[:, None] + dp[None, :], -np.pi / 2 + 1e-6, np.pi / 2 - 1e-6)
+            y = (yaw[:, None] + dy[None, :] / np.maximum(np.cos(pitch), 0.05)[:, None] + np.pi) % (2 * np.pi) - np.pi
+            self._layout = EyeLayout.from_angles(p.ravel(), y.ravel(), samples=self.nb_samples,
+                                                 weights=np.tile(w, self.nb_ommatidia))
+        return self._layout
+
+    def _renderer(self, scene, sky):
+        key = (id(scene), id(sky))
+        if key not in self._renderers:
+            self._renderers[key] = Renderer(scene, self._eye_layout(), sky=sky, device=self.device)
+        return self._renderers[key]
+
+    # ---- pose (reference: eye.xyz = ..., eye.ori = R.from_euler('Z', yaw, degrees=True)) ----
+    @property
+    def xyz(self):
+        return self._xyz
+
+    @xyz.setter
+    def xyz(self, v):
+        self._xyz = np.asarray(v, dtype=np.float64)
+
+    @property
+    def ori(self):
+        return self._ori
+
+    @ori.setter
+    def ori(self, v):
+        self._ori = v
+
+    x = property(lambda self: self._xyz[0])
+    y = property(lambda self: self._xyz[1])
+    z = property(lambda self: self._xyz[2])
+
+    @property
+    def yaw(self):
+        return self._ori.as_euler('ZYX')[0]
+
+    @property
+    def yaw_deg(self):
+        return np.rad2deg(self.yaw)
+
+    # ---- sensing ----
+    def responses_from(self, rgb, with_sky):
+        """(…, N, 3) cone-averaged world colours -> responses (documented transform, see module docstring)."""
+        rgb = np.array(rgb, dtype=np.float64)
+        if with_sky:
+            sky_px = np.nan_to_num(rgb, nan=0.).max(axis=-1) > 1.     # background on the 0..255 scale
+            rgb[sky_px] /= 255.
+        w = self.c_sensitive[1:4] if self.c_sensitive.size >= 4 else np.ones(3)
+        return np.clip(np.nan_to_num(rgb, nan=0.) * w * self.omm_res, 0., 1.).astype(self.dtype)
+
+    def __call__(self, sky=None, scene=None, callback=None):
+        if scene is None:
+            raise ValueError("CompoundEye needs a scene (a WorldBase) to look at")
+        r = self._renderer(scene, sky)
+        q = self._ori.as_quat()
+        out = r.render_host(self._xyz.reshape(1, 3), quat=q.reshape(1, 1, 4), outputs=("rgb",),
+                            init_from_sky=sky is not None)
+        self.responses = self.responses_from(out["rgb"].numpy()[0], sky is not None)
+        if callback is not None:
+            callback(self)
+        return self.responses
+
+    def render_batch(self, scene, sky, pos, yaw_deg):
+        """Batched equivalent of calling the eye at P positions x H yaw-only headings: (P*H, N, 3) responses."""
+        r = self._renderer(scene, sky)
+        out = r.render_host(pos, np.deg2rad(yaw_deg), outputs=("rgb",), init_from_sky=sky is not None)
+        return self.responses_from(out["rgb"].numpy(), sky is not None)

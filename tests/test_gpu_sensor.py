@@ -1,0 +1,85 @@
+"""GPU: the CompoundEye-compatible sensor (N1) and the batched dataset writer (N2)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from scipy.spatial.transform import Rotation as R
+
+import isy_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ib():
+    import invertsy_b200
+    assert torch.cuda.is_available()
+    return invertsy_b200
+
+
+def _oracle_responses(eye, world, sky_args, pos, ori):
+    """reference world()/sky() on every sample direction, NumPy cone average, the eye's documented transform"""
+    lay = eye._eye_layout()
+    glob = ori * R.from_quat(lay.quat)
+    init = None
+    if sky_args is not None:
+        init, _, _ = o.sky_render(sky_args[0], sky_args[1], glob)
+    c = o.world_render(world.polygons, world.colours, 2.0, pos.reshape(1, 3), glob, init_c=init).astype(np.float64)
+    w = lay.weights.astype(np.float64).reshape(eye.nb_ommatidia, eye.nb_samples) if lay.weights is not None else None
+    c = c.reshape(eye.nb_ommatidia, eye.nb_samples, 3)
+    avg = (c * w[:, :, None]).sum(1) if w is not None else c.mean(1)
+    return eye.responses_from(avg, sky_args is not None)
+
+
+@pytest.mark.parametrize("nb_samples,with_sky", [(1, False), (4, True), (16, True)])
+def test_compound_eye_matches_reference_composition(ib, nb_samples, with_sky):
+    world = ib.Seville2009()
+    sky_args = (np.deg2rad(50.), 2.0) if with_sky else None
+    sky = ib.Sky(*sky_args) if with_sky else None
+    eye = ib.CompoundEye(nb_input=600, omm_rho=np.deg2rad(6.), omm_res=1.5, c_sensitive=[0, 0.2, 1., 0.1, 0],
+                         nb_samples=nb_samples)
+    route = ib.Seville2009.load_routes(degrees=True)["path"][0]
+    seen = []
+    for k in (0, 350, 700):
+        eye.xyz = route[k, :3]
+        eye.ori = R.from_euler('ZYX', [route[k, 3], 5., -3.], degrees=True)    # not yaw-only: the bins path
+        r = eye(sky=sky, scene=world, callback=seen.append)
+        assert r.shape == (600, 3) and r.dtype == np.float32 and r.min() >= 0 and r.max() <= 1
+        ref = _oracle_responses(eye, world, sky_args, route[k, :3], eye.ori)
+        assert np.abs(r - ref).max() < 1e-5
+        assert np.allclose(np.clip(r.mean(axis=1), 0, 1), np.clip(ref.mean(axis=1), 0, 1), atol=1e-5)   # agent.py:744
+    assert len(seen) == 3 and seen[0] is eye
+    assert abs(eye.yaw_deg - route[700, 3]) < 1e-9 and eye.x == route[700, 0]
+
+
+def test_dataset_writer_matches_per_view_calls_and_schema(ib, tmp_path):
+    from invertsy_b200 import datasets, views
+    world = ib.Seville2009()
+    sky = ib.UniformSky(10.)                                   # simulation.py:2602-2603
+    eye = ib.CompoundEye(nb_input=300, omm_rho=np.deg2rad(4.), omm_res=10., c_sensitive=[0, 0., 1., 0., 0.], nb_samples=4)
+    route = ib.Seville2009.load_routes(degrees=True)["path"][0][::100]
+    name = datasets.dataset_name(4, 3, 2, 1, 1, world, nb_ommatidia=300)
+    assert name == "dataset-scan4-rows3-cols2-ant1-route1-seville2009-omm300"
+    stats = datasets.collect_familiarity_dataset(route, eye, world, sky, method="grid", nb_orientations=4, nb_rows=3,
+                                                 nb_cols=2, filename=str(tmp_path / name))
+    L = route.shape[0]
+    assert stats["ommatidia_out"].shape == (L, 300, 3) and stats["xyz_out"].shape == (L, 4)
+    assert stats["ommatidia"].shape == (3 * 2 * 4, 300, 3) and stats["xyz"].shape == (24, 4)
+    with np.load(str(tmp_path / name) + ".npz") as f:
+        assert sorted(f.keys()) == ["ommatidia", "ommatidia_out", "xyz", "xyz_out"]
+        assert np.array_equal(f["ommatidia"], stats["ommatidia"])
+    # the same views one at a time, as the reference's loop does (simulation.py:2660-2707)
+    pos, yaw = views.grid_views(3, 2, 4, z=route[0, 2])
+    for j in (0, 5, 23):
+        p, h = divmod(j, 4)
+        eye.xyz = pos[p]
+        eye.ori = R.from_euler('Z', yaw[p, h], degrees=True)
+        r = eye(sky=sky, scene=world)
+        assert np.abs(r - stats["ommatidia"][j]).max() < 1e-6
+        assert np.allclose(stats["xyz"][j], [pos[p, 0], pos[p, 1], pos[p, 2], yaw[p, h]])
+    par = datasets.collect_familiarity_dataset(route, eye, world, sky, method="parallel", nb_orientations=3, nb_parallel=3)
+    assert par["ommatidia"].shape == (3 * L * 3, 300, 3)
+    blk = datasets.collect_familiarity_dataset(route, eye, world, sky, method="parallel", nb_orientations=3, nb_parallel=3,
+                                               block=(2, 5))
+    assert np.array_equal(blk["ommatidia"], par["ommatidia"][2 * 3:5 * 3])
