@@ -493,64 +493,105 @@ int isy_render_host(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, 
     return rc;
 }
 
+}  // extern "C"
+
+namespace {
+
+// Scratch of the two "call" entry points (one view of N explicit rays, the shape of a closed-loop
+// simulation step): a device arena and a pinned host mirror that only grow, one stream, per device.
+// One packed H2D, the kernels, one packed D2H per call; no allocation after warm-up.
+struct CallCtx {
+    std::mutex mu;
+    bool init = false;
+    cudaStream_t st = nullptr;
+    void* dev = nullptr;
+    size_t dev_bytes = 0;
+    void* pin = nullptr;
+    size_t pin_bytes = 0;
+};
+CallCtx g_call_ctx[16];
+
+cudaError_t grow_pinned(void** p, size_t* have, size_t need) {
+    if (*have >= need) return cudaSuccess;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr, *have = 0;
+    cudaError_t e = cudaMallocHost(p, need);
+    if (e == cudaSuccess) *have = need;
+    return e;
+}
+
+int call_ctx(int device, size_t dev_need, size_t pin_need, CallCtx** out) {
+    if (device < 0 || device >= 16) return fail(ISY_ERR_INVALID, "device index out of range");
+    CallCtx& cx = g_call_ctx[device];
+    if (!cx.init) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&cx.st, cudaStreamNonBlocking));
+        cx.init = true;
+    }
+    CUDA_TRY(grow(&cx.dev, &cx.dev_bytes, dev_need));
+    CUDA_TRY(grow_pinned(&cx.pin, &cx.pin_bytes, pin_need));
+    *out = &cx;
+    return ISY_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int isy_world_call_host(const isy_world* w, const double* pos3_host, const double* ray_quat_host, int64_t N,
                         const double* init_c_host, double* rgb_host, int32_t* hit_host, double* depth_host) {
     if (!w || !pos3_host || !ray_quat_host || N < 0) return fail(ISY_ERR_INVALID, "isy_world_call_host: bad argument");
     if (N == 0) return ISY_OK;
-    isy_eye* eye = nullptr;
-    int rc = isy_eye_create(ray_quat_host, nullptr, N, 1, w->device, &eye);
-    if (rc != ISY_OK) return rc;
+    if (N > (1ll << 28)) return fail(ISY_ERR_INVALID, "isy_world_call_host: too many rays");
     DeviceGuard g(w->device);
-    DevBuf<double> d_pos, d_init, d_rgb, d_depth;
-    DevBuf<int32_t> d_hit;
-    DevBuf<unsigned char> ws;
-    size_t ws_bytes = isy_render_workspace_bytes(w, eye, 1, 1);
-    auto done = [&](int code) {
-        isy_eye_destroy(eye);
-        return code;
-    };
-#define TRY_EYE(expr)                                                                                     \
-    do {                                                                                                  \
-        cudaError_t e__ = (expr);                                                                         \
-        if (e__ != cudaSuccess)                                                                           \
-            return done(fail(ISY_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__)); \
-    } while (0)
-    TRY_EYE(d_pos.alloc(3));
-    TRY_EYE(cudaMemcpy(d_pos.p, pos3_host, 24, cudaMemcpyHostToDevice));
-    if (init_c_host) {
-        TRY_EYE(d_init.alloc(N));
-        TRY_EYE(cudaMemcpy(d_init.p, init_c_host, N * 8, cudaMemcpyHostToDevice));
-    }
+    if (!g.ok) return fail(ISY_ERR_CUDA, "isy_world_call_host: cannot select CUDA device %d (no CPU fallback)", w->device);
+    std::lock_guard<std::mutex> lk(g_call_ctx[std::min(std::max(w->device, 0), 15)].mu);
+    const size_t n = (size_t)N;
+    // a transient eye of N explicit rays (no pitch-sorted table: the per-position bins path serves it)
+    isy_eye eye;
+    memset(&eye, 0, sizeof eye);
+    eye.device = w->device, eye.N = N, eye.S = 1, eye.R = N;
+    const size_t ws_bytes = align_up(isy_render_workspace_bytes(w, &eye, 1, 1));
+    // device layout: [in: pos 3 | quat 4n | init n] [scratch: py 2n | trig 4n] [out: rgb 3n | depth n | hit n(i32)] [ws]
+    const size_t in_d = 3 + 4 * n + (init_c_host ? n : 0);
+    const size_t off_py = align_up(in_d * 8), off_trig = off_py + align_up(2 * n * 8);
+    const size_t off_out = off_trig + align_up(4 * n * 8);
+    const size_t out_bytes = 3 * n * 8 + n * 8 + n * 4;
+    const size_t off_ws = off_out + align_up(out_bytes);
+    CallCtx* cx = nullptr;
+    int rc = call_ctx(w->device, off_ws + ws_bytes, std::max(in_d * 8, out_bytes), &cx);
+    if (rc != ISY_OK) return rc;
+    unsigned char* dev = (unsigned char*)cx->dev;
+    double* pin = (double*)cx->pin;
+    memcpy(pin, pos3_host, 24);
+    memcpy(pin + 3, ray_quat_host, 4 * n * 8);
+    if (init_c_host) memcpy(pin + 3 + 4 * n, init_c_host, n * 8);
+    CUDA_TRY(cudaMemcpyAsync(dev, pin, in_d * 8, cudaMemcpyHostToDevice, cx->st));
+    double* d_in = (double*)dev;
+    eye.d_quat = d_in + 3;
+    eye.d_py = (double*)(dev + off_py);
+    eye.d_trig = (double*)(dev + off_trig);
+    eye_setup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cx->st>>>(eye.d_quat, eye.d_py, eye.d_trig, (int)n);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
     isy_outputs o;
     memset(&o, 0, sizeof o);
-    if (rgb_host) {
-        TRY_EYE(d_rgb.alloc(N * 3));
-        o.rgb = d_rgb.p;
-    }
-    if (hit_host) {
-        TRY_EYE(d_hit.alloc(N));
-        o.hit = d_hit.p;
-    }
-    if (depth_host) {
-        TRY_EYE(d_depth.alloc(N));
-        o.depth = d_depth.p;
-    }
-    TRY_EYE(ws.alloc(ws_bytes));
-    rc = launch_render(w, eye, 1, 1, d_pos.p, nullptr, nullptr, nullptr, d_init.p, nullptr, ISY_FLAG_OUT_F64, &o, ws.p,
-                       ws_bytes, 0);
-    if (rc != ISY_OK) return done(rc);
-    rc = check_status(ws.p, 0);
-    if (rc != ISY_OK) return done(rc);
-    if (rgb_host) TRY_EYE(cudaMemcpy(rgb_host, d_rgb.p, N * 24, cudaMemcpyDeviceToHost));
-    if (hit_host) TRY_EYE(cudaMemcpy(hit_host, d_hit.p, N * 4, cudaMemcpyDeviceToHost));
-    if (depth_host) TRY_EYE(cudaMemcpy(depth_host, d_depth.p, N * 8, cudaMemcpyDeviceToHost));
-    return done(ISY_OK);
-#undef TRY_EYE
+    double* d_rgb = (double*)(dev + off_out);
+    double* d_depth = d_rgb + 3 * n;
+    int32_t* d_hit = (int32_t*)(d_depth + n);
+    if (rgb_host) o.rgb = d_rgb;
+    if (depth_host) o.depth = d_depth;
+    if (hit_host) o.hit = d_hit;
+    rc = launch_render(w, &eye, 1, 1, d_in, nullptr, nullptr, nullptr, init_c_host ? d_in + 3 + 4 * n : nullptr, nullptr,
+                       ISY_FLAG_OUT_F64, &o, dev + off_ws, ws_bytes, cx->st);
+    if (rc != ISY_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(pin, d_rgb, out_bytes, cudaMemcpyDeviceToHost, cx->st));
+    rc = check_status(dev + off_ws, cx->st);   // synchronises the stream
+    if (rc != ISY_OK) return rc;
+    if (rgb_host) memcpy(rgb_host, pin, 3 * n * 8);
+    if (depth_host) memcpy(depth_host, pin + 3 * n, n * 8);
+    if (hit_host) memcpy(hit_host, pin + 4 * n, n * 4);
+    return ISY_OK;
 }
-
-}  // extern "C"
-
-extern "C" {
 
 int isy_sky_call_host(const isy_sky_params* sky, double theta_s, double phi_s, const double* ray_quat_host, int64_t N,
                       const uint8_t* eta_host, int device, double* Y_host, double* dop_host, double* aop_host,
@@ -562,34 +603,40 @@ int isy_sky_call_host(const isy_sky_params* sky, double theta_s, double phi_s, c
     if (N == 0) return ISY_OK;
     DeviceGuard g(device);
     if (!g.ok) return fail(ISY_ERR_CUDA, "isy_sky_call_host: cannot select CUDA device %d (no CPU fallback)", device);
-    DevBuf<double> d_q, d_out, d_sun;
-    DevBuf<SunConst> d_sc;
-    DevBuf<uint8_t> d_eta;
-    if (eta_host) {
-        CUDA_TRY(d_eta.alloc((size_t)N));
-        CUDA_TRY(cudaMemcpy(d_eta.p, eta_host, (size_t)N, cudaMemcpyHostToDevice));
-    }
-    CUDA_TRY(d_q.alloc((size_t)N * 4));
-    CUDA_TRY(d_out.alloc((size_t)N * 5));
-    CUDA_TRY(d_sun.alloc(2));
-    CUDA_TRY(d_sc.alloc(1));
-    CUDA_TRY(cudaMemcpy(d_q.p, ray_quat_host, (size_t)N * 32, cudaMemcpyHostToDevice));
+    std::lock_guard<std::mutex> lk(g_call_ctx[std::min(std::max(device, 0), 15)].mu);
+    const size_t n = (size_t)N;
+    // device layout: [in: sun 2 | quat 4n | eta n bytes] [SunConst] [out: Y P A theta phi, n each]
+    const size_t in_bytes = (2 + 4 * n) * 8 + (eta_host ? n : 0);
+    const size_t off_sc = align_up(in_bytes), off_out = off_sc + align_up(sizeof(SunConst));
+    const size_t out_bytes = 5 * n * 8;
+    CallCtx* cx = nullptr;
+    int rc = call_ctx(device, off_out + out_bytes, std::max(in_bytes, out_bytes), &cx);
+    if (rc != ISY_OK) return rc;
+    unsigned char* dev = (unsigned char*)cx->dev;
+    double* pin = (double*)cx->pin;
+    pin[0] = theta_s, pin[1] = phi_s;
+    memcpy(pin + 2, ray_quat_host, 4 * n * 8);
+    if (eta_host) memcpy(pin + 2 + 4 * n, eta_host, n);
+    CUDA_TRY(cudaMemcpyAsync(dev, pin, in_bytes, cudaMemcpyHostToDevice, cx->st));
+    double* d_in = (double*)dev;
+    SunConst* d_sc = (SunConst*)(dev + off_sc);
     if (sky->kind == ISY_SKY_PEREZ) {
-        double s[2] = {theta_s, phi_s};
-        CUDA_TRY(cudaMemcpy(d_sun.p, s, 16, cudaMemcpyHostToDevice));
-        sun_setup_kernel<<<1, 32>>>(d_sun.p, 1, *sky, d_sc.p);
+        sun_setup_kernel<<<1, 32, 0, cx->st>>>(d_in, 1, *sky, d_sc);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
     }
-    double *dY = d_out.p, *dP = dY + N, *dA = dP + N, *dT = dA + N, *dF = dT + N;
-    sky_dirs_kernel<<<(unsigned)((N + 255) / 256), 256>>>(d_q.p, N, *sky, d_sc.p, d_eta.p, dY, dP, dA, dT, dF);
+    double *dY = (double*)(dev + off_out), *dP = dY + n, *dA = dP + n, *dT = dA + n, *dF = dT + n;
+    sky_dirs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cx->st>>>(
+        d_in + 2, N, *sky, d_sc, eta_host ? (const uint8_t*)(d_in + 2 + 4 * n) : nullptr, dY, dP, dA, dT, dF);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpy(Y_host, dY, (size_t)N * 8, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(dop_host, dP, (size_t)N * 8, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(aop_host, dA, (size_t)N * 8, cudaMemcpyDeviceToHost));
-    if (theta_host) CUDA_TRY(cudaMemcpy(theta_host, dT, (size_t)N * 8, cudaMemcpyDeviceToHost));
-    if (phi_host) CUDA_TRY(cudaMemcpy(phi_host, dF, (size_t)N * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpyAsync(pin, dY, out_bytes, cudaMemcpyDeviceToHost, cx->st));
+    CUDA_TRY(cudaStreamSynchronize(cx->st));
+    memcpy(Y_host, pin, n * 8);
+    memcpy(dop_host, pin + n, n * 8);
+    memcpy(aop_host, pin + 2 * n, n * 8);
+    if (theta_host) memcpy(theta_host, pin + 3 * n, n * 8);
+    if (phi_host) memcpy(phi_host, pin + 4 * n, n * 8);
     return ISY_OK;
 }
 
