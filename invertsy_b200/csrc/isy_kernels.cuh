@@ -750,46 +750,58 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
         const int pos = __ldg(rp.grid_pos_of + rr);
         const int hend = min(Hcur, (hc + 1) * hper);
 
-        for (int hh = hc * hper; hh < hend; ++hh) {
-            const size_t view = (size_t)p * rp.H + grp + (size_t)hh * rp.ngroups;   // group = every ngroups-th heading
-            const size_t vbase = view * (size_t)R;                                  // first ray of this view
-            const int hs = sm.ras.hinv[hh];
-            const unsigned int id = kSmem ? (unsigned)sm.ras.best[hs * R + pos] : gbest[(size_t)hs * R + pos];
-            double Y = 0, P = 0, A = CUDART_NAN;
-            if (perez) {
-                const double hs = sm.head_sin[hh], hcs = sm.head_cos[hh];
-                const double sy = t4v.z * hcs + t4v.w * hs, cy = t4v.w * hcs - t4v.z * hs;   // yaw_e + heading
-                const SunConst& sc = rp.sun_per_view ? rp.sun[view] : sm.sun0;   // one sun: read from shared memory
-                sky_eval<false>(rp.sky, sc, t4v.y * cy, t4v.y * sy, -t4v.x, e_pitch + kHalfPi, f_theta, Y, P, A, false, sm.gtab);
-            } else if (uniform) {
-                Y = rp.sky.luminance;
-            }
-            float cr = nanf_, cg = nanf_, cb = nanf_, depth = nanf_;
-            int hit = -1;
-            if (from_sky) {                                              // luminance2skycolour, world.py:479
-                cr = (float)fmin(fmax(19.0 * Y + 13.0, 0.0), 255.0);
-                cg = (float)fmin(fmax(19.0 * Y + 135.0, 0.0), 255.0);
-                cb = (float)fmin(fmax(19.0 * Y + 201.0, 0.0), 255.0);
-            }
-            if (ground) cr = (float)(229.0 / 255.0), cg = (float)(183.0 / 255.0), cb = (float)(90.0 / 255.0);
-            if (id != kNoCopy) {
-                const Entry& w = sm.tile[id];
-                hit = w.tri;
-                depth = (float)__hiloint2double(w.dist_hi, w.dist_lo);
-                const float* col = rp.tri_rgb + 3 * (size_t)hit;
-                cr = __ldg(col + 0), cg = __ldg(col + 1), cb = __ldg(col + 2);
-            }
-            if (valid) {
-                const size_t i = vbase + r;
-                if (o_rgb) {
-                    float* q = o_rgb + 3 * i;
-                    q[0] = cr, q[1] = cg, q[2] = cb;
+        // two headings per trip: their sky evaluations are independent instruction streams (the pass is
+        // bound by the latency of the fp64 chain, not by issue slots)
+        for (int hh0 = hc * hper; hh0 < hend; hh0 += 2) {
+            double Y[2] = {0, 0}, P[2] = {0, 0}, A[2] = {CUDART_NAN, CUDART_NAN};
+            size_t view[2];
+            unsigned int id[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int hh = min(hh0 + q, hend - 1);
+                view[q] = (size_t)p * rp.H + grp + (size_t)hh * rp.ngroups;   // group = every ngroups-th heading
+                const int hs = sm.ras.hinv[hh];
+                id[q] = kSmem ? (unsigned)sm.ras.best[hs * R + pos] : gbest[(size_t)hs * R + pos];
+                if (perez) {
+                    const double hsn = sm.head_sin[hh], hcs = sm.head_cos[hh];
+                    const double sy = t4v.z * hcs + t4v.w * hsn, cy = t4v.w * hcs - t4v.z * hsn;   // yaw_e + heading
+                    const SunConst& sc = rp.sun_per_view ? rp.sun[view[q]] : sm.sun0;   // one sun: shared memory
+                    sky_eval<false>(rp.sky, sc, t4v.y * cy, t4v.y * sy, -t4v.x, e_pitch + kHalfPi, f_theta, Y[q], P[q], A[q],
+                                    false, sm.gtab);
+                } else if (uniform) {
+                    Y[q] = rp.sky.luminance;
                 }
-                if (rp.out.hit) rp.out.hit[i] = hit;
-                if (o_depth) o_depth[i] = depth;
-                if (o_Y) o_Y[i] = (float)Y;
-                if (o_P) o_P[i] = (float)P;
-                if (o_A) o_A[i] = (float)A;
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (hh0 + q >= hend) break;
+                float cr = nanf_, cg = nanf_, cb = nanf_, depth = nanf_;
+                int hit = -1;
+                if (from_sky) {                                              // luminance2skycolour, world.py:479
+                    cr = (float)fmin(fmax(19.0 * Y[q] + 13.0, 0.0), 255.0);
+                    cg = (float)fmin(fmax(19.0 * Y[q] + 135.0, 0.0), 255.0);
+                    cb = (float)fmin(fmax(19.0 * Y[q] + 201.0, 0.0), 255.0);
+                }
+                if (ground) cr = (float)(229.0 / 255.0), cg = (float)(183.0 / 255.0), cb = (float)(90.0 / 255.0);
+                if (id[q] != kNoCopy) {
+                    const Entry& w = sm.tile[id[q]];
+                    hit = w.tri;
+                    depth = (float)__hiloint2double(w.dist_hi, w.dist_lo);
+                    const float* col = rp.tri_rgb + 3 * (size_t)hit;
+                    cr = __ldg(col + 0), cg = __ldg(col + 1), cb = __ldg(col + 2);
+                }
+                if (valid) {
+                    const size_t i = view[q] * (size_t)R + r;
+                    if (o_rgb) {
+                        float* qq = o_rgb + 3 * i;
+                        qq[0] = cr, qq[1] = cg, qq[2] = cb;
+                    }
+                    if (rp.out.hit) rp.out.hit[i] = hit;
+                    if (o_depth) o_depth[i] = depth;
+                    if (o_Y) o_Y[i] = (float)Y[q];
+                    if (o_P) o_P[i] = (float)P[q];
+                    if (o_A) o_A[i] = (float)A[q];
+                }
             }
         }
     }
