@@ -147,6 +147,24 @@ def main():
     np.savez_compressed(os.path.join(OUT, "world_initc.npz"), poses=np.asarray(poses[:3]), rgb=np.asarray(rgb64),
                         init_c=np.asarray(ys), uniform_Y=uy, uniform_P=up, uniform_A=ua)
 
+    # ---- sun ephemeris (row N4): reference Sun.compute on random places / times ----
+    import importlib
+    from datetime import datetime, timedelta
+    eph = importlib.import_module('invertsy.env.ephemeris')
+    obsm = importlib.import_module('invertsy.env.observer')
+    erng = np.random.RandomState(4)
+    rows = []
+    for _ in range(200):
+        d = datetime(2021, 1, 1) + timedelta(seconds=int(erng.uniform(0, 365 * 86400)))
+        lon, lat = erng.uniform(-np.pi, np.pi), erng.uniform(-1.4, 1.4)
+        ob = obsm.Observer(lon=lon, lat=lat, date=d)
+        sun = eph.Sun()
+        sun.compute(ob)
+        rows.append((d.year, d.month, d.day, d.hour, d.minute, d.second, lon, lat, ob.tzgmt, sun.alt, sun.az))
+    dsk = refsky.Sky.from_observer()
+    np.savez_compressed(os.path.join(OUT, "ephemeris.npz"), rows=np.asarray(rows, dtype=np.float64),
+                        default_sky=np.array([dsk.theta_s, dsk.phi_s]))
+
     import scipy
     meta = dict(reference_sha256=reference_file_hashes(), numpy=np.__version__, scipy=scipy.__version__,
                 note="generated by oracle/gen_golden.py from the unmodified reference")

@@ -166,3 +166,21 @@ def test_sky_table_construction_is_accurate_enough():
             sel = (c < 0) == bool(half)
             out[sel] = val[sel]
         assert np.abs(out - np.exp(D * np.arccos(c))).max() < 1e-9
+
+
+def test_ephemeris_matches_reference_goldens():
+    """vectorised NOAA sun position == the reference's Sun.compute (goldens made from the reference)"""
+    from datetime import datetime
+    import invertsy_b200 as ib
+    from invertsy_b200 import ephemeris
+    g = golden("ephemeris")
+    rows = g["rows"]
+    dates = [datetime(*[int(v) for v in r[:6]]) for r in rows]
+    alt, az = ephemeris.sun_position(rows[:, 6], rows[:, 7], dates, rows[:, 8])
+    assert np.abs(alt - rows[:, 9]).max() < 1e-12 and np.abs(az - rows[:, 10]).max() < 1e-12
+    sky = ib.Sky.from_observer()                       # Seville, 21/06/2021 10:00 (sky.py:597-609)
+    if datetime.now().astimezone().utcoffset().total_seconds() == 0:   # the reference's tz rule reads the local clock
+        assert np.allclose([sky.theta_s, sky.phi_s], g["default_sky"], atol=1e-12)
+    from scipy.spatial.transform import Rotation as R
+    s2 = ib.Sky.from_observer(ori=R.from_euler('Z', 0.5))
+    assert abs(((s2.phi_s - (sky.phi_s - 0.5) + np.pi) % (2 * np.pi)) - np.pi) < 1e-12
