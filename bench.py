@@ -279,7 +279,7 @@ def main():
     value = world_size * B * args.steps / (elapsed_ms / 1e3)
 
     pc = r.phase_cycles().astype(np.float64)
-    phase = {"project_frac": pc[0] / pc[:3].sum(), "bin_frac": pc[1] / pc[:3].sum(), "rays_frac": pc[2] / pc[:3].sum(),
+    phase = {"project_frac": pc[0] / pc[:3].sum(), "raster_frac": pc[1] / pc[:3].sum(), "shade_frac": pc[2] / pc[:3].sum(),
              "cycles_per_position": pc[:3].sum() / max(pc[3], 1)}
     # sanity on the last step's result (cheap, outside the timed region)
     hit_frac = float((out["hit"][: 36 * 64] >= 0).float().mean().item())

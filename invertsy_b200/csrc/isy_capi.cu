@@ -356,14 +356,6 @@ int isy_workspace_status(void* workspace_dev, void* stream) { return check_statu
 
 int isy_workspace_phase_cycles(void* workspace_dev, void* stream, uint64_t* out4) {
     if (!workspace_dev || !out4) return fail(ISY_ERR_INVALID, "isy_workspace_phase_cycles: bad argument");
-#ifdef ISY_DBG_COUNT
-    {
-        uint64_t dbg[8];
-        cudaMemcpy(dbg, (unsigned char*)workspace_dev + 256 + 64, sizeof dbg, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "DBG positions=%llu iters=%llu rounds=%llu tests=%llu posts=%llu\n", (unsigned long long)dbg[3],
-                (unsigned long long)dbg[4], (unsigned long long)dbg[5], (unsigned long long)dbg[6], (unsigned long long)dbg[7]);
-    }
-#endif
     CUDA_TRY(cudaMemcpyAsync(out4, (unsigned char*)workspace_dev + 256 + 64, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                              (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));

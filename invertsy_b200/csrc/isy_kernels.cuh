@@ -602,9 +602,6 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
         // instruction streams, which is what hides the shared-memory and branch latencies here
         for (unsigned jb = jbeg; jb < jend; jb += 32 * kRU) {   // warp-uniform trip count
             __syncwarp();                                       // keep the lanes converged across iterations
-#ifdef ISY_DBG_COUNT
-            if (lane == 0) atomicAdd(&rp.phase_cycles[4], 1ull);
-#endif
             float2 py[kRU];
             int k[kRU], ks[kRU];    // window cursor; sorted slot of the heading under the cursor
             float upper[kRU];
@@ -653,10 +650,6 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
                     any |= act[u];
                 }
                 if (!__any_sync(0xffffffffu, any)) break;
-#ifdef ISY_DBG_COUNT
-                if (lane == 0) atomicAdd(&rp.phase_cycles[5], 1ull);
-                for (int u = 0; u < kRU; ++u) if (act[u]) atomicAdd(&rp.phase_cycles[6], 1ull);
-#endif
                 float fy[kRU], m[kRU];
 #pragma unroll
                 for (int u = 0; u < kRU; ++u) {                 // branch-free: the common case of every slot
@@ -694,9 +687,6 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
                         if (kSmem) post_copy_u16(sm.ras.best, (unsigned)ks[u] * R + j, sm.tile, dist, ent.tri, e);
                         else post_copy_u32(&gbest[(size_t)ks[u] * R + j], sm.tile, dist, ent.tri, e);
                     }
-#ifdef ISY_DBG_COUNT
-                    if (in) atomicAdd(&rp.phase_cycles[7], 1ull);
-#endif
                     if (kUniform) {
                         if (act[u]) {
                             --k[u];

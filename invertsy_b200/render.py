@@ -121,6 +121,7 @@ class Renderer(object):
         self._w = world._device_world()
         self._e = eye._device_eye(self.device)
         self._workspace = None
+        self._inflight = None
 
     # ---- helpers ----
     def _dev(self, a, shape):
@@ -203,8 +204,8 @@ class Renderer(object):
                                          None if sun_t is None else sun_t.data_ptr(),
                                          ctypes.byref(sp), flags, ctypes.byref(o), ws.data_ptr(), ws.numel(),
                                          ctypes.c_void_p(stream)))
-        # keep inputs alive until the stream has consumed them
-        res["_keepalive"] = (pos, yaw, quat, sun_t)
+        # keep the input tensors alive until the stream has consumed them
+        self._inflight = (pos, yaw, quat, sun_t)
         return res
 
     def check(self):
