@@ -74,6 +74,10 @@ struct isy_eye {
     void* d_sorted;              // R x float2 (pitch, yaw), pitch order
     int* d_pos_of;               // R: sorted position of ray r
     int* d_sorted_ray;           // R: ray at sorted position j
+    // static (pitch, yaw) ray grid for the few-headings rasteriser
+    int cells_rows, cells_cols;
+    unsigned int* d_cells_start; // rows*cols + 1
+    unsigned int* d_cells_list;  // R: pitch-sorted positions, cell by cell
 };
 
 extern "C" {
@@ -117,7 +121,7 @@ int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int3
     if (N * S > (1ll << 30)) return fail(ISY_ERR_INVALID, "isy_eye_create: too many rays");
     DeviceGuard g(device);
     if (!g.ok) return fail(ISY_ERR_CUDA, "isy_eye_create: cannot select CUDA device %d (no CPU fallback)", device);
-    isy_eye* e = new isy_eye{device, N, S, N * S, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    isy_eye* e = new isy_eye{device, N, S, N * S, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr};
     size_t R = (size_t)e->R;
     CUDA_TRY(cudaMalloc(&e->d_quat, R * 4 * sizeof(double)));
     CUDA_TRY(cudaMalloc(&e->d_py, R * 2 * sizeof(double)));
@@ -169,6 +173,29 @@ int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int3
         CUDA_TRY(cudaMemcpy(e->d_plut, plut.data(), (kPitchLut + 1) * sizeof(unsigned int), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(e->d_sorted, hot.data(), 2 * R * sizeof(float), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(e->d_pos_of, pos_of.data(), R * sizeof(int), cudaMemcpyHostToDevice));
+
+        // (pitch, yaw) grid with about one ray per cell; lists hold pitch-sorted positions
+        int gp = 4;
+        while (gp < 512 && (size_t)gp * gp < R) gp *= 2;
+        if ((size_t)gp * 2 * gp > (size_t)kCellsSmem && R <= (size_t)kGridRaysSmem) gp = 32;   // shared-memory budget
+        e->cells_rows = gp, e->cells_cols = 2 * gp;
+        const size_t ncell = (size_t)gp * 2 * gp;
+        std::vector<unsigned int> cstart(ncell + 1, 0), cell_of(R), clist(R);
+        for (size_t r = 0; r < R; ++r) {
+            int row = (int)std::floor((py[2 * r] + pi / 2) * e->cells_rows / pi);
+            int colc = (int)std::floor((py[2 * r + 1] + pi) * e->cells_cols / (2 * pi));
+            row = std::min(std::max(row, 0), e->cells_rows - 1);
+            colc = std::min(std::max(colc, 0), e->cells_cols - 1);
+            cell_of[r] = (unsigned)row * e->cells_cols + colc;
+            cstart[cell_of[r] + 1]++;
+        }
+        for (size_t c = 0; c < ncell; ++c) cstart[c + 1] += cstart[c];
+        std::vector<unsigned int> cur(cstart.begin(), cstart.end() - 1);
+        for (size_t r = 0; r < R; ++r) clist[cur[cell_of[r]]++] = (unsigned int)pos_of[r];
+        CUDA_TRY(cudaMalloc(&e->d_cells_start, (ncell + 1) * sizeof(unsigned int)));
+        CUDA_TRY(cudaMalloc(&e->d_cells_list, R * sizeof(unsigned int)));
+        CUDA_TRY(cudaMemcpy(e->d_cells_start, cstart.data(), (ncell + 1) * sizeof(unsigned int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(e->d_cells_list, clist.data(), R * sizeof(unsigned int), cudaMemcpyHostToDevice));
     }
     *out = e;
     return ISY_OK;
@@ -185,6 +212,8 @@ int isy_eye_destroy(isy_eye* e) {
     cudaFree(e->d_sorted);
     cudaFree(e->d_pos_of);
     cudaFree(e->d_sorted_ray);
+    cudaFree(e->d_cells_start);
+    cudaFree(e->d_cells_list);
     delete e;
     return ISY_OK;
 }
@@ -285,6 +314,8 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
     rp.Hg = pl.Hg, rp.ngroups = pl.ngroups;
     rp.grid_plut = e->d_plut, rp.grid_sorted = e->d_sorted, rp.grid_pos_of = e->d_pos_of;
     rp.grid_sorted_ray = e->d_sorted_ray;
+    rp.cells_start = e->d_cells_start, rp.cells_list = e->d_cells_list;
+    rp.cells_rows = e->cells_rows, rp.cells_cols = e->cells_cols;
 
     CUDA_TRY(cudaMemsetAsync(base, 0, 512, st));
     if (sp.kind == ISY_SKY_PEREZ) {

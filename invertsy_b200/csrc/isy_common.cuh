@@ -78,6 +78,10 @@ struct RenderParams {
     const unsigned int* grid_plut;        // [kPitchLut + 1] first sorted ray at or above each pitch slot
     const void* grid_sorted;              // [R] float2 (pitch, yaw) of the rays in pitch order
     const int* grid_sorted_ray;           // [R] ray index of each sorted position
+    // the eye's static (pitch, yaw) ray grid (few-headings rasteriser)
+    const unsigned int* cells_start;      // [rows*cols + 1]
+    const unsigned int* cells_list;       // [R] pitch-sorted positions of the rays, cell by cell
+    int cells_rows, cells_cols;
     const int* grid_pos_of;               // [R] sorted position of ray r
     int N, S, R;
     // views

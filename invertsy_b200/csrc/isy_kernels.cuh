@@ -40,6 +40,8 @@ constexpr int kBestCap = 36864;       // (heading, ray) slots of the rasteriser'
 constexpr int kGridRaysSmem = 1280;   // eyes up to this many rays keep their pitch-sorted ray table in shared memory
 constexpr int kPitchLut = 1024;       // slots of the pitch -> first sorted ray look-up table
 constexpr int kHeadLut = 1024;        // slots of the azimuth -> first sorted heading look-up table
+constexpr int kCellsSmem = 2048;      // cells of the eye's (pitch, yaw) ray grid kept in shared memory
+constexpr int kSmallH = 4;            // up to this many headings per group the rasteriser walks the ray grid
 
 struct SmemBins {
     unsigned int bin_off[kBins + 4];  // exclusive offsets into list (counts during the count pass)
@@ -57,6 +59,8 @@ struct SmemRaster {
     unsigned char hinv[kMaxH];        // sorted slot of each heading
     unsigned short hlut[kHeadLut];    // first sorted slot that can reach each azimuth slot
     float uni[4];                     // {h0, delta, 1/delta, flag}: sorted headings are h0 + k*delta over the full circle
+    unsigned int cell_start[kCellsSmem + 4];      // the eye's static (pitch, yaw) ray grid: first list entry of each cell
+    unsigned short cell_list[kGridRaysSmem];      // ... and the pitch-sorted positions of the rays in each cell
 };
 
 struct SmemLayout {
@@ -702,6 +706,118 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
 }
 
 // ------------------------------------------------------------------------------------------
+// Few headings per position (single views, route batches): walking every ray of a copy's pitch band
+// would test ~98 % of the pairs for nothing, so each (copy, heading) pair instead visits the few
+// cells of the eye's static (pitch, yaw) ray grid under the copy's bounding box, shifted by the
+// heading.  Lanes hold different pairs; the work per position is a few thousand warp instructions.
+// ------------------------------------------------------------------------------------------
+// tests the rays stored in one cell of the eye's ray grid against one projected copy at one heading
+template <bool kSmem>
+__device__ __forceinline__ void raster_cell(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest,
+                                            const Exact* exacts, int cell, const Entry& ent, double dist, int e, int hh,
+                                            int hs, float hf) {
+    const int R = rp.R;
+    const float2* gsorted = reinterpret_cast<const float2*>(rp.grid_sorted);
+    const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
+    const unsigned i0 = kSmem ? sm.ras.cell_start[cell] : __ldg(rp.cells_start + cell);
+    const unsigned i1 = kSmem ? sm.ras.cell_start[cell + 1] : __ldg(rp.cells_start + cell + 1);
+    for (unsigned i = i0; i < i1; ++i) {
+        const unsigned j = kSmem ? (unsigned)sm.ras.cell_list[i] : __ldg(rp.cells_list + i);
+        const float2 py = kSmem ? sm.ras.sorted[j] : __ldg(gsorted + j);
+        float fy = py.y + hf;                                  // both in (-pi, pi]: one shift wraps
+        fy = fy > pi_f ? fy - twopi_f : (fy <= -pi_f ? fy + twopi_f : fy);
+        const bool seam = fabsf(fy) > 3.14159f;
+        float m = fminf(fmaf(ent.A0, py.x, fmaf(ent.B0, fy, ent.C0)),
+                        fminf(fmaf(ent.A1, py.x, fmaf(ent.B1, fy, ent.C1)), fmaf(ent.A2, py.x, fmaf(ent.B2, fy, ent.C2))));
+        if (!seam && m < -kEdgeEps) continue;
+        bool in = m > kEdgeEps && !seam;
+        if (!in) {   // redo the query in fp64 exactly as the reference composes it
+            const int ray = __ldg(rp.grid_sorted_ray + j);
+            double yg = rp.eye_py[2 * (size_t)ray + 1] + sm.head_val[hh];
+            if (yg > kPi) yg -= kTwoPi;
+            else if (yg <= -kPi) yg += kTwoPi;
+            const float f = (float)yg;
+            m = fminf(fmaf(ent.A0, py.x, fmaf(ent.B0, f, ent.C0)),
+                      fminf(fmaf(ent.A1, py.x, fmaf(ent.B1, f, ent.C1)), fmaf(ent.A2, py.x, fmaf(ent.B2, f, ent.C2))));
+            in = m > kEdgeEps;
+            if (!in && m >= -kEdgeEps) in = inside_exact(exacts[e], rp.eye_py[2 * (size_t)ray], yg);
+        }
+        if (in) {
+            if (kSmem) post_copy_u16(sm.ras.best, (unsigned)hs * R + j, sm.tile, dist, ent.tri, e);
+            else post_copy_u32(&gbest[(size_t)hs * R + j], sm.tile, dist, ent.tri, e);
+        }
+    }
+}
+
+template <bool kSmem>
+__device__ void raster_cells(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest, const Exact* exacts, int E,
+                             int Hcur, int* s_next) {
+    const int lane = threadIdx.x & 31, Gp = rp.cells_rows, Gy = rp.cells_cols;
+    const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
+    const float inv_dp = (float)Gp / pi_f, inv_dy = (float)Gy / twopi_f;
+    const int items = E * Hcur;
+    constexpr int kBigItem = 12;    // pairs that cover more cells than this are walked by the whole warp
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = smem_atomic_add(s_next, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= items) break;
+        const int item = base + lane;
+        int e = 0, hh = 0, r0 = 0, nrows = 0, c0 = 0, ncols = 0;
+        if (item < items) {
+            e = item / Hcur, hh = item - e * Hcur;
+            const float4 bb = sm.bbox[e];
+            const float glo = fmaxf(bb.z, -pi_f - kBinMargin) - kBinMargin, ghi = fminf(bb.w, pi_f + kBinMargin) + kBinMargin;
+            if (glo <= ghi) {
+                const float hf = (float)sm.head_val[hh];
+                // eye-frame azimuth window [glo - h, ghi - h], as a run of grid columns modulo the circle
+                const int c_first = (int)floorf((glo - hf + pi_f) * inv_dy);
+                ncols = min((int)floorf((ghi - hf + pi_f) * inv_dy) - c_first + 1, Gy);
+                c0 = c_first % Gy;
+                if (c0 < 0) c0 += Gy;
+                r0 = max((int)floorf((bb.x + (float)kHalfPi) * inv_dp), 0);
+                nrows = max(min((int)floorf((bb.y + (float)kHalfPi) * inv_dp), Gp - 1) - r0 + 1, 0);
+            }
+        }
+        const int ncell = nrows * ncols;
+        // small pairs: one lane each
+        if (ncell > 0 && ncell <= kBigItem) {
+            const Entry ent = sm.tile[e];
+            const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
+            const float hf = (float)sm.head_val[hh];
+            const int hs = sm.ras.hinv[hh];
+            for (int q = 0; q < ncell; ++q) {
+                const int row = r0 + q / ncols;
+                int c = c0 + q % ncols;
+                if (c >= Gy) c -= Gy;
+                raster_cell<kSmem>(rp, sm, gbest, exacts, row * Gy + c, ent, dist, e, hh, hs, hf);
+            }
+        }
+        // large pairs (a blade right in front of the eye): the warp shares their cells
+        unsigned int big = __ballot_sync(0xffffffffu, ncell > kBigItem);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const int be = __shfl_sync(0xffffffffu, e, src), bh = __shfl_sync(0xffffffffu, hh, src);
+            const int br0 = __shfl_sync(0xffffffffu, r0, src), bc0 = __shfl_sync(0xffffffffu, c0, src);
+            const int bnc = __shfl_sync(0xffffffffu, ncols, src), bn = __shfl_sync(0xffffffffu, ncell, src);
+            const Entry ent = sm.tile[be];
+            const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
+            const float hf = (float)sm.head_val[bh];
+            const int hs = sm.ras.hinv[bh];
+            for (int q = lane; q < bn; q += 32) {
+                const int row = br0 + q / bnc;
+                int c = bc0 + q % bnc;
+                if (c >= Gy) c -= Gy;
+                raster_cell<kSmem>(rp, sm, gbest, exacts, row * Gy + c, ent, dist, be, bh, hs, hf);
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // final pass of the rasteriser path, float outputs, one sample per ommatidium: per ray pick the
 // winner from best[], shade, evaluate the sky and write the view (the only HBM traffic).
 // Warp units = (block of 32 consecutive rays) x (chunk of headings); a ray's eye data are loaded
@@ -841,8 +957,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                 mode = kModeRaster;
                 if (smem_grid && !grid_loaded) {   // the bins path shares this memory: (re)load when needed
                     for (int i = tid; i <= kPitchLut; i += kThreads) sm.ras.plut[i] = rp.grid_plut[i];
-                    for (int i = tid; i < rp.R; i += kThreads)
+                    for (int i = tid; i < rp.R; i += kThreads) {
                         sm.ras.sorted[i] = reinterpret_cast<const float2*>(rp.grid_sorted)[i];
+                        sm.ras.cell_list[i] = (unsigned short)rp.cells_list[i];
+                    }
+                    for (int i = tid; i <= rp.cells_rows * rp.cells_cols; i += kThreads) sm.ras.cell_start[i] = rp.cells_start[i];
                     grid_loaded = true;
                 }
             } else if (build_bins(sm, grid, E, s_band, s_warp)) {
@@ -875,7 +994,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                 sort_headings(sm, Hcur);
                 __syncthreads();
                 const bool uniform = sm.ras.uni[3] != 0.f;
-                if (smem_grid) {
+                if (Hcur <= kSmallH && smem_grid) {
+                    // (large eyes keep the pitch-run walk: their cells hold many rays and the lanes of a run stay full)
+                    raster_cells<true>(rp, sm, gbest, exacts, E, Hcur, &s_count);
+                } else if (smem_grid) {
                     if (uniform) raster_copies<true, true>(rp, sm, gbest, exacts, E, Hcur, &s_count);
                     else raster_copies<true, false>(rp, sm, gbest, exacts, E, Hcur, &s_count);
                 } else {
