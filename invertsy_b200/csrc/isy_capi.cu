@@ -58,6 +58,11 @@ struct isy_world {
     double horizon;
     float* d_planes;  // 9 planes of T floats
     float* d_rgb;     // T*3
+    // xy cell grid (cell = horizon / 4): triangles filed under the cell of each of their vertices
+    unsigned int* d_cell_start;
+    unsigned int* d_cell_tris;
+    float gx0, gy0, ginv;
+    int gnx, gny;
 };
 
 struct isy_eye {
@@ -88,10 +93,10 @@ int64_t isy_launch_count(void) { return g_launches.load(); }
 
 int isy_world_create(const float* tri_xyz, const float* tri_rgb, int64_t T, double horizon, int device,
                      isy_world** out) {
-    if (!tri_xyz || !tri_rgb || !out || T < 0 || T > (1 << 30)) return fail(ISY_ERR_INVALID, "isy_world_create: bad argument");
+    if (!tri_xyz || !tri_rgb || !out || T < 0 || T >= (1 << 30)) return fail(ISY_ERR_INVALID, "isy_world_create: bad argument");
     DeviceGuard g(device);
     if (!g.ok) return fail(ISY_ERR_CUDA, "isy_world_create: cannot select CUDA device %d (no CPU fallback)", device);
-    isy_world* w = new isy_world{device, T, horizon, nullptr, nullptr};
+    isy_world* w = new isy_world{device, T, horizon, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, 1.f, 1, 1};
     size_t n = (size_t)std::max<int64_t>(T, 1);
     std::vector<float> planes(9 * n);
     for (int64_t t = 0; t < T; ++t)
@@ -100,6 +105,54 @@ int isy_world_create(const float* tri_xyz, const float* tri_rgb, int64_t T, doub
     CUDA_TRY(cudaMalloc(&w->d_rgb, 3 * n * sizeof(float)));
     CUDA_TRY(cudaMemcpy(w->d_planes, planes.data(), 9 * (size_t)T * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(w->d_rgb, tri_rgb, 3 * (size_t)T * sizeof(float), cudaMemcpyHostToDevice));
+    if (T >= (1 << 30)) return fail(ISY_ERR_INVALID, "isy_world_create: too many triangles");
+
+    // ---- xy cell grid over the vertices ----
+    {
+        float xmin = 0.f, xmax = 1.f, ymin = 0.f, ymax = 1.f;
+        bool any = false;
+        for (int64_t t = 0; t < T; ++t)
+            for (int k = 0; k < 3; ++k) {
+                const float x = tri_xyz[t * 9 + 3 * k], y = tri_xyz[t * 9 + 3 * k + 1];
+                if (!(x == x) || !(y == y) || std::isinf(x) || std::isinf(y)) continue;
+                if (!any) xmin = xmax = x, ymin = ymax = y, any = true;
+                xmin = std::min(xmin, x), xmax = std::max(xmax, x), ymin = std::min(ymin, y), ymax = std::max(ymax, y);
+            }
+        double cell = horizon > 0 ? horizon / 4 : 1.0;
+        const double span_x = std::max<double>(xmax - xmin, 1e-3), span_y = std::max<double>(ymax - ymin, 1e-3);
+        while ((span_x / cell + 1) * (span_y / cell + 1) > 4.0e6) cell *= 2;       // at most ~4 M cells
+        w->gx0 = xmin, w->gy0 = ymin, w->ginv = (float)(1.0 / cell);
+        w->gnx = (int)(span_x / cell) + 1, w->gny = (int)(span_y / cell) + 1;
+        const size_t ncell = (size_t)w->gnx * w->gny;
+        std::vector<unsigned int> start(ncell + 1, 0);
+        std::vector<unsigned int> cells(3 * n);     // cell of each vertex, or ~0u for "not filed"
+        for (int64_t t = 0; t < T; ++t) {
+            bool bad = false;
+            for (int k = 0; k < 9; ++k) bad = bad || !(tri_xyz[t * 9 + k] == tri_xyz[t * 9 + k]);
+            unsigned int c[3];
+            for (int k = 0; k < 3; ++k) {
+                const int cx = world_cell(tri_xyz[t * 9 + 3 * k], w->gx0, w->ginv, w->gnx);
+                const int cy = world_cell(tri_xyz[t * 9 + 3 * k + 1], w->gy0, w->ginv, w->gny);
+                c[k] = (unsigned int)cy * w->gnx + cx;
+            }
+            for (int k = 0; k < 3; ++k) {
+                bool dup = bad;                       // NaN triangles are never visible (world.py:98, :102)
+                for (int j = 0; j < k; ++j) dup = dup || c[j] == c[k];
+                cells[3 * t + k] = dup ? ~0u : c[k];
+                if (!dup) start[c[k] + 1]++;
+            }
+        }
+        for (size_t c = 0; c < ncell; ++c) start[c + 1] += start[c];
+        std::vector<unsigned int> list(std::max<size_t>(start[ncell], 1));
+        std::vector<unsigned int> cur(start.begin(), start.end() - 1);
+        for (int64_t t = 0; t < T; ++t)
+            for (int k = 0; k < 3; ++k)
+                if (cells[3 * t + k] != ~0u) list[cur[cells[3 * t + k]]++] = (unsigned int)t | ((unsigned int)k << 30);
+        CUDA_TRY(cudaMalloc(&w->d_cell_start, (ncell + 1) * sizeof(unsigned int)));
+        CUDA_TRY(cudaMalloc(&w->d_cell_tris, list.size() * sizeof(unsigned int)));
+        CUDA_TRY(cudaMemcpy(w->d_cell_start, start.data(), (ncell + 1) * sizeof(unsigned int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(w->d_cell_tris, list.data(), list.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
+    }
     *out = w;
     return ISY_OK;
 }
@@ -109,6 +162,8 @@ int isy_world_destroy(isy_world* w) {
     DeviceGuard g(w->device);
     cudaFree(w->d_planes);
     cudaFree(w->d_rgb);
+    cudaFree(w->d_cell_start);
+    cudaFree(w->d_cell_tris);
     delete w;
     return ISY_OK;
 }
@@ -294,6 +349,8 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
     RenderParams rp;
     memset(&rp, 0, sizeof rp);
     rp.tri_planes = w->d_planes, rp.tri_rgb = w->d_rgb, rp.T = (int)w->T, rp.horizon = w->horizon;
+    rp.wg_cell_start = w->d_cell_start, rp.wg_cell_tris = w->d_cell_tris;
+    rp.wg_x0 = w->gx0, rp.wg_y0 = w->gy0, rp.wg_inv_cell = w->ginv, rp.wg_nx = w->gnx, rp.wg_ny = w->gny;
     rp.eye_py = e->d_py, rp.eye_quat = e->d_quat, rp.eye_w = e->d_w, rp.eye_trig = e->d_trig;
     rp.eye_ftheta = (const double*)(base + pl.off_ftheta);
     rp.sky_gtab = (const double2*)(base + pl.off_gtab);

@@ -68,6 +68,11 @@ struct RenderParams {
     const float* tri_rgb;
     int T;
     double horizon;
+    // xy cell grid over the world's vertices (cull candidates)
+    const unsigned int* wg_cell_start;   // [ny*nx + 1] row-major
+    const unsigned int* wg_cell_tris;    // triangle index | (vertex tag << 30)
+    float wg_x0, wg_y0, wg_inv_cell;
+    int wg_nx, wg_ny;
     // eye
     const double* eye_py;    // [R][2] eye-frame (pitch, yaw)
     const double* eye_trig;  // [R][4] sin pitch, cos pitch, sin yaw, cos yaw (eye frame)

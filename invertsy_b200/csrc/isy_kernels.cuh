@@ -173,6 +173,13 @@ __device__ __forceinline__ void load_vertices(const float* __restrict__ planes, 
     }
 }
 
+// cell index of a coordinate in the world's xy grid -- the host files vertices with the same float ops
+__host__ __device__ __forceinline__ int world_cell(float x, float x0, float inv_cell, int n) {
+    const float q = (x - x0) * inv_cell;
+    int c = (int)floorf(q);
+    return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+
 __device__ __forceinline__ int float_key(float f) {   // order-preserving int key for atomicMin/Max
     int i = __float_as_int(f);
     return i >= 0 ? i : i ^ 0x7fffffff;
@@ -212,18 +219,59 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
     __syncthreads();
 
     // ---- A1: cull (world.py:97-98) ----
-    for (int base = 0; base < rp.T; base += kThreads) {
-        int t = base + tid;
+    // Candidates come from the world's xy cell grid (isy_world_create): a visible triangle has a vertex
+    // within the horizon, so it is listed in a cell that meets the disc around the eye.  A triangle is
+    // listed once per distinct vertex cell (tagged with that vertex); it is taken from the list entry
+    // whose cell holds its NEAREST vertex, i.e. exactly once.  The test itself is the reference's, fp64.
+    const float gx0 = rp.wg_x0, gy0 = rp.wg_y0, ginv = rp.wg_inv_cell;
+    const int nx = rp.wg_nx, ny = rp.wg_ny;
+    const double slack = 1e-2;   // cells; covers the float rounding of the vertex filing (< 1e-3 cells for 4096 cells a side)
+    const int cx0 = (int)fmax(fmin(floor((px - h - gx0) * ginv - slack), (double)(nx - 1)), 0.0);
+    const int cx1 = (int)fmax(fmin(floor((px + h - gx0) * ginv + slack), (double)(nx - 1)), 0.0);
+    const int cy0 = (int)fmax(fmin(floor((py - h - gy0) * ginv - slack), (double)(ny - 1)), 0.0);
+    const int cy1 = (int)fmax(fmin(floor((py + h - gy0) * ginv + slack), (double)(ny - 1)), 0.0);
+    // the candidate cells form one contiguous list range per grid row: flatten the (<= 16) rows
+    __shared__ unsigned int s_rowbeg[16], s_rowoff[17];
+    const int nrows = min(cy1 - cy0 + 1, 16);   // cell = horizon / 4 or larger: at most 10 rows
+    if (tid == 0) {
+        unsigned int acc = 0;
+        for (int rr = 0; rr < nrows; ++rr) {
+            const unsigned int beg = __ldg(rp.wg_cell_start + (size_t)(cy0 + rr) * nx + cx0);
+            const unsigned int end = __ldg(rp.wg_cell_start + (size_t)(cy0 + rr) * nx + cx1 + 1);
+            s_rowbeg[rr] = beg;
+            s_rowoff[rr] = acc;
+            acc += end - beg;
+        }
+        s_rowoff[nrows] = acc;
+    }
+    __syncthreads();
+    const unsigned int ncand = s_rowoff[nrows];
+    for (unsigned int base = 0; base < ncand; base += kThreads) {   // block-uniform trip count
+        const unsigned int c = base + tid;
         bool visible = false;
-        if (t < rp.T) {
+        int t = 0;
+        if (c < ncand) {
+            int rr = 0;
+            while (rr + 1 < nrows && c >= s_rowoff[rr + 1]) ++rr;
+            const unsigned int packed = __ldg(rp.wg_cell_tris + s_rowbeg[rr] + (c - s_rowoff[rr]));
+            t = (int)(packed & 0x3fffffffu);
+            const int tag = (int)(packed >> 30);
             double v[3][3];
             load_vertices(rp.tri_planes, rp.T, t, px, py, pz, v);
-            double s0 = norm2_rn(v[0][0], v[0][1], v[0][2]);
-            double s1 = norm2_rn(v[1][0], v[1][1], v[1][2]);
-            double s2 = norm2_rn(v[2][0], v[2][1], v[2][2]);
-            bool nan_any = (s0 != s0) || (s1 != s1) || (s2 != s2);   // NaN vertex -> never visible (:98, :102)
-            double smin = fmin(s0, fmin(s1, s2));
-            if (!nan_any && smin <= h2_hi) visible = __dsqrt_rn(smin) <= h;
+            const double s0 = norm2_rn(v[0][0], v[0][1], v[0][2]);
+            const double s1 = norm2_rn(v[1][0], v[1][1], v[1][2]);
+            const double s2 = norm2_rn(v[2][0], v[2][1], v[2][2]);
+            const double smin = fmin(s0, fmin(s1, s2));
+            if (smin <= h2_hi && __dsqrt_rn(smin) <= h) {
+                const int kn = (s0 <= s1 && s0 <= s2) ? 0 : (s1 <= s2 ? 1 : 2);   // nearest vertex
+                // same float arithmetic as the host used to file the vertices into cells
+                const float* pl = rp.tri_planes;
+                const float xn = __ldg(pl + (size_t)(3 * kn) * rp.T + t), yn = __ldg(pl + (size_t)(3 * kn + 1) * rp.T + t);
+                const float xt = __ldg(pl + (size_t)(3 * tag) * rp.T + t), yt = __ldg(pl + (size_t)(3 * tag + 1) * rp.T + t);
+                const int cnx = world_cell(xn, gx0, ginv, nx), cny = world_cell(yn, gy0, ginv, ny);
+                const int ctx = world_cell(xt, gx0, ginv, nx), cty = world_cell(yt, gy0, ginv, ny);
+                visible = cnx == ctx && cny == cty;
+            }
         }
         unsigned m = __ballot_sync(0xffffffffu, visible);
         if (m) {
