@@ -1,0 +1,68 @@
+// Tunables and the shared-memory layout of the render kernel.
+#pragma once
+#include "isy_common.cuh"
+
+namespace isy {
+
+constexpr int kThreads = ISY_THREADS;  // CTA size, one persistent CTA per SM
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxE = 1152;           // projected copies resident in shared memory (54 KB)
+constexpr int kBinRows = 32;          // finest angular grid over the vegetation band
+constexpr int kBinCols = 128;         // ... and over azimuth [-pi, pi]
+constexpr int kBins = kBinRows * kBinCols;
+constexpr int kListCap = 24576;       // candidate list entries (u16, 48 KB)
+constexpr int kMaxH = 128;            // headings whose sin/cos are cached per position
+constexpr float kBinMargin = 1e-4f;   // rad; >> every fp32 rounding in the bin arithmetic
+constexpr float kBinReject = -1e-5f;  // a bin is dropped only if an edge function is below this on all of it
+
+constexpr int kBestCap = 36864;       // (heading, ray) slots of the rasteriser's winner buffer (u16 copy slots, 72 KB)
+constexpr int kGridRaysSmem = 1280;   // eyes up to this many rays keep their pitch-sorted ray table in shared memory
+constexpr int kPitchLut = 1024;       // slots of the pitch -> first sorted ray look-up table
+constexpr int kHeadLut = 1024;        // slots of the azimuth -> first sorted heading look-up table
+constexpr int kCellsSmem = 2048;      // cells of the eye's (pitch, yaw) ray grid kept in shared memory
+constexpr int kSmallH = 4;            // up to this many headings per group the rasteriser walks the ray grid
+
+struct SmemBins {
+    unsigned int bin_off[kBins + 4];  // exclusive offsets into list (counts during the count pass)
+    unsigned int bin_cur[kBins];      // fill cursors
+    unsigned short list[kListCap];
+};
+
+struct SmemRaster {
+    unsigned short best[kBestCap];    // nearest containing copy (slot in tile) per (sorted heading, sorted ray)
+    float2 sorted[kGridRaysSmem];     // the eye's rays in pitch order: (pitch, yaw) as floats (copied once per CTA)
+    unsigned int plut[kPitchLut + 4]; // first sorted ray at or above each pitch slot
+    float hsort[2 * kMaxH];           // wrapped headings of the group, ascending, then the same + 2 pi
+    float hvalf[2 * kMaxH];           // the wrapped heading itself (no + 2 pi) of each sorted slot
+    unsigned char hperm[2 * kMaxH];   // heading index of each sorted slot
+    unsigned char hinv[kMaxH];        // sorted slot of each heading
+    unsigned short hlut[kHeadLut];    // first sorted slot that can reach each azimuth slot
+    float uni[4];                     // {h0, delta, 1/delta, flag}: sorted headings are h0 + k*delta over the full circle
+    unsigned int cell_start[kCellsSmem + 4];      // the eye's static (pitch, yaw) ray grid: first list entry of each cell
+    unsigned short cell_list[kGridRaysSmem];      // ... and the pitch-sorted positions of the rays in each cell
+};
+
+struct SmemLayout {
+    Entry tile[kMaxE];
+    float4 bbox[kMaxE];               // (theta_lo, theta_hi, phi_lo, phi_hi) of each copy, margin included
+    double head_sin[kMaxH], head_cos[kMaxH], head_val[kMaxH];   // per heading of the current group
+    double2 gtab[2 * (kGTab + 1)];    // exp(D acos c) table of this call's sky (copied once per CTA)
+    SunConst sun0;                    // sun constants when all views share one sun (copied once per CTA)
+    union {
+        SmemBins bins;
+        SmemRaster ras;
+    };
+};
+static_assert(sizeof(SmemLayout) <= 192 * 1024, "leave some of the 228 KB for L1");
+
+struct RayOut {
+    double r, g, b;
+    double Y, P, A;
+};
+
+template <typename T>
+__device__ __forceinline__ void store_val(void* base, size_t idx, double v) {
+    reinterpret_cast<T*>(base)[idx] = (T)v;
+}
+
+}  // namespace isy

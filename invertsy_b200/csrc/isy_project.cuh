@@ -1,0 +1,183 @@
+// Phase A: cull (world cell grid) and angular projection of one position.
+#pragma once
+#include "isy_layout.cuh"
+
+namespace isy {
+
+// ------------------------------------------------------------------------------------------
+// phase A: cull + project one position. Entries go to the CTA's slab (always) and to the
+// shared-memory tile (first kMaxE). Returns the number of copies E.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_vertices(const float* __restrict__ planes, int T, int t, double px, double py,
+                                              double pz, double v[3][3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        v[k][0] = (double)__ldg(planes + (size_t)(3 * k + 0) * T + t) - px;   // world.py:94
+        v[k][1] = (double)__ldg(planes + (size_t)(3 * k + 1) * T + t) - py;
+        v[k][2] = (double)__ldg(planes + (size_t)(3 * k + 2) * T + t) - pz;
+    }
+}
+
+// cell index of a coordinate in the world's xy grid -- the host files vertices with the same float ops
+__host__ __device__ __forceinline__ int world_cell(float x, float x0, float inv_cell, int n) {
+    const float q = (x - x0) * inv_cell;
+    int c = (int)floorf(q);
+    return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+
+__device__ __forceinline__ int float_key(float f) {   // order-preserving int key for atomicMin/Max
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__device__ __forceinline__ void emit_copy(const double th[3], const double ph[3], double dist, int t, int slot,
+                                          Entry* entries, Exact* exacts, SmemLayout& sm, int* s_band) {
+    Entry e;
+    finish_copy(th, ph, dist, t, e, exacts[slot]);
+    entries[slot] = e;
+    if (slot < kMaxE) {
+        sm.tile[slot] = e;
+        float tlo = (float)fmin(th[0], fmin(th[1], th[2])) - kBinMargin;
+        float thi = (float)fmax(th[0], fmax(th[1], th[2])) + kBinMargin;
+        float plo = (float)fmin(ph[0], fmin(ph[1], ph[2])) - kBinMargin;
+        float phi = (float)fmax(ph[0], fmax(ph[1], ph[2])) + kBinMargin;
+        sm.bbox[slot] = make_float4(tlo, thi, plo, phi);
+        atomicMin(&s_band[0], float_key(tlo));
+        atomicMax(&s_band[1], float_key(thi));
+    }
+}
+
+__device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* entries, Exact* exacts,
+                                SmemLayout& sm, int* s_count, int* s_nent, int* s_band) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const double px = rp.pos[3 * p + 0], py = rp.pos[3 * p + 1], pz = rp.pos[3 * p + 2];
+    const double h = rp.horizon;
+    const double h2_hi = h * h * (1.0 + 1e-12);  // above this the rounded norm cannot be <= horizon
+
+    if (tid == 0) {
+        *s_count = 0;
+        *s_nent = 0;
+        s_band[0] = float_key(CUDART_INF_F);
+        s_band[1] = float_key(-CUDART_INF_F);
+    }
+    __syncthreads();
+
+    // ---- A1: cull (world.py:97-98) ----
+    // Candidates come from the world's xy cell grid (isy_world_create): a visible triangle has a vertex
+    // within the horizon, so it is listed in a cell that meets the disc around the eye.  A triangle is
+    // listed once per distinct vertex cell (tagged with that vertex); it is taken from the list entry
+    // whose cell holds its NEAREST vertex, i.e. exactly once.  The test itself is the reference's, fp64.
+    const float gx0 = rp.wg_x0, gy0 = rp.wg_y0, ginv = rp.wg_inv_cell;
+    const int nx = rp.wg_nx, ny = rp.wg_ny;
+    const double slack = 1e-2;   // cells; covers the float rounding of the vertex filing (< 1e-3 cells for 4096 cells a side)
+    const int cx0 = (int)fmax(fmin(floor((px - h - gx0) * ginv - slack), (double)(nx - 1)), 0.0);
+    const int cx1 = (int)fmax(fmin(floor((px + h - gx0) * ginv + slack), (double)(nx - 1)), 0.0);
+    const int cy0 = (int)fmax(fmin(floor((py - h - gy0) * ginv - slack), (double)(ny - 1)), 0.0);
+    const int cy1 = (int)fmax(fmin(floor((py + h - gy0) * ginv + slack), (double)(ny - 1)), 0.0);
+    // the candidate cells form one contiguous list range per grid row: flatten the (<= 16) rows
+    __shared__ unsigned int s_rowbeg[16], s_rowoff[17];
+    const int nrows = min(cy1 - cy0 + 1, 16);   // cell = horizon / 4 or larger: at most 10 rows
+    if (tid == 0) {
+        unsigned int acc = 0;
+        for (int rr = 0; rr < nrows; ++rr) {
+            const unsigned int beg = __ldg(rp.wg_cell_start + (size_t)(cy0 + rr) * nx + cx0);
+            const unsigned int end = __ldg(rp.wg_cell_start + (size_t)(cy0 + rr) * nx + cx1 + 1);
+            s_rowbeg[rr] = beg;
+            s_rowoff[rr] = acc;
+            acc += end - beg;
+        }
+        s_rowoff[nrows] = acc;
+    }
+    __syncthreads();
+    const unsigned int ncand = s_rowoff[nrows];
+    for (unsigned int base = 0; base < ncand; base += kThreads) {   // block-uniform trip count
+        const unsigned int c = base + tid;
+        bool visible = false;
+        int t = 0;
+        if (c < ncand) {
+            int rr = 0;
+            while (rr + 1 < nrows && c >= s_rowoff[rr + 1]) ++rr;
+            const unsigned int packed = __ldg(rp.wg_cell_tris + s_rowbeg[rr] + (c - s_rowoff[rr]));
+            t = (int)(packed & 0x3fffffffu);
+            const int tag = (int)(packed >> 30);
+            double v[3][3];
+            load_vertices(rp.tri_planes, rp.T, t, px, py, pz, v);
+            const double s0 = norm2_rn(v[0][0], v[0][1], v[0][2]);
+            const double s1 = norm2_rn(v[1][0], v[1][1], v[1][2]);
+            const double s2 = norm2_rn(v[2][0], v[2][1], v[2][2]);
+            const double smin = fmin(s0, fmin(s1, s2));
+            if (smin <= h2_hi && __dsqrt_rn(smin) <= h) {
+                const int kn = (s0 <= s1 && s0 <= s2) ? 0 : (s1 <= s2 ? 1 : 2);   // nearest vertex
+                // same float arithmetic as the host used to file the vertices into cells
+                const float* pl = rp.tri_planes;
+                const float xn = __ldg(pl + (size_t)(3 * kn) * rp.T + t), yn = __ldg(pl + (size_t)(3 * kn + 1) * rp.T + t);
+                const float xt = __ldg(pl + (size_t)(3 * tag) * rp.T + t), yt = __ldg(pl + (size_t)(3 * tag + 1) * rp.T + t);
+                const int cnx = world_cell(xn, gx0, ginv, nx), cny = world_cell(yn, gy0, ginv, ny);
+                const int ctx = world_cell(xt, gx0, ginv, nx), cty = world_cell(yt, gy0, ginv, ny);
+                visible = cnx == ctx && cny == cty;
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, visible);
+        if (m) {
+            int basei = 0;
+            if (lane == 0) basei = atomicAdd(s_count, __popc(m));
+            basei = __shfl_sync(0xffffffffu, basei, 0);
+            if (visible) {
+                int slot = basei + __popc(m & ((1u << lane) - 1));
+                if (slot < rp.slab_cap) vis[slot] = t;
+            }
+        }
+    }
+    __syncthreads();
+    int V = *s_count;
+    if (V > rp.slab_cap) {
+        if (tid == 0) atomicExch(rp.status, (int)ISY_ERR_OVERFLOW);
+        V = rp.slab_cap;
+    }
+
+    // ---- A2: angular projection of the visible triangles (world.py:109-120) ----
+    for (int j = tid; j < V; j += kThreads) {
+        int t = vis[j];
+        double v[3][3];
+        load_vertices(rp.tri_planes, rp.T, t, px, py, pz, v);
+        double smin = fmin(norm2_rn(v[0][0], v[0][1], v[0][2]),
+                           fmin(norm2_rn(v[1][0], v[1][1], v[1][2]), norm2_rn(v[2][0], v[2][1], v[2][2])));
+        double dist = __dsqrt_rn(smin);
+        double th[3], ph[3];
+        double phmax = -CUDART_INF, phmin = CUDART_INF;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            ph[k] = atan2(v[k][1], v[k][0]);                                              // :109
+            double rxy = __dsqrt_rn(__dadd_rn(__dmul_rn(v[k][0], v[k][0]), __dmul_rn(v[k][1], v[k][1])));
+            th[k] = atan2(rxy, v[k][2]) - kHalfPi;                                        // :110
+            phmax = fmax(phmax, ph[k]);
+            phmin = fmin(phmin, ph[k]);
+        }
+        bool seam = (phmax - phmin) >= kPi;                                               // :116
+        int slot = atomicAdd(s_nent, seam ? 2 : 1);
+        if (slot + (seam ? 2 : 1) <= rp.slab_cap) {
+            if (seam) {
+                double p1[3], p2[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    p1[k] = ph[k] < 0 ? ph[k] + kTwoPi : ph[k];                           // :118
+                    p2[k] = ph[k] > 0 ? ph[k] - kTwoPi : ph[k];                           // :119
+                }
+                emit_copy(th, p1, dist, t, slot, entries, exacts, sm, s_band);
+                emit_copy(th, p2, dist, t, slot + 1, entries, exacts, sm, s_band);
+            } else {
+                emit_copy(th, ph, dist, t, slot, entries, exacts, sm, s_band);
+            }
+        }
+    }
+    __syncthreads();
+    int E = *s_nent;
+    if (E > rp.slab_cap) {
+        if (tid == 0) atomicExch(rp.status, (int)ISY_ERR_OVERFLOW);
+        E = rp.slab_cap;
+    }
+    return E;
+}
+
+}  // namespace isy

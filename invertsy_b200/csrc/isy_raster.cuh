@@ -1,0 +1,349 @@
+// Triangle-centric rasterisers for yaw-only views: pitch-run walk and ray-grid walk.
+#pragma once
+#include "isy_bins.cuh"
+
+namespace isy {
+
+// ------------------------------------------------------------------------------------------
+// phase A3' + B' (yaw-only views): triangle-centric rasterisation over the eye's pitch-sorted rays.
+//
+// For a yaw-only view the query of ray r is (pitch_r, yaw_r + heading).  A projected copy with
+// bounding box [t0,t1] x [p0,p1] can only contain rays whose pitch lies in [t0,t1] -- a contiguous
+// run of the eye's rays sorted by pitch (static per eye, isy_eye_create) -- and, for such a ray,
+// only the headings h with yaw_r + h in [p0,p1]: a window of the group's sorted headings found
+// through a small look-up table.  One warp takes a copy, its lanes the rays of the pitch run;
+// each (ray, heading) that survives gets the fp32 edge test (+ exact re-check) and posts the
+// copy's distance rank with an atomic min into best[heading][sorted ray].
+// The work is proportional to (copies x rays in their pitch band) + (true candidate pairs) for
+// ALL headings of the position at once; nothing is built per position beyond the ranks.
+// ------------------------------------------------------------------------------------------
+constexpr unsigned int kNoCopy = 0xffffu;
+
+// atomicAdd on a __shared__ int through an explicit shared-space instruction (a generic-address
+// atomic on shared memory is much slower)
+__device__ __forceinline__ int smem_atomic_add(int* p, int v) {
+    int old;
+    const unsigned int a = (unsigned int)__cvta_generic_to_shared(p);
+    asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+    return old;
+}
+constexpr int kRU = 4;                // rays per lane and iteration in the rasteriser
+
+// is copy e (distance d, triangle tri) nearer than copy c? (ties: lower triangle index, then lower slot)
+__device__ __forceinline__ bool nearer(const Entry* tile, double d, int tri, unsigned int e, unsigned int c) {
+    const Entry& o = tile[c];
+    const double dc = __hiloint2double(o.dist_hi, o.dist_lo);
+    return d < dc || (d == dc && (tri < o.tri || (tri == o.tri && e < c)));
+}
+
+// best[idx] = nearer(e, best[idx]) ? e : best[idx], atomically (CAS on the 32-bit word holding the u16)
+__device__ __forceinline__ void post_copy_u16(unsigned short* best, unsigned int idx, const Entry* tile, double d, int tri,
+                                              unsigned int e) {
+    unsigned int* word = reinterpret_cast<unsigned int*>(best) + (idx >> 1);
+    const bool hi = idx & 1u;
+    unsigned int old = *reinterpret_cast<volatile unsigned int*>(word);
+    for (;;) {
+        const unsigned int cur = hi ? (old >> 16) : (old & 0xffffu);
+        if (cur != kNoCopy && !nearer(tile, d, tri, e, cur)) return;
+        const unsigned int nw = hi ? ((old & 0xffffu) | (e << 16)) : ((old & 0xffff0000u) | e);
+        const unsigned int prev = atomicCAS(word, old, nw);
+        if (prev == old) return;
+        old = prev;
+    }
+}
+
+__device__ __forceinline__ void post_copy_u32(unsigned int* slot, const Entry* tile, double d, int tri, unsigned int e) {
+    unsigned int old = *reinterpret_cast<volatile unsigned int*>(slot);
+    for (;;) {
+        if (old != kNoCopy && !nearer(tile, d, tri, e, old)) return;
+        const unsigned int prev = atomicCAS(slot, old, e);
+        if (prev == old) return;
+        old = prev;
+    }
+}
+
+// sorts the group's wrapped headings (head_val[0..Hcur)) and builds the azimuth look-up table
+__device__ void sort_headings(SmemLayout& sm, int Hcur) {
+    const int tid = threadIdx.x;
+    if (tid < Hcur) {
+        const float h = (float)sm.head_val[tid];
+        int pos = 0;
+        for (int k = 0; k < Hcur; ++k) {
+            const float hk = (float)sm.head_val[k];
+            pos += (hk < h) || (hk == h && k < tid);
+        }
+        sm.ras.hsort[pos] = h;
+        sm.ras.hsort[pos + Hcur] = h + (float)kTwoPi;
+        sm.ras.hvalf[pos] = h;
+        sm.ras.hvalf[pos + Hcur] = h;
+        sm.ras.hperm[pos] = (unsigned char)tid;
+        sm.ras.hperm[pos + Hcur] = (unsigned char)tid;
+        sm.ras.hinv[tid] = (unsigned char)pos;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // evenly spaced headings over the full circle (every scan of the reference's simulations, and a
+        // single heading) let the window walk use arithmetic instead of the look-up table
+        const float h0 = sm.ras.hsort[0];
+        const float delta = (float)kTwoPi / (float)Hcur;
+        bool ok = true;
+        for (int k = 1; k < Hcur; ++k) ok = ok && fabsf(sm.ras.hsort[k] - (h0 + k * delta)) < 5e-7f;
+        sm.ras.uni[0] = h0, sm.ras.uni[1] = delta, sm.ras.uni[2] = 1.0f / delta, sm.ras.uni[3] = ok ? 1.f : 0.f;
+    }
+    for (int s = tid; s < kHeadLut; s += kThreads) {
+        // first sorted slot whose heading is not below this azimuth slot (minus a guard band):
+        // windows start their walk here; whatever they pick up below `lower` just fails the edge test
+        const float start = -(float)kPi + s * ((float)kTwoPi / kHeadLut) - 1e-4f;
+        int k = 0;
+        while (k < 2 * Hcur && sm.ras.hsort[k] < start) ++k;
+        sm.ras.hlut[s] = (unsigned short)k;
+    }
+}
+
+// kSmem: the eye's sorted ray table and the winner buffer live in shared memory (u16 slots);
+// otherwise both are in global memory (u32 slots), for eyes too large for that.
+// The hot path is fp32: query azimuth = fl(yaw_f + heading_f) wrapped in fp32; kEdgeEps covers that
+// rounding.  Rays that land within 3e-6 rad of the +-pi seam, and rays inside the rounding band of
+// an edge, redo the query in fp64 exactly as the reference composes it.
+template <bool kSmem, bool kUniform>
+__device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest, const Exact* exacts, int E,
+                              int Hcur, int* s_next) {
+    const int R = rp.R, lane = threadIdx.x & 31;
+    const float2* gsorted = reinterpret_cast<const float2*>(rp.grid_sorted);
+    const int H2 = 2 * Hcur;
+    const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
+    const float uh0 = sm.ras.uni[0], udelta = sm.ras.uni[1], uinv = sm.ras.uni[2];
+    for (;;) {
+        // copies differ a lot in size (a near blade spans hundreds of rays): warps pull them from a counter
+        int e = 0;
+        if (lane == 0) e = smem_atomic_add(s_next, 1);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= E) break;
+        const float4 bb = sm.bbox[e];
+        // azimuth window of the copy clipped to the query domain (-pi, pi]
+        const float glo = fmaxf(bb.z, -pi_f - kBinMargin) - kBinMargin, ghi = fminf(bb.w, pi_f + kBinMargin) + kBinMargin;
+        if (glo > ghi) continue;
+        const float width = ghi - glo;
+        const Entry ent = sm.tile[e];
+        const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
+        // run of pitch-sorted rays that covers [bb.x, bb.y] (a few extra rays at both ends)
+        const int s0 = min(max((int)floorf((bb.x + (float)kHalfPi) * (kPitchLut / (float)kPi)), 0), kPitchLut - 1);
+        const int s1 = min(max((int)floorf((bb.y + (float)kHalfPi) * (kPitchLut / (float)kPi)) + 2, 0), kPitchLut);
+        const unsigned jbeg = kSmem ? sm.ras.plut[s0] : __ldg(rp.grid_plut + s0);
+        const unsigned jend = kSmem ? sm.ras.plut[s1] : __ldg(rp.grid_plut + s1);
+        // kRU rays per lane and iteration: their window walks and edge tests are independent
+        // instruction streams, which is what hides the shared-memory and branch latencies here
+        for (unsigned jb = jbeg; jb < jend; jb += 32 * kRU) {   // warp-uniform trip count
+            __syncwarp();                                       // keep the lanes converged across iterations
+            float2 py[kRU];
+            int k[kRU], ks[kRU];    // window cursor; sorted slot of the heading under the cursor
+            float upper[kRU];
+#pragma unroll
+            for (int u = 0; u < kRU; ++u) {
+                const unsigned j = jb + u * 32 + lane;
+                py[u] = make_float2(4.f, 0.f);                  // pitch 4 rad: outside every band
+                if (j < jend) py[u] = kSmem ? sm.ras.sorted[j] : __ldg(gsorted + j);
+            }
+#pragma unroll
+            for (int u = 0; u < kRU; ++u) {
+                // headings h with yaw + h in [glo, ghi]  <=>  h in [lower, lower + width] on the circle
+                float lower = glo - py[u].y;
+                if (lower < -pi_f) lower += twopi_f;
+                else if (lower >= pi_f) lower -= twopi_f;
+                const bool band = py[u].x >= bb.x && py[u].x <= bb.y;
+                if (kUniform) {
+                    // headings are h0 + k*delta (k mod H): the window is the index range [k0, k1];
+                    // k[] counts the headings left in the window, ks[] is the sorted slot of the next one
+                    const float a = (lower - uh0) * uinv;
+                    const int k0 = (int)ceilf(a - 2e-4f), k1 = (int)floorf(fmaf(width, uinv, a) + 2e-4f);
+                    k[u] = band ? min(k1 - k0 + 1, Hcur) : 0;            // lower in [-pi, pi): k0 in [-H, H]
+                    ks[u] = k0 < 0 ? k0 + Hcur : (k0 >= Hcur ? k0 - Hcur : k0);
+                    upper[u] = 0.f;
+                } else {
+                    const int ls = min(max((int)((lower + pi_f) * (kHeadLut / twopi_f)), 0), kHeadLut - 1);
+                    k[u] = band ? (int)sm.ras.hlut[ls] : H2;
+                    upper[u] = lower + width;
+                }
+            }
+            // lanes walk their heading windows in lock step (most windows hold 0 or 1 heading)
+            for (;;) {
+                bool act[kRU], any = false;
+                float hv[kRU];
+#pragma unroll
+                for (int u = 0; u < kRU; ++u) {
+                    if (kUniform) {
+                        act[u] = k[u] > 0;
+                        hv[u] = fmaf((float)ks[u], udelta, uh0);
+                    } else {
+                        const int kk = min(k[u], H2 - 1);
+                        act[u] = k[u] < H2 && sm.ras.hsort[kk] <= upper[u];
+                        hv[u] = sm.ras.hvalf[kk];
+                        ks[u] = kk >= Hcur ? kk - Hcur : kk;       // the + 2 pi copy is the same heading
+                    }
+                    any |= act[u];
+                }
+                if (!__any_sync(0xffffffffu, any)) break;
+                float fy[kRU], m[kRU];
+#pragma unroll
+                for (int u = 0; u < kRU; ++u) {                 // branch-free: the common case of every slot
+                    float f = py[u].y + hv[u];                  // both in (-pi, pi]: one shift wraps
+                    f = f > pi_f ? f - twopi_f : (f <= -pi_f ? f + twopi_f : f);
+                    fy[u] = f;
+                    const float e0 = fmaf(ent.A0, py[u].x, fmaf(ent.B0, f, ent.C0));
+                    const float e1 = fmaf(ent.A1, py[u].x, fmaf(ent.B1, f, ent.C1));
+                    const float e2 = fmaf(ent.A2, py[u].x, fmaf(ent.B2, f, ent.C2));
+                    m[u] = fminf(e0, fminf(e1, e2));
+                }
+#pragma unroll
+                for (int u = 0; u < kRU; ++u) {
+                    const unsigned j = jb + u * 32 + lane;
+                    const bool seam = fabsf(fy[u]) > 3.14159f;
+                    bool in = act[u] && m[u] > kEdgeEps && !seam;
+                    // rare: the rounding band of an edge, or a query within 3e-6 rad of the seam ->
+                    // redo the query in fp64 exactly as the reference composes it
+                    if (act[u] && (seam || (m[u] >= -kEdgeEps && m[u] <= kEdgeEps))) {
+                        const int hh = sm.ras.hperm[ks[u]];
+                        const int ray = __ldg(rp.grid_sorted_ray + j);
+                        double yg = rp.eye_py[2 * (size_t)ray + 1] + sm.head_val[hh];
+                        if (yg > kPi) yg -= kTwoPi;
+                        else if (yg <= -kPi) yg += kTwoPi;
+                        const float f = (float)yg;
+                        const float e0 = fmaf(ent.A0, py[u].x, fmaf(ent.B0, f, ent.C0));
+                        const float e1 = fmaf(ent.A1, py[u].x, fmaf(ent.B1, f, ent.C1));
+                        const float e2 = fmaf(ent.A2, py[u].x, fmaf(ent.B2, f, ent.C2));
+                        const float mm = fminf(e0, fminf(e1, e2));
+                        in = mm > kEdgeEps;
+                        if (!in && mm >= -kEdgeEps) in = inside_exact(exacts[e], rp.eye_py[2 * (size_t)ray], yg);
+                    }
+                    // rows of best[] are SORTED heading slots
+                    if (in) {
+                        if (kSmem) post_copy_u16(sm.ras.best, (unsigned)ks[u] * R + j, sm.tile, dist, ent.tri, e);
+                        else post_copy_u32(&gbest[(size_t)ks[u] * R + j], sm.tile, dist, ent.tri, e);
+                    }
+                    if (kUniform) {
+                        if (act[u]) {
+                            --k[u];
+                            ks[u] = ks[u] + 1 == Hcur ? 0 : ks[u] + 1;
+                        }
+                    } else if (act[u]) {
+                        ++k[u];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Few headings per position (single views, route batches): walking every ray of a copy's pitch band
+// would test ~98 % of the pairs for nothing, so each (copy, heading) pair instead visits the few
+// cells of the eye's static (pitch, yaw) ray grid under the copy's bounding box, shifted by the
+// heading.  Lanes hold different pairs; the work per position is a few thousand warp instructions.
+// ------------------------------------------------------------------------------------------
+// tests the rays stored in one cell of the eye's ray grid against one projected copy at one heading
+template <bool kSmem>
+__device__ __forceinline__ void raster_cell(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest,
+                                            const Exact* exacts, int cell, const Entry& ent, double dist, int e, int hh,
+                                            int hs, float hf) {
+    const int R = rp.R;
+    const float2* gsorted = reinterpret_cast<const float2*>(rp.grid_sorted);
+    const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
+    const unsigned i0 = kSmem ? sm.ras.cell_start[cell] : __ldg(rp.cells_start + cell);
+    const unsigned i1 = kSmem ? sm.ras.cell_start[cell + 1] : __ldg(rp.cells_start + cell + 1);
+    for (unsigned i = i0; i < i1; ++i) {
+        const unsigned j = kSmem ? (unsigned)sm.ras.cell_list[i] : __ldg(rp.cells_list + i);
+        const float2 py = kSmem ? sm.ras.sorted[j] : __ldg(gsorted + j);
+        float fy = py.y + hf;                                  // both in (-pi, pi]: one shift wraps
+        fy = fy > pi_f ? fy - twopi_f : (fy <= -pi_f ? fy + twopi_f : fy);
+        const bool seam = fabsf(fy) > 3.14159f;
+        float m = fminf(fmaf(ent.A0, py.x, fmaf(ent.B0, fy, ent.C0)),
+                        fminf(fmaf(ent.A1, py.x, fmaf(ent.B1, fy, ent.C1)), fmaf(ent.A2, py.x, fmaf(ent.B2, fy, ent.C2))));
+        if (!seam && m < -kEdgeEps) continue;
+        bool in = m > kEdgeEps && !seam;
+        if (!in) {   // redo the query in fp64 exactly as the reference composes it
+            const int ray = __ldg(rp.grid_sorted_ray + j);
+            double yg = rp.eye_py[2 * (size_t)ray + 1] + sm.head_val[hh];
+            if (yg > kPi) yg -= kTwoPi;
+            else if (yg <= -kPi) yg += kTwoPi;
+            const float f = (float)yg;
+            m = fminf(fmaf(ent.A0, py.x, fmaf(ent.B0, f, ent.C0)),
+                      fminf(fmaf(ent.A1, py.x, fmaf(ent.B1, f, ent.C1)), fmaf(ent.A2, py.x, fmaf(ent.B2, f, ent.C2))));
+            in = m > kEdgeEps;
+            if (!in && m >= -kEdgeEps) in = inside_exact(exacts[e], rp.eye_py[2 * (size_t)ray], yg);
+        }
+        if (in) {
+            if (kSmem) post_copy_u16(sm.ras.best, (unsigned)hs * R + j, sm.tile, dist, ent.tri, e);
+            else post_copy_u32(&gbest[(size_t)hs * R + j], sm.tile, dist, ent.tri, e);
+        }
+    }
+}
+
+template <bool kSmem>
+__device__ void raster_cells(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest, const Exact* exacts, int E,
+                             int Hcur, int* s_next) {
+    const int lane = threadIdx.x & 31, Gp = rp.cells_rows, Gy = rp.cells_cols;
+    const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
+    const float inv_dp = (float)Gp / pi_f, inv_dy = (float)Gy / twopi_f;
+    const int items = E * Hcur;
+    constexpr int kBigItem = 12;    // pairs that cover more cells than this are walked by the whole warp
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = smem_atomic_add(s_next, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= items) break;
+        const int item = base + lane;
+        int e = 0, hh = 0, r0 = 0, nrows = 0, c0 = 0, ncols = 0;
+        if (item < items) {
+            e = item / Hcur, hh = item - e * Hcur;
+            const float4 bb = sm.bbox[e];
+            const float glo = fmaxf(bb.z, -pi_f - kBinMargin) - kBinMargin, ghi = fminf(bb.w, pi_f + kBinMargin) + kBinMargin;
+            if (glo <= ghi) {
+                const float hf = (float)sm.head_val[hh];
+                // eye-frame azimuth window [glo - h, ghi - h], as a run of grid columns modulo the circle
+                const int c_first = (int)floorf((glo - hf + pi_f) * inv_dy);
+                ncols = min((int)floorf((ghi - hf + pi_f) * inv_dy) - c_first + 1, Gy);
+                c0 = c_first % Gy;
+                if (c0 < 0) c0 += Gy;
+                r0 = max((int)floorf((bb.x + (float)kHalfPi) * inv_dp), 0);
+                nrows = max(min((int)floorf((bb.y + (float)kHalfPi) * inv_dp), Gp - 1) - r0 + 1, 0);
+            }
+        }
+        const int ncell = nrows * ncols;
+        // small pairs: one lane each
+        if (ncell > 0 && ncell <= kBigItem) {
+            const Entry ent = sm.tile[e];
+            const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
+            const float hf = (float)sm.head_val[hh];
+            const int hs = sm.ras.hinv[hh];
+            for (int q = 0; q < ncell; ++q) {
+                const int row = r0 + q / ncols;
+                int c = c0 + q % ncols;
+                if (c >= Gy) c -= Gy;
+                raster_cell<kSmem>(rp, sm, gbest, exacts, row * Gy + c, ent, dist, e, hh, hs, hf);
+            }
+        }
+        // large pairs (a blade right in front of the eye): the warp shares their cells
+        unsigned int big = __ballot_sync(0xffffffffu, ncell > kBigItem);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const int be = __shfl_sync(0xffffffffu, e, src), bh = __shfl_sync(0xffffffffu, hh, src);
+            const int br0 = __shfl_sync(0xffffffffu, r0, src), bc0 = __shfl_sync(0xffffffffu, c0, src);
+            const int bnc = __shfl_sync(0xffffffffu, ncols, src), bn = __shfl_sync(0xffffffffu, ncell, src);
+            const Entry ent = sm.tile[be];
+            const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
+            const float hf = (float)sm.head_val[bh];
+            const int hs = sm.ras.hinv[bh];
+            for (int q = lane; q < bn; q += 32) {
+                const int row = br0 + q / bnc;
+                int c = bc0 + q % bnc;
+                if (c >= Gy) c -= Gy;
+                raster_cell<kSmem>(rp, sm, gbest, exacts, row * Gy + c, ent, dist, be, bh, hs, hf);
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace isy

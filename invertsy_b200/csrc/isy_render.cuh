@@ -1,0 +1,227 @@
+// The persistent render kernel.
+#pragma once
+#include "isy_shade.cuh"
+
+namespace isy {
+
+enum { kModeBrute = 0, kModeBins = 1, kModeRaster = 2 };
+
+template <bool kF64>
+__global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams rp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
+    __shared__ int s_count, s_nent, s_band[2];
+    __shared__ unsigned int s_item, s_warp[kWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int* vis = rp.slab_vis + (size_t)blockIdx.x * rp.slab_cap;
+    Entry* entries = rp.slab_entry + (size_t)blockIdx.x * rp.slab_cap;
+    Exact* exacts = rp.slab_exact + (size_t)blockIdx.x * rp.slab_cap;
+    unsigned int* gbest = rp.slab_best ? rp.slab_best + (size_t)blockIdx.x * rp.R : nullptr;
+    const bool want_sky = rp.sky.kind != ISY_SKY_NONE;
+    const bool perez = rp.sky.kind == ISY_SKY_PEREZ;
+    const bool yaw_only = !rp.vquat;
+    const bool raster_ok = yaw_only && rp.grid_sorted && !(rp.flags & ISY_FLAG_BRUTE_FORCE);
+    const bool smem_grid = raster_ok && !gbest;
+    bool grid_loaded = false;
+
+    if (perez) {
+        for (int i = tid; i < 2 * (kGTab + 1); i += kThreads) sm.gtab[i] = rp.sky_gtab[i];
+        if (tid == 0) sm.sun0 = rp.sun[0];
+    }
+    long long t_phase[4] = {0, 0, 0, 0};   // project, accel (bins / raster), final ray pass, positions
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(rp.queue, 1u);
+        __syncthreads();
+        const unsigned item = s_item;
+        if (item >= (unsigned)rp.items) break;
+        const int p = item / rp.splits, split = item % rp.splits;
+        long long t0 = clock64();
+
+        const int E = cull_and_project(rp, p, vis, entries, exacts, sm, &s_count, &s_nent, s_band);
+        long long t1 = clock64();
+        int mode = kModeBrute;
+        BinGrid grid;
+        if (!(rp.flags & ISY_FLAG_BRUTE_FORCE) && E <= kMaxE) {
+            if (raster_ok) {
+                mode = kModeRaster;
+                if (smem_grid && !grid_loaded) {   // the bins path shares this memory: (re)load when needed
+                    for (int i = tid; i <= kPitchLut; i += kThreads) sm.ras.plut[i] = rp.grid_plut[i];
+                    for (int i = tid; i < rp.R; i += kThreads) {
+                        sm.ras.sorted[i] = reinterpret_cast<const float2*>(rp.grid_sorted)[i];
+                        sm.ras.cell_list[i] = (unsigned short)rp.cells_list[i];
+                    }
+                    for (int i = tid; i <= rp.cells_rows * rp.cells_cols; i += kThreads) sm.ras.cell_start[i] = rp.cells_start[i];
+                    grid_loaded = true;
+                }
+            } else if (build_bins(sm, grid, E, s_band, s_warp)) {
+                mode = kModeBins;
+                grid_loaded = false;
+            }
+        }
+        long long t2 = clock64();
+
+        // headings are handled in groups of rp.Hg (the rasteriser's winner buffer holds one group)
+        for (int grp = split; grp < rp.ngroups; grp += rp.splits) {
+            // group grp = headings grp, grp + ngroups, ...: an evenly spaced scan stays evenly spaced
+            const int Hcur = (rp.H - grp + rp.ngroups - 1) / rp.ngroups;
+            long long t3 = clock64();
+            __syncthreads();
+            if (yaw_only && tid < Hcur) {
+                const double hw = wrap_yaw(rp.yaw ? rp.yaw[(size_t)p * rp.H + grp + (size_t)tid * rp.ngroups] : 0.0);
+                sm.head_val[tid] = hw;
+                sincos(hw, &sm.head_sin[tid], &sm.head_cos[tid]);
+            }
+            if (mode == kModeRaster) {
+                if (smem_grid) {
+                    unsigned int* b32 = reinterpret_cast<unsigned int*>(sm.ras.best);
+                    for (int i = tid; i < (Hcur * rp.R + 1) / 2; i += kThreads) b32[i] = 0xffffffffu;
+                } else {
+                    for (int i = tid; i < Hcur * rp.R; i += kThreads) gbest[i] = kNoCopy;
+                }
+                __syncthreads();
+                if (tid == 0) s_count = 0;     // (the cull's counter is free again: next copy to rasterise)
+                sort_headings(sm, Hcur);
+                __syncthreads();
+                const bool uniform = sm.ras.uni[3] != 0.f;
+                if (Hcur <= kSmallH && smem_grid) {
+                    // (large eyes keep the pitch-run walk: their cells hold many rays and the lanes of a run stay full)
+                    raster_cells<true>(rp, sm, gbest, exacts, E, Hcur, &s_count);
+                } else if (smem_grid) {
+                    if (uniform) raster_copies<true, true>(rp, sm, gbest, exacts, E, Hcur, &s_count);
+                    else raster_copies<true, false>(rp, sm, gbest, exacts, E, Hcur, &s_count);
+                } else {
+                    if (uniform) raster_copies<false, true>(rp, sm, gbest, exacts, E, Hcur, &s_count);
+                    else raster_copies<false, false>(rp, sm, gbest, exacts, E, Hcur, &s_count);
+                }
+            }
+            __syncthreads();
+            long long t4 = clock64();
+            t_phase[1] += t4 - t3;
+
+            if (mode == kModeRaster && !kF64 && rp.S == 1 && !rp.init_c) {
+                if (smem_grid) final_pass_fast<true>(rp, sm, gbest, p, grp, Hcur);
+                else final_pass_fast<false>(rp, sm, gbest, p, grp, Hcur);
+                t_phase[2] += clock64() - t4;
+                continue;
+            }
+            // ---- generic final pass: warp units = (block of 32 consecutive rays) x (chunk of headings);
+            //      the eye data of a ray are loaded once per unit and reused for its headings
+            const int nb = (rp.R + 31) >> 5;
+            int nch = min(Hcur, max(1, (2 * kWarps + nb - 1) / nb));
+            const int hper = (Hcur + nch - 1) / nch;
+            nch = (Hcur + hper - 1) / hper;
+            for (int u = warp; u < nb * nch; u += kWarps) {
+                const int rb = u / nch, hc = u - rb * nch;
+                const int r = rb * 32 + lane;
+                const bool valid = r < rp.R;
+                const int rr = valid ? r : rp.R - 1;
+                double e_pitch = 0, e_yaw = 0, f_theta = 0;
+                double4 t4v = make_double4(0, 1, 0, 1);
+                int pos = 0;
+                if (yaw_only) {
+                    e_pitch = rp.eye_py[2 * (size_t)rr + 0];
+                    e_yaw = rp.eye_py[2 * (size_t)rr + 1];
+                    if (perez) {
+                        t4v = *reinterpret_cast<const double4*>(rp.eye_trig + 4 * (size_t)rr);
+                        f_theta = rp.eye_ftheta[rr];
+                    }
+                    if (mode == kModeRaster) pos = __ldg(rp.grid_pos_of + rr);
+                }
+                const int hend = min(Hcur, (hc + 1) * hper);
+                for (int hh = hc * hper; hh < hend; ++hh) {
+                    const size_t b = (size_t)p * rp.H + grp + (size_t)hh * rp.ngroups;
+                    Ray ray;
+                    double dx = 0, dy = 0, dz = 0;
+                    if (!yaw_only) {
+                        const double* qv = rp.vquat + 4 * b;
+                        const double* qo = rp.eye_quat + 4 * (size_t)rr;
+                        double x1 = qv[0], y1 = qv[1], z1 = qv[2], w1 = qv[3];
+                        double x2 = qo[0], y2 = qo[1], z2 = qo[2], w2 = qo[3];
+                        double w = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2;
+                        double x = w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2;
+                        double y = w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2;
+                        double z = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2;
+                        quat_dir(x, y, z, w, dx, dy, dz);
+                        dir_pitch_yaw(dx, dy, dz, ray.pitch, ray.yaw);
+                        if (perez) f_theta = perez_f(dz, ray.pitch + kHalfPi < kHalfPi, rp.sky.A, rp.sky.B);
+                    } else {
+                        ray.pitch = e_pitch;
+                        double yg = e_yaw + sm.head_val[hh];   // both in (-pi, pi]: one shift wraps
+                        if (yg > kPi) yg -= kTwoPi;
+                        else if (yg <= -kPi) yg += kTwoPi;
+                        ray.yaw = yg;
+                        if (perez) {
+                            const double hs = sm.head_sin[hh], hcs = sm.head_cos[hh];
+                            // sin/cos(yaw_e + heading) by the addition formulas
+                            double sy = t4v.z * hcs + t4v.w * hs, cy = t4v.w * hcs - t4v.z * hs;
+                            dx = t4v.y * cy, dy = t4v.y * sy, dz = -t4v.x;
+                        }
+                    }
+                    ray.fp = (float)ray.pitch;
+                    ray.fy = (float)ray.yaw;
+                    ray.best = CUDART_INF;
+                    ray.hit = -1;
+
+                    if (mode == kModeRaster) {
+                        const int hs = sm.ras.hinv[hh];
+                        const unsigned int rk = smem_grid ? (unsigned)sm.ras.best[hs * rp.R + pos]
+                                                          : gbest[(size_t)hs * rp.R + pos];
+                        if (rk != kNoCopy) {
+                            const Entry& w = sm.tile[rk];
+                            ray.hit = w.tri;
+                            ray.best = __hiloint2double(w.dist_hi, w.dist_lo);
+                        }
+                    } else if (mode == kModeBins) {
+                        if (ray.fp >= grid.th_lo && ray.fp <= grid.th_hi) {
+                            int row = min((int)((ray.fp - grid.th_lo) * grid.inv_dth), grid.rows - 1);
+                            int col = min(max((int)((ray.fy + (float)kPi) * grid.inv_dph), 0), grid.cols - 1);
+                            int bin = row * grid.cols + col;
+                            unsigned i0 = sm.bins.bin_off[bin], i1 = sm.bins.bin_off[bin + 1];
+                            for (unsigned i = i0; i < i1; ++i) {
+                                int e = sm.bins.list[i];
+                                test_entry(ray, &sm.tile[e], &exacts[e]);
+                            }
+                        }
+                    } else if (E <= kMaxE) {
+                        for (int j = 0; j < E; ++j) test_entry(ray, &sm.tile[j], &exacts[j]);
+                    } else {   // more copies than the tile holds: stream them from the slab
+                        for (int j = 0; j < E; ++j) test_entry(ray, &entries[j], &exacts[j]);
+                    }
+
+                    RayOut o;
+                    o.Y = 0, o.P = 0, o.A = CUDART_NAN;
+                    if (perez) {
+                        const SunConst sc = rp.sun[rp.sun_per_view ? b : 0];
+                        sky_eval<kF64>(rp.sky, sc, dx, dy, dz, ray.pitch + kHalfPi, f_theta, o.Y, o.P, o.A, false, sm.gtab);
+                    } else if (want_sky) {
+                        o.Y = rp.sky.luminance;   // UniformSky: y = luminance, p = 0, a = nan (sky.py:77-79)
+                    }
+                    // world colour (world.py:79-90, :123)
+                    o.r = CUDART_NAN, o.g = CUDART_NAN, o.b = CUDART_NAN;
+                    const bool from_sky = (rp.flags & ISY_FLAG_INIT_FROM_SKY) && want_sky;
+                    if (rp.init_c || from_sky) {
+                        double lum = rp.init_c ? rp.init_c[b * (size_t)rp.R + rr] : o.Y;
+                        o.r = fmin(fmax(19.0 * lum + 13.0, 0.0), 255.0);      // luminance2skycolour, world.py:479
+                        o.g = fmin(fmax(19.0 * lum + 135.0, 0.0), 255.0);
+                        o.b = fmin(fmax(19.0 * lum + 201.0, 0.0), 255.0);
+                    }
+                    if (ray.pitch >= 0) o.r = 229.0 / 255.0, o.g = 183.0 / 255.0, o.b = 90.0 / 255.0;   // :90
+                    if (ray.hit >= 0) {
+                        const float* col = rp.tri_rgb + 3 * (size_t)ray.hit;
+                        o.r = __ldg(col + 0), o.g = __ldg(col + 1), o.b = __ldg(col + 2);
+                    }
+                    write_view<kF64>(rp, b, rr, valid, ray.hit, ray.best, o);
+                }
+            }
+            t_phase[2] += clock64() - t4;
+        }
+        t_phase[0] += t1 - t0, t_phase[1] += t2 - t1, t_phase[3] += 1;
+    }
+    if (tid == 0) {
+        for (int k = 0; k < 4; ++k) atomicAdd(&rp.phase_cycles[k], (unsigned long long)t_phase[k]);
+    }
+}
+
+}  // namespace isy

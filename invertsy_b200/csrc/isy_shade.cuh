@@ -1,0 +1,103 @@
+// Final pass of the rasteriser path: shade, sky, write.
+#pragma once
+#include "isy_raster.cuh"
+
+namespace isy {
+
+// ------------------------------------------------------------------------------------------
+// final pass of the rasteriser path, float outputs, one sample per ommatidium: per ray pick the
+// winner from best[], shade, evaluate the sky and write the view (the only HBM traffic).
+// Warp units = (block of 32 consecutive rays) x (chunk of headings); a ray's eye data are loaded
+// once per unit and reused for all its headings; each store instruction covers 32 consecutive
+// rays of one view.
+// ------------------------------------------------------------------------------------------
+template <bool kSmem>
+__device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const unsigned int* gbest, int p, int grp,
+                                int Hcur) {
+    const int R = rp.R, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool perez = rp.sky.kind == ISY_SKY_PEREZ, uniform = rp.sky.kind == ISY_SKY_UNIFORM;
+    const bool from_sky = (rp.flags & ISY_FLAG_INIT_FROM_SKY) && (perez || uniform);
+    float* const o_rgb = reinterpret_cast<float*>(rp.out.rgb);
+    float* const o_depth = reinterpret_cast<float*>(rp.out.depth);
+    float* const o_Y = reinterpret_cast<float*>(rp.out.Y);
+    float* const o_P = reinterpret_cast<float*>(rp.out.dop);
+    float* const o_A = reinterpret_cast<float*>(rp.out.aop);
+    const float nanf_ = __int_as_float(0x7fc00000);
+    const int nb = (R + 31) >> 5;
+    int nch = min(Hcur, max(1, (2 * kWarps + nb - 1) / nb));
+    const int hper = (Hcur + nch - 1) / nch;
+    nch = (Hcur + hper - 1) / hper;
+    for (int u = warp; u < nb * nch; u += kWarps) {
+        const int rb = u / nch, hc = u - rb * nch;
+        const int r = rb * 32 + lane;
+        const bool valid = r < R;
+        const int rr = valid ? r : R - 1;
+        const double e_pitch = rp.eye_py[2 * (size_t)rr];
+        const bool ground = e_pitch >= 0;                               // world.py:90
+        double4 t4v = make_double4(0, 1, 0, 1);
+        double f_theta = 0;
+        if (perez) {
+            t4v = *reinterpret_cast<const double4*>(rp.eye_trig + 4 * (size_t)rr);
+            f_theta = rp.eye_ftheta[rr];
+        }
+        const int pos = __ldg(rp.grid_pos_of + rr);
+        const int hend = min(Hcur, (hc + 1) * hper);
+
+        // two headings per trip: their sky evaluations are independent instruction streams (the pass is
+        // bound by the latency of the fp64 chain, not by issue slots)
+        for (int hh0 = hc * hper; hh0 < hend; hh0 += 2) {
+            double Y[2] = {0, 0}, P[2] = {0, 0}, A[2] = {CUDART_NAN, CUDART_NAN};
+            size_t view[2];
+            unsigned int id[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int hh = min(hh0 + q, hend - 1);
+                view[q] = (size_t)p * rp.H + grp + (size_t)hh * rp.ngroups;   // group = every ngroups-th heading
+                const int hs = sm.ras.hinv[hh];
+                id[q] = kSmem ? (unsigned)sm.ras.best[hs * R + pos] : gbest[(size_t)hs * R + pos];
+                if (perez) {
+                    const double hsn = sm.head_sin[hh], hcs = sm.head_cos[hh];
+                    const double sy = t4v.z * hcs + t4v.w * hsn, cy = t4v.w * hcs - t4v.z * hsn;   // yaw_e + heading
+                    const SunConst& sc = rp.sun_per_view ? rp.sun[view[q]] : sm.sun0;   // one sun: shared memory
+                    sky_eval<false>(rp.sky, sc, t4v.y * cy, t4v.y * sy, -t4v.x, e_pitch + kHalfPi, f_theta, Y[q], P[q], A[q],
+                                    false, sm.gtab);
+                } else if (uniform) {
+                    Y[q] = rp.sky.luminance;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (hh0 + q >= hend) break;
+                float cr = nanf_, cg = nanf_, cb = nanf_, depth = nanf_;
+                int hit = -1;
+                if (from_sky) {                                              // luminance2skycolour, world.py:479
+                    cr = (float)fmin(fmax(19.0 * Y[q] + 13.0, 0.0), 255.0);
+                    cg = (float)fmin(fmax(19.0 * Y[q] + 135.0, 0.0), 255.0);
+                    cb = (float)fmin(fmax(19.0 * Y[q] + 201.0, 0.0), 255.0);
+                }
+                if (ground) cr = (float)(229.0 / 255.0), cg = (float)(183.0 / 255.0), cb = (float)(90.0 / 255.0);
+                if (id[q] != kNoCopy) {
+                    const Entry& w = sm.tile[id[q]];
+                    hit = w.tri;
+                    depth = (float)__hiloint2double(w.dist_hi, w.dist_lo);
+                    const float* col = rp.tri_rgb + 3 * (size_t)hit;
+                    cr = __ldg(col + 0), cg = __ldg(col + 1), cb = __ldg(col + 2);
+                }
+                if (valid) {
+                    const size_t i = view[q] * (size_t)R + r;
+                    if (o_rgb) {
+                        float* qq = o_rgb + 3 * i;
+                        qq[0] = cr, qq[1] = cg, qq[2] = cb;
+                    }
+                    if (rp.out.hit) rp.out.hit[i] = hit;
+                    if (o_depth) o_depth[i] = depth;
+                    if (o_Y) o_Y[i] = (float)Y[q];
+                    if (o_P) o_P[i] = (float)P[q];
+                    if (o_A) o_A[i] = (float)A[q];
+                }
+            }
+        }
+    }
+}
+
+}  // namespace isy
