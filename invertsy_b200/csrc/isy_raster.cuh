@@ -27,7 +27,10 @@ __device__ __forceinline__ int smem_atomic_add(int* p, int v) {
     asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
     return old;
 }
-constexpr int kRU = 4;                // rays per lane and iteration in the rasteriser
+#ifndef ISY_RU
+#define ISY_RU 2
+#endif
+constexpr int kRU = ISY_RU;           // rays per lane and iteration in the rasteriser
 
 // is copy e (distance d, triangle tri) nearer than copy c? (ties: lower triangle index, then lower slot)
 __device__ __forceinline__ bool nearer(const Entry* tile, double d, int tri, unsigned int e, unsigned int c) {
