@@ -42,6 +42,13 @@ __device__ __forceinline__ void emit_copy(const double th[3], const double ph[3]
         float thi = (float)fmax(th[0], fmax(th[1], th[2])) + kBinMargin;
         float plo = (float)fmin(ph[0], fmin(ph[1], ph[2])) - kBinMargin;
         float phi = (float)fmax(ph[0], fmax(ph[1], ph[2])) + kBinMargin;
+        // The three reference crosses of a proper triangle have signs (+,-,+) or (-,+,-) and the same-side
+        // region is the triangle itself.  If any of them is 0 (vertices collinear or coincident in angle
+        // space) that test passes for EVERY direction (world.py:526), and if rounding breaks the pattern the
+        // region is an unbounded wedge: such copies may contain rays anywhere, so their box is the whole domain.
+        const Exact& x = exacts[slot];
+        const bool proper = (x.o[0] > 0 && x.o[1] < 0 && x.o[2] > 0) || (x.o[0] < 0 && x.o[1] > 0 && x.o[2] < 0);
+        if (!proper) tlo = -4.f, thi = 4.f, plo = -8.f, phi = 8.f;
         sm.bbox[slot] = make_float4(tlo, thi, plo, phi);
         atomicMin(&s_band[0], float_key(tlo));
         atomicMax(&s_band[1], float_key(thi));
