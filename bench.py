@@ -249,12 +249,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)      # nvidia-smi needs ~0.3 s to start streaming: start it before the warm-up
+    sampler.start()
     for _ in range(max(args.warmup, 0)):
         step()
     barrier()
     r.check()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.rows.clear()                    # keep only the samples of the timed region
     launches0 = _lib.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
