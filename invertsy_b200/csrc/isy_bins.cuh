@@ -155,7 +155,7 @@ __device__ __forceinline__ void write_view(const RenderParams& rp, size_t b, int
     using T = typename std::conditional<kF64, double, float>::type;
     if (valid) {
         size_t ray_idx = b * (size_t)rp.R + r;
-        if (rp.out.hit) rp.out.hit[ray_idx] = hit;
+        if (rp.out.hit) __stcs(rp.out.hit + ray_idx, hit);
         if (rp.out.depth) store_val<T>(rp.out.depth, ray_idx, hit >= 0 ? best : CUDART_NAN);
     }
     const int S = rp.S;
@@ -185,7 +185,7 @@ __device__ __forceinline__ void write_view(const RenderParams& rp, size_t b, int
     size_t oi = b * (size_t)rp.N + r;
     if (rp.out.rgb) {
         T* q = reinterpret_cast<T*>(rp.out.rgb) + 3 * oi;
-        q[0] = (T)o.r, q[1] = (T)o.g, q[2] = (T)o.b;
+        __stcs(q, (T)o.r), __stcs(q + 1, (T)o.g), __stcs(q + 2, (T)o.b);
     }
     if (rp.out.Y) store_val<T>(rp.out.Y, oi, o.Y);
     if (rp.out.dop) store_val<T>(rp.out.dop, oi, o.P);

@@ -13,6 +13,10 @@ constexpr int kBins = kBinRows * kBinCols;
 constexpr int kListCap = 24576;       // candidate list entries (u16, 48 KB)
 constexpr int kMaxH = 128;            // headings whose sin/cos are cached per position
 constexpr float kBinMargin = 1e-4f;   // rad; >> every fp32 rounding in the bin arithmetic
+#ifndef ISY_TALL
+#define ISY_TALL 0.35f
+#endif
+constexpr float kTallCopy = ISY_TALL;    // rad of pitch: copies taller than this are rasterised first (they take longest)
 constexpr float kBinReject = -1e-5f;  // a bin is dropped only if an edge function is below this on all of it
 
 constexpr int kBestCap = 36864;       // (heading, ray) slots of the rasteriser's winner buffer (u16 copy slots, 72 KB)
@@ -48,6 +52,8 @@ struct SmemLayout {
     double head_sin[kMaxH], head_cos[kMaxH], head_val[kMaxH];   // per heading of the current group
     double2 gtab[2 * (kGTab + 1)];    // exp(D acos c) table of this call's sky (copied once per CTA)
     SunConst sun0;                    // sun constants when all views share one sun (copied once per CTA)
+    unsigned short order[kMaxE];      // rasterisation order: tall copies from the front, the rest from the back
+    int order_n[2];                   // ... and how many of each
     union {
         SmemBins bins;
         SmemRaster ras;
@@ -62,7 +68,7 @@ struct RayOut {
 
 template <typename T>
 __device__ __forceinline__ void store_val(void* base, size_t idx, double v) {
-    reinterpret_cast<T*>(base)[idx] = (T)v;
+    __stcs(reinterpret_cast<T*>(base) + idx, (T)v);   // streaming: written once, never read back by the kernel
 }
 
 }  // namespace isy

@@ -5,8 +5,8 @@
 namespace isy {
 
 // ------------------------------------------------------------------------------------------
-// phase A: cull + project one position. Entries go to the CTA's slab (always) and to the
-// shared-memory tile (first kMaxE). Returns the number of copies E.
+// phase A: cull + project one position. Entries go to the shared-memory tile (first kMaxE) and
+// beyond that to the CTA's slab; the exact fp64 records always go to the slab. Returns the number of copies E.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void load_vertices(const float* __restrict__ planes, int T, int t, double px, double py,
                                               double pz, double v[3][3]) {
@@ -35,7 +35,7 @@ __device__ __forceinline__ void emit_copy(const double th[3], const double ph[3]
                                           Entry* entries, Exact* exacts, SmemLayout& sm, int* s_band) {
     Entry e;
     finish_copy(th, ph, dist, t, e, exacts[slot]);
-    entries[slot] = e;
+    if (slot >= kMaxE) entries[slot] = e;   // the slab only takes what the shared-memory tile cannot hold
     if (slot < kMaxE) {
         sm.tile[slot] = e;
         float tlo = (float)fmin(th[0], fmin(th[1], th[2])) - kBinMargin;
@@ -50,13 +50,16 @@ __device__ __forceinline__ void emit_copy(const double th[3], const double ph[3]
         const bool proper = (x.o[0] > 0 && x.o[1] < 0 && x.o[2] > 0) || (x.o[0] < 0 && x.o[1] > 0 && x.o[2] < 0);
         if (!proper) tlo = -4.f, thi = 4.f, plo = -8.f, phi = 8.f;
         sm.bbox[slot] = make_float4(tlo, thi, plo, phi);
+        // longest-first order for the rasteriser's dynamic queue: a copy's cost grows with its pitch run
+        if (thi - tlo > kTallCopy) sm.order[atomicAdd(&sm.order_n[0], 1)] = (unsigned short)slot;
+        else sm.order[kMaxE - 1 - atomicAdd(&sm.order_n[1], 1)] = (unsigned short)slot;
         atomicMin(&s_band[0], float_key(tlo));
         atomicMax(&s_band[1], float_key(thi));
     }
 }
 
 __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* entries, Exact* exacts,
-                                SmemLayout& sm, int* s_count, int* s_nent, int* s_band) {
+                                SmemLayout& sm, int* s_count, int* s_nent, int* s_band, long long* t_mid = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31;
     const double px = rp.pos[3 * p + 0], py = rp.pos[3 * p + 1], pz = rp.pos[3 * p + 2];
     const double h = rp.horizon;
@@ -65,6 +68,7 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
     if (tid == 0) {
         *s_count = 0;
         *s_nent = 0;
+        sm.order_n[0] = 0, sm.order_n[1] = 0;
         s_band[0] = float_key(CUDART_INF_F);
         s_band[1] = float_key(-CUDART_INF_F);
     }
@@ -82,39 +86,70 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
     const int cx1 = (int)fmax(fmin(floor((px + h - gx0) * ginv + slack), (double)(nx - 1)), 0.0);
     const int cy0 = (int)fmax(fmin(floor((py - h - gy0) * ginv - slack), (double)(ny - 1)), 0.0);
     const int cy1 = (int)fmax(fmin(floor((py + h - gy0) * ginv + slack), (double)(ny - 1)), 0.0);
-    // the candidate cells form one contiguous list range per grid row: flatten the (<= 16) rows
+    // the candidate cells form one contiguous list range per grid row: flatten the (<= 16) rows.
+    // One lane per row: the row keeps only the columns that meet the disc of radius h around the eye
+    // (a visible triangle's nearest vertex is within h in xy), then a warp scan gives the offsets.
     __shared__ unsigned int s_rowbeg[16], s_rowoff[17];
     const int nrows = min(cy1 - cy0 + 1, 16);   // cell = horizon / 4 or larger: at most 10 rows
-    if (tid == 0) {
-        unsigned int acc = 0;
-        for (int rr = 0; rr < nrows; ++rr) {
-            const unsigned int beg = __ldg(rp.wg_cell_start + (size_t)(cy0 + rr) * nx + cx0);
-            const unsigned int end = __ldg(rp.wg_cell_start + (size_t)(cy0 + rr) * nx + cx1 + 1);
-            s_rowbeg[rr] = beg;
-            s_rowoff[rr] = acc;
-            acc += end - beg;
+    if (tid < 32) {
+        unsigned int beg = 0, cnt = 0;
+        if (tid < nrows) {
+            const int row = cy0 + tid;
+            int rx0 = cx0, rx1 = cx1;
+            if (row > 0 && row < ny - 1) {   // (border rows also hold whatever lies beyond the grid: keep the full span)
+                const double cell = 1.0 / (double)ginv;
+                const double ylo = (double)gy0 + row * cell, yhi = ylo + cell;
+                const double dy = fmax(fmax(ylo - py, py - yhi) - slack * cell, 0.0);
+                const double half = sqrt(fmax(h * h - dy * dy, 0.0)) + 1e-9;
+                rx0 = (int)fmax(fmin(floor((px - half - gx0) * ginv - slack), (double)(nx - 1)), 0.0);
+                rx1 = (int)fmax(fmin(floor((px + half - gx0) * ginv + slack), (double)(nx - 1)), 0.0);
+            }
+            beg = __ldg(rp.wg_cell_start + (size_t)row * nx + rx0);
+            cnt = __ldg(rp.wg_cell_start + (size_t)row * nx + rx1 + 1) - beg;
         }
-        s_rowoff[nrows] = acc;
+        unsigned int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) {
+            const unsigned int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        if (tid < nrows) s_rowbeg[tid] = beg, s_rowoff[tid] = incl - cnt;
+        if (tid == nrows - 1) s_rowoff[nrows] = incl;
     }
     __syncthreads();
     const unsigned int ncand = s_rowoff[nrows];
-    for (unsigned int base = 0; base < ncand; base += kThreads) {   // block-uniform trip count
-        const unsigned int c = base + tid;
-        bool visible = false;
-        int t = 0;
-        if (c < ncand) {
-            int rr = 0;
-            while (rr + 1 < nrows && c >= s_rowoff[rr + 1]) ++rr;
-            const unsigned int packed = __ldg(rp.wg_cell_tris + s_rowbeg[rr] + (c - s_rowoff[rr]));
-            t = (int)(packed & 0x3fffffffu);
-            const int tag = (int)(packed >> 30);
+    // two candidates per thread and trip: their list reads and vertex gathers (two dependent trips to L2
+    // each) overlap
+    for (unsigned int base = 0; base < ncand; base += 2 * kThreads) {   // block-uniform trip count
+        unsigned int packed[2];
+        bool have[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const unsigned int c = base + u * kThreads + tid;
+            have[u] = c < ncand;
+            packed[u] = 0;
+            if (have[u]) {
+                int rr = 0;
+                while (rr + 1 < nrows && c >= s_rowoff[rr + 1]) ++rr;
+                packed[u] = __ldg(rp.wg_cell_tris + s_rowbeg[rr] + (c - s_rowoff[rr]));
+            }
+        }
+        double s3[2][3];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
             double v[3][3];
-            load_vertices(rp.tri_planes, rp.T, t, px, py, pz, v);
-            const double s0 = norm2_rn(v[0][0], v[0][1], v[0][2]);
-            const double s1 = norm2_rn(v[1][0], v[1][1], v[1][2]);
-            const double s2 = norm2_rn(v[2][0], v[2][1], v[2][2]);
+            load_vertices(rp.tri_planes, rp.T, (int)(packed[u] & 0x3fffffffu), px, py, pz, v);
+            s3[u][0] = norm2_rn(v[0][0], v[0][1], v[0][2]);
+            s3[u][1] = norm2_rn(v[1][0], v[1][1], v[1][2]);
+            s3[u][2] = norm2_rn(v[2][0], v[2][1], v[2][2]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int t = (int)(packed[u] & 0x3fffffffu), tag = (int)(packed[u] >> 30);
+            const double s0 = s3[u][0], s1 = s3[u][1], s2 = s3[u][2];
             const double smin = fmin(s0, fmin(s1, s2));
-            if (smin <= h2_hi && __dsqrt_rn(smin) <= h) {
+            bool visible = false;
+            if (have[u] && smin <= h2_hi && __dsqrt_rn(smin) <= h) {
                 const int kn = (s0 <= s1 && s0 <= s2) ? 0 : (s1 <= s2 ? 1 : 2);   // nearest vertex
                 // same float arithmetic as the host used to file the vertices into cells
                 const float* pl = rp.tri_planes;
@@ -124,19 +159,22 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
                 const int ctx = world_cell(xt, gx0, ginv, nx), cty = world_cell(yt, gy0, ginv, ny);
                 visible = cnx == ctx && cny == cty;
             }
-        }
-        unsigned m = __ballot_sync(0xffffffffu, visible);
-        if (m) {
-            int basei = 0;
-            if (lane == 0) basei = atomicAdd(s_count, __popc(m));
-            basei = __shfl_sync(0xffffffffu, basei, 0);
-            if (visible) {
-                int slot = basei + __popc(m & ((1u << lane) - 1));
-                if (slot < rp.slab_cap) vis[slot] = t;
+            unsigned m = __ballot_sync(0xffffffffu, visible);
+            if (m) {
+                int basei = 0;
+                if (lane == 0) basei = atomicAdd(s_count, __popc(m));
+                basei = __shfl_sync(0xffffffffu, basei, 0);
+                if (visible) {
+                    int slot = basei + __popc(m & ((1u << lane) - 1));
+                    if (slot < rp.slab_cap) vis[slot] = t;
+                }
             }
         }
     }
     __syncthreads();
+#ifdef ISY_PHASE_DETAIL
+    *t_mid = clock64();   // (profiling build only) end of the cull
+#endif
     int V = *s_count;
     if (V > rp.slab_cap) {
         if (tid == 0) atomicExch(rp.status, (int)ISY_ERR_OVERFLOW);

@@ -65,8 +65,10 @@ __device__ __forceinline__ void post_copy_u32(unsigned int* slot, const Entry* t
     }
 }
 
-// sorts the group's wrapped headings (head_val[0..Hcur)) and builds the azimuth look-up table
-__device__ void sort_headings(SmemLayout& sm, int Hcur) {
+// sorts the group's wrapped headings (head_val[0..Hcur)); returns true (to every thread) when they are evenly
+// spaced over the full circle -- every scan of the reference's simulations, and a single heading -- so that
+// the window walk can use arithmetic; otherwise it also builds the azimuth look-up table
+__device__ bool sort_headings(SmemLayout& sm, int Hcur) {
     const int tid = threadIdx.x;
     if (tid < Hcur) {
         const float h = (float)sm.head_val[tid];
@@ -84,22 +86,129 @@ __device__ void sort_headings(SmemLayout& sm, int Hcur) {
         sm.ras.hinv[tid] = (unsigned char)pos;
     }
     __syncthreads();
-    if (tid == 0) {
-        // evenly spaced headings over the full circle (every scan of the reference's simulations, and a
-        // single heading) let the window walk use arithmetic instead of the look-up table
-        const float h0 = sm.ras.hsort[0];
-        const float delta = (float)kTwoPi / (float)Hcur;
-        bool ok = true;
-        for (int k = 1; k < Hcur; ++k) ok = ok && fabsf(sm.ras.hsort[k] - (h0 + k * delta)) < 5e-7f;
-        sm.ras.uni[0] = h0, sm.ras.uni[1] = delta, sm.ras.uni[2] = 1.0f / delta, sm.ras.uni[3] = ok ? 1.f : 0.f;
+    const float h0 = sm.ras.hsort[0];
+    const float delta = (float)kTwoPi / (float)Hcur;
+    const bool mine = tid >= Hcur || fabsf(sm.ras.hsort[tid] - (h0 + tid * delta)) < 5e-7f;
+    const bool uniform = __syncthreads_and(mine);
+    if (tid == 0) sm.ras.uni[0] = h0, sm.ras.uni[1] = delta, sm.ras.uni[2] = 1.0f / delta, sm.ras.uni[3] = uniform ? 1.f : 0.f;
+    if (!uniform) {
+        for (int s = tid; s < kHeadLut; s += kThreads) {
+            // first sorted slot whose heading is not below this azimuth slot (minus a guard band):
+            // windows start their walk here; whatever they pick up below `lower` just fails the edge test
+            const float start = -(float)kPi + s * ((float)kTwoPi / kHeadLut) - 1e-4f;
+            int k = 0;
+            while (k < 2 * Hcur && sm.ras.hsort[k] < start) ++k;
+            sm.ras.hlut[s] = (unsigned short)k;
+        }
     }
-    for (int s = tid; s < kHeadLut; s += kThreads) {
-        // first sorted slot whose heading is not below this azimuth slot (minus a guard band):
-        // windows start their walk here; whatever they pick up below `lower` just fails the edge test
-        const float start = -(float)kPi + s * ((float)kTwoPi / kHeadLut) - 1e-4f;
-        int k = 0;
-        while (k < 2 * Hcur && sm.ras.hsort[k] < start) ++k;
-        sm.ras.hlut[s] = (unsigned short)k;
+    return uniform;
+}
+
+// One step of the pitch-run walk: RU rays per lane (32 * RU consecutive pitch-sorted rays from jb) against copy e.
+// Their window walks and edge tests are independent instruction streams, which is what hides the
+// shared-memory and branch latencies here.
+template <bool kSmem, bool kUniform, int RU>
+__device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest, const Exact* exacts,
+                                           const Entry& ent, const float4 bb, double dist, int e, unsigned jb, unsigned jend,
+                                           float glo, float width, int Hcur) {
+    const int R = rp.R, lane = threadIdx.x & 31, H2 = 2 * Hcur;
+    const float2* gsorted = reinterpret_cast<const float2*>(rp.grid_sorted);
+    const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
+    const float uh0 = sm.ras.uni[0], udelta = sm.ras.uni[1], uinv = sm.ras.uni[2];
+    float2 py[RU];
+    int k[RU], ks[RU];    // window cursor; sorted slot of the heading under the cursor
+    float upper[RU];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+        const unsigned j = jb + u * 32 + lane;
+        py[u] = make_float2(4.f, 0.f);                  // pitch 4 rad: outside every band
+        if (j < jend) py[u] = kSmem ? sm.ras.sorted[j] : __ldg(gsorted + j);
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+        // headings h with yaw + h in [glo, ghi]  <=>  h in [lower, lower + width] on the circle
+        float lower = glo - py[u].y;
+        if (lower < -pi_f) lower += twopi_f;
+        else if (lower >= pi_f) lower -= twopi_f;
+        const bool band = py[u].x >= bb.x && py[u].x <= bb.y;
+        if (kUniform) {
+            // headings are h0 + k*delta (k mod H): the window is the index range [k0, k1];
+            // k[] counts the headings left in the window, ks[] is the sorted slot of the next one
+            const float a = (lower - uh0) * uinv;
+            const int k0 = (int)ceilf(a - 2e-4f), k1 = (int)floorf(fmaf(width, uinv, a) + 2e-4f);
+            k[u] = band ? min(k1 - k0 + 1, Hcur) : 0;            // lower in [-pi, pi): k0 in [-H, H]
+            ks[u] = k0 < 0 ? k0 + Hcur : (k0 >= Hcur ? k0 - Hcur : k0);
+            upper[u] = 0.f;
+        } else {
+            const int ls = min(max((int)((lower + pi_f) * (kHeadLut / twopi_f)), 0), kHeadLut - 1);
+            k[u] = band ? (int)sm.ras.hlut[ls] : H2;
+            upper[u] = lower + width;
+        }
+    }
+    // lanes walk their heading windows in lock step (most windows hold 0 or 1 heading)
+    for (;;) {
+        bool act[RU], any = false;
+        float hv[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            if (kUniform) {
+                act[u] = k[u] > 0;
+                hv[u] = fmaf((float)ks[u], udelta, uh0);
+            } else {
+                const int kk = min(k[u], H2 - 1);
+                act[u] = k[u] < H2 && sm.ras.hsort[kk] <= upper[u];
+                hv[u] = sm.ras.hvalf[kk];
+                ks[u] = kk >= Hcur ? kk - Hcur : kk;       // the + 2 pi copy is the same heading
+            }
+            any |= act[u];
+        }
+        if (!__any_sync(0xffffffffu, any)) break;
+        float fy[RU], m[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {                 // branch-free: the common case of every slot
+            float f = py[u].y + hv[u];                  // both in (-pi, pi]: one shift wraps
+            f = f > pi_f ? f - twopi_f : (f <= -pi_f ? f + twopi_f : f);
+            fy[u] = f;
+            const float e0 = fmaf(ent.A0, py[u].x, fmaf(ent.B0, f, ent.C0));
+            const float e1 = fmaf(ent.A1, py[u].x, fmaf(ent.B1, f, ent.C1));
+            const float e2 = fmaf(ent.A2, py[u].x, fmaf(ent.B2, f, ent.C2));
+            m[u] = fminf(e0, fminf(e1, e2));
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const unsigned j = jb + u * 32 + lane;
+            const bool seam = fabsf(fy[u]) > 3.14159f;
+            bool in = act[u] && m[u] > kEdgeEps && !seam;
+            // rare: the rounding band of an edge, or a query within 3e-6 rad of the seam ->
+            // redo the query in fp64 exactly as the reference composes it
+            if (act[u] && (seam || (m[u] >= -kEdgeEps && m[u] <= kEdgeEps))) {
+                const int hh = sm.ras.hperm[ks[u]];
+                const int ray = __ldg(rp.grid_sorted_ray + j);
+                double yg = rp.eye_py[2 * (size_t)ray + 1] + sm.head_val[hh];
+                if (yg > kPi) yg -= kTwoPi;
+                else if (yg <= -kPi) yg += kTwoPi;
+                const float f = (float)yg;
+                const float e0 = fmaf(ent.A0, py[u].x, fmaf(ent.B0, f, ent.C0));
+                const float e1 = fmaf(ent.A1, py[u].x, fmaf(ent.B1, f, ent.C1));
+                const float e2 = fmaf(ent.A2, py[u].x, fmaf(ent.B2, f, ent.C2));
+                const float mm = fminf(e0, fminf(e1, e2));
+                in = mm > kEdgeEps;
+                if (!in && mm >= -kEdgeEps) in = inside_exact(exacts[e], rp.eye_py[2 * (size_t)ray], yg);
+            }
+            // rows of best[] are SORTED heading slots
+            if (in) {
+                if (kSmem) post_copy_u16(sm.ras.best, (unsigned)ks[u] * R + j, sm.tile, dist, ent.tri, e);
+                else post_copy_u32(&gbest[(size_t)ks[u] * R + j], sm.tile, dist, ent.tri, e);
+            }
+            if (kUniform) {
+                if (act[u]) {
+                    --k[u];
+                    ks[u] = ks[u] + 1 == Hcur ? 0 : ks[u] + 1;
+                }
+            } else if (act[u]) {
+                ++k[u];
+            }
+        }
     }
 }
 
@@ -111,17 +220,16 @@ __device__ void sort_headings(SmemLayout& sm, int Hcur) {
 template <bool kSmem, bool kUniform>
 __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest, const Exact* exacts, int E,
                               int Hcur, int* s_next) {
-    const int R = rp.R, lane = threadIdx.x & 31;
-    const float2* gsorted = reinterpret_cast<const float2*>(rp.grid_sorted);
-    const int H2 = 2 * Hcur;
-    const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
-    const float uh0 = sm.ras.uni[0], udelta = sm.ras.uni[1], uinv = sm.ras.uni[2];
+    const int lane = threadIdx.x & 31;
+    const float pi_f = (float)kPi;
+    const int ntall = sm.order_n[0];
     for (;;) {
         // copies differ a lot in size (a near blade spans hundreds of rays): warps pull them from a counter
         int e = 0;
         if (lane == 0) e = smem_atomic_add(s_next, 1);
         e = __shfl_sync(0xffffffffu, e, 0);
         if (e >= E) break;
+        e = sm.order[e < ntall ? e : kMaxE - 1 - (e - ntall)];   // tall copies first: no long straggler at the end
         const float4 bb = sm.bbox[e];
         // azimuth window of the copy clipped to the query domain (-pi, pi]
         const float glo = fmaxf(bb.z, -pi_f - kBinMargin) - kBinMargin, ghi = fminf(bb.w, pi_f + kBinMargin) + kBinMargin;
@@ -134,105 +242,15 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
         const int s1 = min(max((int)floorf((bb.y + (float)kHalfPi) * (kPitchLut / (float)kPi)) + 2, 0), kPitchLut);
         const unsigned jbeg = kSmem ? sm.ras.plut[s0] : __ldg(rp.grid_plut + s0);
         const unsigned jend = kSmem ? sm.ras.plut[s1] : __ldg(rp.grid_plut + s1);
-        // kRU rays per lane and iteration: their window walks and edge tests are independent
-        // instruction streams, which is what hides the shared-memory and branch latencies here
-        for (unsigned jb = jbeg; jb < jend; jb += 32 * kRU) {   // warp-uniform trip count
+        // two rays per lane while more than a warp's worth is left, one ray per lane for the tail
+        unsigned jb = jbeg;
+        for (; jb + 32 * (kRU - 1) < jend; jb += 32 * kRU) {   // warp-uniform trip count
             __syncwarp();                                       // keep the lanes converged across iterations
-            float2 py[kRU];
-            int k[kRU], ks[kRU];    // window cursor; sorted slot of the heading under the cursor
-            float upper[kRU];
-#pragma unroll
-            for (int u = 0; u < kRU; ++u) {
-                const unsigned j = jb + u * 32 + lane;
-                py[u] = make_float2(4.f, 0.f);                  // pitch 4 rad: outside every band
-                if (j < jend) py[u] = kSmem ? sm.ras.sorted[j] : __ldg(gsorted + j);
-            }
-#pragma unroll
-            for (int u = 0; u < kRU; ++u) {
-                // headings h with yaw + h in [glo, ghi]  <=>  h in [lower, lower + width] on the circle
-                float lower = glo - py[u].y;
-                if (lower < -pi_f) lower += twopi_f;
-                else if (lower >= pi_f) lower -= twopi_f;
-                const bool band = py[u].x >= bb.x && py[u].x <= bb.y;
-                if (kUniform) {
-                    // headings are h0 + k*delta (k mod H): the window is the index range [k0, k1];
-                    // k[] counts the headings left in the window, ks[] is the sorted slot of the next one
-                    const float a = (lower - uh0) * uinv;
-                    const int k0 = (int)ceilf(a - 2e-4f), k1 = (int)floorf(fmaf(width, uinv, a) + 2e-4f);
-                    k[u] = band ? min(k1 - k0 + 1, Hcur) : 0;            // lower in [-pi, pi): k0 in [-H, H]
-                    ks[u] = k0 < 0 ? k0 + Hcur : (k0 >= Hcur ? k0 - Hcur : k0);
-                    upper[u] = 0.f;
-                } else {
-                    const int ls = min(max((int)((lower + pi_f) * (kHeadLut / twopi_f)), 0), kHeadLut - 1);
-                    k[u] = band ? (int)sm.ras.hlut[ls] : H2;
-                    upper[u] = lower + width;
-                }
-            }
-            // lanes walk their heading windows in lock step (most windows hold 0 or 1 heading)
-            for (;;) {
-                bool act[kRU], any = false;
-                float hv[kRU];
-#pragma unroll
-                for (int u = 0; u < kRU; ++u) {
-                    if (kUniform) {
-                        act[u] = k[u] > 0;
-                        hv[u] = fmaf((float)ks[u], udelta, uh0);
-                    } else {
-                        const int kk = min(k[u], H2 - 1);
-                        act[u] = k[u] < H2 && sm.ras.hsort[kk] <= upper[u];
-                        hv[u] = sm.ras.hvalf[kk];
-                        ks[u] = kk >= Hcur ? kk - Hcur : kk;       // the + 2 pi copy is the same heading
-                    }
-                    any |= act[u];
-                }
-                if (!__any_sync(0xffffffffu, any)) break;
-                float fy[kRU], m[kRU];
-#pragma unroll
-                for (int u = 0; u < kRU; ++u) {                 // branch-free: the common case of every slot
-                    float f = py[u].y + hv[u];                  // both in (-pi, pi]: one shift wraps
-                    f = f > pi_f ? f - twopi_f : (f <= -pi_f ? f + twopi_f : f);
-                    fy[u] = f;
-                    const float e0 = fmaf(ent.A0, py[u].x, fmaf(ent.B0, f, ent.C0));
-                    const float e1 = fmaf(ent.A1, py[u].x, fmaf(ent.B1, f, ent.C1));
-                    const float e2 = fmaf(ent.A2, py[u].x, fmaf(ent.B2, f, ent.C2));
-                    m[u] = fminf(e0, fminf(e1, e2));
-                }
-#pragma unroll
-                for (int u = 0; u < kRU; ++u) {
-                    const unsigned j = jb + u * 32 + lane;
-                    const bool seam = fabsf(fy[u]) > 3.14159f;
-                    bool in = act[u] && m[u] > kEdgeEps && !seam;
-                    // rare: the rounding band of an edge, or a query within 3e-6 rad of the seam ->
-                    // redo the query in fp64 exactly as the reference composes it
-                    if (act[u] && (seam || (m[u] >= -kEdgeEps && m[u] <= kEdgeEps))) {
-                        const int hh = sm.ras.hperm[ks[u]];
-                        const int ray = __ldg(rp.grid_sorted_ray + j);
-                        double yg = rp.eye_py[2 * (size_t)ray + 1] + sm.head_val[hh];
-                        if (yg > kPi) yg -= kTwoPi;
-                        else if (yg <= -kPi) yg += kTwoPi;
-                        const float f = (float)yg;
-                        const float e0 = fmaf(ent.A0, py[u].x, fmaf(ent.B0, f, ent.C0));
-                        const float e1 = fmaf(ent.A1, py[u].x, fmaf(ent.B1, f, ent.C1));
-                        const float e2 = fmaf(ent.A2, py[u].x, fmaf(ent.B2, f, ent.C2));
-                        const float mm = fminf(e0, fminf(e1, e2));
-                        in = mm > kEdgeEps;
-                        if (!in && mm >= -kEdgeEps) in = inside_exact(exacts[e], rp.eye_py[2 * (size_t)ray], yg);
-                    }
-                    // rows of best[] are SORTED heading slots
-                    if (in) {
-                        if (kSmem) post_copy_u16(sm.ras.best, (unsigned)ks[u] * R + j, sm.tile, dist, ent.tri, e);
-                        else post_copy_u32(&gbest[(size_t)ks[u] * R + j], sm.tile, dist, ent.tri, e);
-                    }
-                    if (kUniform) {
-                        if (act[u]) {
-                            --k[u];
-                            ks[u] = ks[u] + 1 == Hcur ? 0 : ks[u] + 1;
-                        }
-                    } else if (act[u]) {
-                        ++k[u];
-                    }
-                }
-            }
+            walk_chunk<kSmem, kUniform, kRU>(rp, sm, gbest, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur);
+        }
+        if (jb < jend) {
+            __syncwarp();
+            walk_chunk<kSmem, kUniform, 1>(rp, sm, gbest, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur);
         }
     }
 }

@@ -30,17 +30,33 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
         if (tid == 0) sm.sun0 = rp.sun[0];
     }
     long long t_phase[4] = {0, 0, 0, 0};   // project, accel (bins / raster), final ray pass, positions
+#ifdef ISY_PHASE_DETAIL
+    long long t_detail[3] = {0, 0, 0};     // profiling build: cull, projection, raster set-up (replace phases 0..2)
+#endif
+    // work items come from a global counter; the next one is requested while the current one is rendered,
+    // so the round trip of the atomic is never waited for
+    unsigned int pulled = 0;
+    if (tid == 0) pulled = atomicAdd(rp.queue, 1u);
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_item = atomicAdd(rp.queue, 1u);
+        if (tid == 0) s_item = pulled;
         __syncthreads();
         const unsigned item = s_item;
         if (item >= (unsigned)rp.items) break;
+        if (tid == 0) pulled = atomicAdd(rp.queue, 1u);
         const int p = item / rp.splits, split = item % rp.splits;
         long long t0 = clock64();
 
+#ifdef ISY_PHASE_DETAIL
+        long long g_detail_t = t0;
+        const int E = cull_and_project(rp, p, vis, entries, exacts, sm, &s_count, &s_nent, s_band, &g_detail_t);
+#else
         const int E = cull_and_project(rp, p, vis, entries, exacts, sm, &s_count, &s_nent, s_band);
+#endif
         long long t1 = clock64();
+#ifdef ISY_PHASE_DETAIL
+        t_detail[0] += g_detail_t - t0, t_detail[1] += t1 - g_detail_t;
+#endif
         int mode = kModeBrute;
         BinGrid grid;
         if (!(rp.flags & ISY_FLAG_BRUTE_FORCE) && E <= kMaxE) {
@@ -67,6 +83,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
             // group grp = headings grp, grp + ngroups, ...: an evenly spaced scan stays evenly spaced
             const int Hcur = (rp.H - grp + rp.ngroups - 1) / rp.ngroups;
             long long t3 = clock64();
+#ifdef ISY_PHASE_DETAIL
+            long long t_walk = t3;
+#endif
             __syncthreads();
             if (yaw_only && tid < Hcur) {
                 const double hw = wrap_yaw(rp.yaw ? rp.yaw[(size_t)p * rp.H + grp + (size_t)tid * rp.ngroups] : 0.0);
@@ -82,9 +101,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                 }
                 __syncthreads();
                 if (tid == 0) s_count = 0;     // (the cull's counter is free again: next copy to rasterise)
-                sort_headings(sm, Hcur);
+                const bool uniform = sort_headings(sm, Hcur);
                 __syncthreads();
-                const bool uniform = sm.ras.uni[3] != 0.f;
+#ifdef ISY_PHASE_DETAIL
+                t_walk = clock64();
+#endif
                 if (Hcur <= kSmallH && smem_grid) {
                     // (large eyes keep the pitch-run walk: their cells hold many rays and the lanes of a run stay full)
                     raster_cells<true>(rp, sm, gbest, exacts, E, Hcur, &s_count);
@@ -99,6 +120,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
             __syncthreads();
             long long t4 = clock64();
             t_phase[1] += t4 - t3;
+#ifdef ISY_PHASE_DETAIL
+            t_detail[2] += t_walk - t3;
+#endif
 
             if (mode == kModeRaster && !kF64 && rp.S == 1 && !rp.init_c) {
                 if (smem_grid) final_pass_fast<true>(rp, sm, gbest, p, grp, Hcur);
@@ -187,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                     } else if (E <= kMaxE) {
                         for (int j = 0; j < E; ++j) test_entry(ray, &sm.tile[j], &exacts[j]);
                     } else {   // more copies than the tile holds: stream them from the slab
-                        for (int j = 0; j < E; ++j) test_entry(ray, &entries[j], &exacts[j]);
+                        for (int j = 0; j < E; ++j) test_entry(ray, j < kMaxE ? &sm.tile[j] : &entries[j], &exacts[j]);
                     }
 
                     RayOut o;
@@ -220,6 +244,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
         t_phase[0] += t1 - t0, t_phase[1] += t2 - t1, t_phase[3] += 1;
     }
     if (tid == 0) {
+#ifdef ISY_PHASE_DETAIL
+        for (int k = 0; k < 3; ++k) t_phase[k] = t_detail[k];
+#endif
         for (int k = 0; k < 4; ++k) atomicAdd(&rp.phase_cycles[k], (unsigned long long)t_phase[k]);
     }
 }

@@ -11,6 +11,11 @@ namespace isy {
 // once per unit and reused for all its headings; each store instruction covers 32 consecutive
 // rays of one view.
 // ------------------------------------------------------------------------------------------
+#ifndef ISY_SHADE_U
+#define ISY_SHADE_U 2
+#endif
+constexpr int kSU = ISY_SHADE_U;      // headings per lane and trip in the final pass
+
 template <bool kSmem>
 __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const unsigned int* gbest, int p, int grp,
                                 int Hcur) {
@@ -43,14 +48,15 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
         const int pos = __ldg(rp.grid_pos_of + rr);
         const int hend = min(Hcur, (hc + 1) * hper);
 
-        // two headings per trip: their sky evaluations are independent instruction streams (the pass is
+        // kSU headings per trip: their sky evaluations are independent instruction streams (the pass is
         // bound by the latency of the fp64 chain, not by issue slots)
-        for (int hh0 = hc * hper; hh0 < hend; hh0 += 2) {
-            double Y[2] = {0, 0}, P[2] = {0, 0}, A[2] = {CUDART_NAN, CUDART_NAN};
-            size_t view[2];
-            unsigned int id[2];
+        for (int hh0 = hc * hper; hh0 < hend; hh0 += kSU) {
+            double Y[kSU], P[kSU], A[kSU];
+            size_t view[kSU];
+            unsigned int id[kSU];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < kSU; ++q) {
+                Y[q] = 0, P[q] = 0, A[q] = CUDART_NAN;
                 const int hh = min(hh0 + q, hend - 1);
                 view[q] = (size_t)p * rp.H + grp + (size_t)hh * rp.ngroups;   // group = every ngroups-th heading
                 const int hs = sm.ras.hinv[hh];
@@ -66,7 +72,7 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < kSU; ++q) {
                 if (hh0 + q >= hend) break;
                 float cr = nanf_, cg = nanf_, cb = nanf_, depth = nanf_;
                 int hit = -1;
@@ -85,15 +91,17 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
                 }
                 if (valid) {
                     const size_t i = view[q] * (size_t)R + r;
+                    // streaming stores: the views are written once and never read back by the kernel, so they
+                    // should leave L2 before the slabs, the world and the eye tables do
                     if (o_rgb) {
                         float* qq = o_rgb + 3 * i;
-                        qq[0] = cr, qq[1] = cg, qq[2] = cb;
+                        __stcs(qq, cr), __stcs(qq + 1, cg), __stcs(qq + 2, cb);
                     }
-                    if (rp.out.hit) rp.out.hit[i] = hit;
-                    if (o_depth) o_depth[i] = depth;
-                    if (o_Y) o_Y[i] = (float)Y[q];
-                    if (o_P) o_P[i] = (float)P[q];
-                    if (o_A) o_A[i] = (float)A[q];
+                    if (rp.out.hit) __stcs(rp.out.hit + i, hit);
+                    if (o_depth) __stcs(o_depth + i, depth);
+                    if (o_Y) __stcs(o_Y + i, (float)Y[q]);
+                    if (o_P) __stcs(o_P + i, (float)P[q]);
+                    if (o_A) __stcs(o_A + i, (float)A[q]);
                 }
             }
         }
