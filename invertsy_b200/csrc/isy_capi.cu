@@ -349,6 +349,16 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
     RenderParams rp;
     memset(&rp, 0, sizeof rp);
     rp.tri_planes = w->d_planes, rp.tri_rgb = w->d_rgb, rp.T = (int)w->T, rp.horizon = w->horizon;
+    {   // sqrt is monotone and correctly rounded on both sides: {s : sqrt(s) <= horizon} = [0, horizon_sq_max]
+        double s2 = w->horizon * w->horizon;
+        if (w->horizon >= 0 && std::isfinite(s2)) {
+            while (std::sqrt(s2) <= w->horizon) s2 = std::nextafter(s2, INFINITY);
+            while (s2 > 0 && std::sqrt(s2) > w->horizon) s2 = std::nextafter(s2, -INFINITY);
+        } else {
+            s2 = w->horizon >= 0 ? INFINITY : -1.0;   // negative horizon: nothing is visible
+        }
+        rp.horizon_sq_max = s2;
+    }
     rp.wg_cell_start = w->d_cell_start, rp.wg_cell_tris = w->d_cell_tris;
     rp.wg_x0 = w->gx0, rp.wg_y0 = w->gy0, rp.wg_inv_cell = w->ginv, rp.wg_nx = w->gnx, rp.wg_ny = w->gny;
     rp.eye_py = e->d_py, rp.eye_quat = e->d_quat, rp.eye_w = e->d_w, rp.eye_trig = e->d_trig;

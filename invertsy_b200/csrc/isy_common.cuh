@@ -68,6 +68,7 @@ struct RenderParams {
     const float* tri_rgb;
     int T;
     double horizon;
+    double horizon_sq_max;                // largest s with sqrt_rn(s) <= horizon: `sqrt(s) <= horizon` without the sqrt
     // xy cell grid over the world's vertices (cull candidates)
     const unsigned int* wg_cell_start;   // [ny*nx + 1] row-major
     const unsigned int* wg_cell_tris;    // triangle index | (vertex tag << 30)

@@ -63,7 +63,7 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
     const int tid = threadIdx.x, lane = tid & 31;
     const double px = rp.pos[3 * p + 0], py = rp.pos[3 * p + 1], pz = rp.pos[3 * p + 2];
     const double h = rp.horizon;
-    const double h2_hi = h * h * (1.0 + 1e-12);  // above this the rounded norm cannot be <= horizon
+    const double h2_max = rp.horizon_sq_max;     // sqrt_rn(s) <= horizon  <=>  s <= h2_max (set by the host)
 
     if (tid == 0) {
         *s_count = 0;
@@ -121,6 +121,11 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
     // two candidates per thread and trip: their list reads and vertex gathers (two dependent trips to L2
     // each) overlap
     for (unsigned int base = 0; base < ncand; base += 2 * kThreads) {   // block-uniform trip count
+#if defined(ISY_PHASE_DETAIL) && ISY_PHASE_DETAIL == 3
+        long long c0, c1;
+        const long long cs = clock64();
+        if (base == 0) t_mid[3] = cs;
+#endif
         unsigned int packed[2];
         bool have[2];
 #pragma unroll
@@ -135,26 +140,34 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
             }
         }
         double s3[2][3];
+        float vx[2][3], vy[2][3];   // raw xy of the vertices: the cell test below files them like the host did
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            double v[3][3];
-            load_vertices(rp.tri_planes, rp.T, (int)(packed[u] & 0x3fffffffu), px, py, pz, v);
-            s3[u][0] = norm2_rn(v[0][0], v[0][1], v[0][2]);
-            s3[u][1] = norm2_rn(v[1][0], v[1][1], v[1][2]);
-            s3[u][2] = norm2_rn(v[2][0], v[2][1], v[2][2]);
+            const int t = (int)(packed[u] & 0x3fffffffu);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                vx[u][k] = __ldg(rp.tri_planes + (size_t)(3 * k + 0) * rp.T + t);
+                vy[u][k] = __ldg(rp.tri_planes + (size_t)(3 * k + 1) * rp.T + t);
+                const float vz = __ldg(rp.tri_planes + (size_t)(3 * k + 2) * rp.T + t);
+                s3[u][k] = norm2_rn((double)vx[u][k] - px, (double)vy[u][k] - py, (double)vz - pz);   // world.py:94-96
+            }
         }
+#if defined(ISY_PHASE_DETAIL) && ISY_PHASE_DETAIL == 3
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(c0) : "d"(s3[0][0] + s3[1][0] + s3[0][1] + s3[1][1] + s3[0][2] + s3[1][2]));
+#endif
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int t = (int)(packed[u] & 0x3fffffffu), tag = (int)(packed[u] >> 30);
             const double s0 = s3[u][0], s1 = s3[u][1], s2 = s3[u][2];
             const double smin = fmin(s0, fmin(s1, s2));
             bool visible = false;
-            if (have[u] && smin <= h2_hi && __dsqrt_rn(smin) <= h) {
+            if (have[u] && smin <= h2_max) {                                      // world.py:97
                 const int kn = (s0 <= s1 && s0 <= s2) ? 0 : (s1 <= s2 ? 1 : 2);   // nearest vertex
                 // same float arithmetic as the host used to file the vertices into cells
-                const float* pl = rp.tri_planes;
-                const float xn = __ldg(pl + (size_t)(3 * kn) * rp.T + t), yn = __ldg(pl + (size_t)(3 * kn + 1) * rp.T + t);
-                const float xt = __ldg(pl + (size_t)(3 * tag) * rp.T + t), yt = __ldg(pl + (size_t)(3 * tag + 1) * rp.T + t);
+                const float xn = kn == 0 ? vx[u][0] : (kn == 1 ? vx[u][1] : vx[u][2]);
+                const float yn = kn == 0 ? vy[u][0] : (kn == 1 ? vy[u][1] : vy[u][2]);
+                const float xt = tag == 0 ? vx[u][0] : (tag == 1 ? vx[u][1] : vx[u][2]);
+                const float yt = tag == 0 ? vy[u][0] : (tag == 1 ? vy[u][1] : vy[u][2]);
                 const int cnx = world_cell(xn, gx0, ginv, nx), cny = world_cell(yn, gy0, ginv, ny);
                 const int ctx = world_cell(xt, gx0, ginv, nx), cty = world_cell(yt, gy0, ginv, ny);
                 visible = cnx == ctx && cny == cty;
@@ -170,6 +183,10 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
                 }
             }
         }
+#if defined(ISY_PHASE_DETAIL) && ISY_PHASE_DETAIL == 3
+        c1 = clock64();
+        t_mid[1] += c0 - cs, t_mid[2] += c1 - c0;   // summed over the trips of this position
+#endif
     }
     __syncthreads();
 #ifdef ISY_PHASE_DETAIL
