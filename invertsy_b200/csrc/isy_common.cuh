@@ -297,7 +297,10 @@ __device__ __forceinline__ void sky_eval(const isy_sky_params& sp, const SunCons
     } else {
         // gamma itself is never needed: exp(D gamma) comes from the table, the sun disc is a test on cos(gamma)
         gamma = cg > 0.99862953475457383 ? 0.0 : kPi;                    // cos(pi / 60)
-        const double i_prez = f_theta * (1.0 + sp.C * g_table_eval(gtab, cg) + sp.E * (cg * cg));
+        // f_theta is exactly 0 for every direction below the horizon (sky.py:366-370): the product is 0 whatever
+        // the finite bracket holds, so those rays (half of a full-sphere eye, whole warps of it) skip the table
+        const double g = f_theta != 0.0 ? g_table_eval(gtab, cg) : 0.0;
+        const double i_prez = f_theta * (1.0 + sp.C * g + sp.E * (cg * cg));
         Y = fmax(sc.Yz * i_prez * sc.inv_i00, 0.0);
         const float cg2 = fminf((float)(cg * cg), 1.0f);
         const float lp = __fdividef(1.0f - cg2, 1.0f + cg2);
