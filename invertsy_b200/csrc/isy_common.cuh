@@ -240,12 +240,13 @@ constexpr int kGTab = 256;   // intervals of the G(c) = exp(D acos c) table, per
 // is analytic on [0, 1], so 256 intervals give |error| < 1e-9 for any |D| < 4 (tests/test_oracle.py checks the
 // construction on the CPU, DESIGN.md "sky error budget").  tab[half][i] = {G(u_i), dG/du(u_i) * h}.
 __device__ __forceinline__ double g_table_eval(const double2* __restrict__ tab, double c) {
-    const double x = 1.0 - fabs(c);
-    double u = 0.0;
-    if (x > 1e-30) {   // sqrt(x): float rsqrt seed + one Newton step in fp64 (relative error ~1e-14)
-        const double r0 = (double)rsqrtf((float)x);
-        u = x * (r0 * (1.5 - 0.5 * x * r0 * r0));
-    }
+    // sqrt(x): float rsqrt seed (bare MUFU.RSQ) + one Newton step in fp64, relative error ~1e-14.
+    // x is kept >= 1e-30 (u = 1e-15 instead of 0 moves G by 3e-15), which makes the step branch-free.
+    const double x = fmax(1.0 - fabs(c), 1e-30);
+    float r0f;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r0f) : "f"((float)x));
+    const double r0 = (double)r0f;
+    const double u = x * (r0 * (1.5 - 0.5 * x * r0 * r0));
     const double um = u * (double)kGTab;
     const int idx = min((int)um, kGTab - 1);
     const double t = um - (double)idx;
@@ -258,10 +259,18 @@ __device__ __forceinline__ double g_table_eval(const double2* __restrict__ tab, 
 
 // atan2 for the float polarisation angle: odd degree-15 minimax polynomial on [0, 1] (max error 1.4e-7
 // in fp32 evaluation) after one fast division, then the usual octant fix-ups; |error| < 5e-7 rad
+// 1 / x by the bare MUFU.RCP (1 ulp, flushes denormals): for operands known to be normal floats, where
+// __fdividef's range fix-ups for huge denominators only cost instructions
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ float atan2_fast(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float hi = fmaxf(ax, ay), lo = fminf(ax, ay);
-    const float a = hi > 0.f ? __fdividef(lo, hi) : 0.f;
+    const float a = hi > 1e-30f ? lo * rcp_fast(hi) : 0.f;   // (hi below 1e-30: the direction IS the sun's, any angle is right)
     const float s = a * a;
     float p = -0.004054563585668802f;
     p = fmaf(p, s, 0.021862946450710297f);
@@ -301,10 +310,11 @@ __device__ __forceinline__ void sky_eval(const isy_sky_params& sp, const SunCons
         // the finite bracket holds, so those rays (half of a full-sphere eye, whole warps of it) skip the table
         const double g = f_theta != 0.0 ? g_table_eval(gtab, cg) : 0.0;
         const double i_prez = f_theta * (1.0 + sp.C * g + sp.E * (cg * cg));
-        Y = fmax(sc.Yz * i_prez * sc.inv_i00, 0.0);
+        const double y = sc.Yz * i_prez * sc.inv_i00;
+        Y = y > 0.0 ? y : 0.0;                                          // max(y, 0) of sky.py:313 (y is never NaN)
         const float cg2 = fminf((float)(cg * cg), 1.0f);
-        const float lp = __fdividef(1.0f - cg2, 1.0f + cg2);
-        const float i = (__fdividef(1.0f, (float)i_prez + (float)kEps) - sc.inv_i00_f) * sc.K_f;
+        const float lp = (1.0f - cg2) * rcp_fast(1.0f + cg2);
+        const float i = (rcp_fast((float)i_prez + (float)kEps) - sc.inv_i00_f) * sc.K_f;   // >= 2.2e-16: normal
         const float p = sc.Mp2_f * lp * fmaf((float)(kHalfPi - theta), i, (float)(theta * cos_t));
         P = (double)fminf(fmaxf(p, 0.0f), 1.0f);
         float a = atan2_fast((float)(dy - sc.sy), (float)(dx - sc.sx)) + (float)kHalfPi;   // in (-pi/2, 3pi/2]

@@ -138,8 +138,16 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 #endif
 
             if (mode == kModeRaster && !kF64 && rp.S == 1 && !rp.init_c) {
-                if (smem_grid) final_pass_fast<true>(rp, sm, gbest, p, grp, Hcur);
-                else final_pass_fast<false>(rp, sm, gbest, p, grp, Hcur);
+                const bool all_out = rp.out.rgb && rp.out.hit && rp.out.depth && rp.out.Y && rp.out.dop && rp.out.aop;
+                if (smem_grid) {
+                    // the common shapes get their own instantiations; everything else takes the general one
+                    if (!rp.sun_per_view && all_out) final_pass_fast<true, true, true>(rp, sm, gbest, p, grp, Hcur);
+                    else if (!rp.sun_per_view) final_pass_fast<true, true, false>(rp, sm, gbest, p, grp, Hcur);
+                    else final_pass_fast<true, false, false>(rp, sm, gbest, p, grp, Hcur);
+                } else {
+                    if (!rp.sun_per_view) final_pass_fast<false, true, false>(rp, sm, gbest, p, grp, Hcur);
+                    else final_pass_fast<false, false, false>(rp, sm, gbest, p, grp, Hcur);
+                }
                 t_phase[2] += clock64() - t4;
                 continue;
             }

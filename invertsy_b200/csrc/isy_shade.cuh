@@ -16,7 +16,9 @@ namespace isy {
 #endif
 constexpr int kSU = ISY_SHADE_U;      // headings per lane and trip in the final pass
 
-template <bool kSmem>
+// kOneSun: every view shares one sun, its constants are read from shared memory (a compile-time address space).
+// kAllOut: all six outputs were asked for (the usual call): no per-store null checks.
+template <bool kSmem, bool kOneSun, bool kAllOut>
 __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const unsigned int* gbest, int p, int grp,
                                 int Hcur) {
     const int R = rp.R, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -30,6 +32,9 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
     const float nanf_ = __int_as_float(0x7fc00000);
     const int nb = (R + 31) >> 5;
     int nch = min(Hcur, max(1, (2 * kWarps + nb - 1) / nb));
+#ifdef ISY_SHADE_NCH
+    nch = min(Hcur, ISY_SHADE_NCH);
+#endif
     const int hper = (Hcur + nch - 1) / nch;
     nch = (Hcur + hper - 1) / hper;
     for (int u = warp; u < nb * nch; u += kWarps) {
@@ -50,7 +55,11 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
 
         // kSU headings per trip: their sky evaluations are independent instruction streams (the pass is
         // bound by the latency of the fp64 chain, not by issue slots)
-        for (int hh0 = hc * hper; hh0 < hend; hh0 += kSU) {
+        // element offset of (view of heading hh0, this lane's ray) in the [view][ray] outputs; consecutive
+        // headings of a group are ngroups views apart, so it advances by a constant
+        const size_t ostride = (size_t)rp.ngroups * (size_t)R;
+        size_t off0 = ((size_t)p * rp.H + grp + (size_t)(hc * hper) * rp.ngroups) * (size_t)R + (size_t)r;
+        for (int hh0 = hc * hper; hh0 < hend; hh0 += kSU, off0 += kSU * ostride) {
             double Y[kSU], P[kSU], A[kSU];
             size_t view[kSU];
             unsigned int id[kSU];
@@ -64,7 +73,7 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
                 if (perez) {
                     const double hsn = sm.head_sin[hh], hcs = sm.head_cos[hh];
                     const double sy = t4v.z * hcs + t4v.w * hsn, cy = t4v.w * hcs - t4v.z * hsn;   // yaw_e + heading
-                    const SunConst& sc = rp.sun_per_view ? rp.sun[view[q]] : sm.sun0;   // one sun: shared memory
+                    const SunConst& sc = kOneSun ? sm.sun0 : rp.sun[view[q]];
                     sky_eval<false>(rp.sky, sc, t4v.y * cy, t4v.y * sy, -t4v.x, e_pitch + kHalfPi, f_theta, Y[q], P[q], A[q],
                                     false, sm.gtab);
                 } else if (uniform) {
@@ -90,18 +99,18 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
                     cr = __ldg(col + 0), cg = __ldg(col + 1), cb = __ldg(col + 2);
                 }
                 if (valid) {
-                    const size_t i = view[q] * (size_t)R + r;
                     // streaming stores: the views are written once and never read back by the kernel, so they
                     // should leave L2 before the slabs, the world and the eye tables do
-                    if (o_rgb) {
+                    const size_t i = off0 + q * ostride;
+                    if (kAllOut || o_rgb) {
                         float* qq = o_rgb + 3 * i;
                         __stcs(qq, cr), __stcs(qq + 1, cg), __stcs(qq + 2, cb);
                     }
-                    if (rp.out.hit) __stcs(rp.out.hit + i, hit);
-                    if (o_depth) __stcs(o_depth + i, depth);
-                    if (o_Y) __stcs(o_Y + i, (float)Y[q]);
-                    if (o_P) __stcs(o_P + i, (float)P[q]);
-                    if (o_A) __stcs(o_A + i, (float)A[q]);
+                    if (kAllOut || rp.out.hit) __stcs(rp.out.hit + i, hit);
+                    if (kAllOut || o_depth) __stcs(o_depth + i, depth);
+                    if (kAllOut || o_Y) __stcs(o_Y + i, (float)Y[q]);
+                    if (kAllOut || o_P) __stcs(o_P + i, (float)P[q]);
+                    if (kAllOut || o_A) __stcs(o_A + i, (float)A[q]);
                 }
             }
         }
