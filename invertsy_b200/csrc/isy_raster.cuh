@@ -39,17 +39,21 @@ __device__ __forceinline__ bool nearer(const Entry* tile, double d, int tri, uns
     return d < dc || (d == dc && (tri < o.tri || (tri == o.tri && e < c)));
 }
 
-// best[idx] = nearer(e, best[idx]) ? e : best[idx], atomically (CAS on the 32-bit word holding the u16)
-__device__ __forceinline__ void post_copy_u16(unsigned short* best, unsigned int idx, const Entry* tile, double d, int tri,
+// best[idx] = nearer(e, best[idx]) ? e : best[idx], atomically (CAS on the 32-bit word holding the u16).
+// best_s is the SHARED-space address of best[0]: explicit ld.shared / atom.shared keep the address
+// arithmetic to two instructions (a generic pointer makes the compiler rebuild the window base every time).
+__device__ __forceinline__ void post_copy_u16(unsigned int best_s, unsigned int idx, const Entry* tile, double d, int tri,
                                               unsigned int e) {
-    unsigned int* word = reinterpret_cast<unsigned int*>(best) + (idx >> 1);
+    const unsigned int addr = best_s + ((idx >> 1) << 2);
     const bool hi = idx & 1u;
-    unsigned int old = *reinterpret_cast<volatile unsigned int*>(word);
+    unsigned int old;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(old) : "r"(addr) : "memory");
     for (;;) {
         const unsigned int cur = hi ? (old >> 16) : (old & 0xffffu);
         if (cur != kNoCopy && !nearer(tile, d, tri, e, cur)) return;
         const unsigned int nw = hi ? ((old & 0xffffu) | (e << 16)) : ((old & 0xffff0000u) | e);
-        const unsigned int prev = atomicCAS(word, old, nw);
+        unsigned int prev;
+        asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(prev) : "r"(addr), "r"(old), "r"(nw) : "memory");
         if (prev == old) return;
         old = prev;
     }
@@ -115,6 +119,7 @@ __device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& s
     const float2* gsorted = reinterpret_cast<const float2*>(rp.grid_sorted);
     const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
     const float uh0 = sm.ras.uni[0], udelta = sm.ras.uni[1], uinv = sm.ras.uni[2];
+    const unsigned int best_s = (unsigned int)__cvta_generic_to_shared(sm.ras.best);
     float2 py[RU];
     int k[RU], ks[RU];    // window cursor; sorted slot of the heading under the cursor
     float upper[RU];
@@ -197,7 +202,7 @@ __device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& s
             }
             // rows of best[] are SORTED heading slots
             if (in) {
-                if (kSmem) post_copy_u16(sm.ras.best, (unsigned)ks[u] * R + j, sm.tile, dist, ent.tri, e);
+                if (kSmem) post_copy_u16(best_s, (unsigned)ks[u] * R + j, sm.tile, dist, ent.tri, e);
                 else post_copy_u32(&gbest[(size_t)ks[u] * R + j], sm.tile, dist, ent.tri, e);
             }
             if (kUniform) {
@@ -269,6 +274,7 @@ __device__ __forceinline__ void raster_cell(const RenderParams& rp, SmemLayout& 
     const int R = rp.R;
     const float2* gsorted = reinterpret_cast<const float2*>(rp.grid_sorted);
     const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
+    const unsigned int best_s = (unsigned int)__cvta_generic_to_shared(sm.ras.best);
     const unsigned i0 = kSmem ? sm.ras.cell_start[cell] : __ldg(rp.cells_start + cell);
     const unsigned i1 = kSmem ? sm.ras.cell_start[cell + 1] : __ldg(rp.cells_start + cell + 1);
     for (unsigned i = i0; i < i1; ++i) {
@@ -293,7 +299,7 @@ __device__ __forceinline__ void raster_cell(const RenderParams& rp, SmemLayout& 
             if (!in && m >= -kEdgeEps) in = inside_exact(exacts[e], rp.eye_py[2 * (size_t)ray], yg);
         }
         if (in) {
-            if (kSmem) post_copy_u16(sm.ras.best, (unsigned)hs * R + j, sm.tile, dist, ent.tri, e);
+            if (kSmem) post_copy_u16(best_s, (unsigned)hs * R + j, sm.tile, dist, ent.tri, e);
             else post_copy_u32(&gbest[(size_t)hs * R + j], sm.tile, dist, ent.tri, e);
         }
     }
