@@ -54,6 +54,7 @@ struct SmemLayout {
     SunConst sun0;                    // sun constants when all views share one sun (copied once per CTA)
     unsigned short order[kMaxE];      // rasterisation order: tall copies from the front, the rest from the back
     int order_n[2];                   // ... and how many of each
+    unsigned int jrange[kMaxE];       // pitch run of each copy in the eye's sorted rays: first | (end << 16) (smem-grid eyes)
     union {
         SmemBins bins;
         SmemRaster ras;

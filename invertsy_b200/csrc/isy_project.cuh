@@ -31,6 +31,9 @@ __device__ __forceinline__ int float_key(float f) {   // order-preserving int ke
 }
 __device__ __forceinline__ float key_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
+// kRuns: the eye's pitch look-up table is resident in shared memory (small eyes, yaw-only views): the copy's run
+// of pitch-sorted rays is worked out here, once per copy by one thread, instead of by every warp that rasterises it
+template <bool kRuns>
 __device__ __forceinline__ void emit_copy(const double th[3], const double ph[3], double dist, int t, int slot,
                                           Entry* entries, Exact* exacts, SmemLayout& sm, int* s_band) {
     Entry e;
@@ -50,6 +53,12 @@ __device__ __forceinline__ void emit_copy(const double th[3], const double ph[3]
         const bool proper = (x.o[0] > 0 && x.o[1] < 0 && x.o[2] > 0) || (x.o[0] < 0 && x.o[1] > 0 && x.o[2] < 0);
         if (!proper) tlo = -4.f, thi = 4.f, plo = -8.f, phi = 8.f;
         sm.bbox[slot] = make_float4(tlo, thi, plo, phi);
+        if (kRuns) {
+            // run of pitch-sorted rays that covers [tlo, thi] (a few extra rays at both ends)
+            const int s0 = min(max((int)floorf((tlo + (float)kHalfPi) * (kPitchLut / (float)kPi)), 0), kPitchLut - 1);
+            const int s1 = min(max((int)floorf((thi + (float)kHalfPi) * (kPitchLut / (float)kPi)) + 2, 0), kPitchLut);
+            sm.jrange[slot] = sm.ras.plut[s0] | (sm.ras.plut[s1] << 16);
+        }
         // longest-first order for the rasteriser's dynamic queue: a copy's cost grows with its pitch run
         if (thi - tlo > kTallCopy) sm.order[atomicAdd(&sm.order_n[0], 1)] = (unsigned short)slot;
         else sm.order[kMaxE - 1 - atomicAdd(&sm.order_n[1], 1)] = (unsigned short)slot;
@@ -58,6 +67,7 @@ __device__ __forceinline__ void emit_copy(const double th[3], const double ph[3]
     }
 }
 
+template <bool kRuns>
 __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* entries, Exact* exacts,
                                 SmemLayout& sm, int* s_count, int* s_nent, int* s_band, long long* t_mid = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31;
@@ -226,10 +236,10 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
                     p1[k] = ph[k] < 0 ? ph[k] + kTwoPi : ph[k];                           // :118
                     p2[k] = ph[k] > 0 ? ph[k] - kTwoPi : ph[k];                           // :119
                 }
-                emit_copy(th, p1, dist, t, slot, entries, exacts, sm, s_band);
-                emit_copy(th, p2, dist, t, slot + 1, entries, exacts, sm, s_band);
+                emit_copy<kRuns>(th, p1, dist, t, slot, entries, exacts, sm, s_band);
+                emit_copy<kRuns>(th, p2, dist, t, slot + 1, entries, exacts, sm, s_band);
             } else {
-                emit_copy(th, ph, dist, t, slot, entries, exacts, sm, s_band);
+                emit_copy<kRuns>(th, ph, dist, t, slot, entries, exacts, sm, s_band);
             }
         }
     }

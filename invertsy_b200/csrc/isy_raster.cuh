@@ -243,10 +243,15 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
         const Entry ent = sm.tile[e];
         const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
         // run of pitch-sorted rays that covers [bb.x, bb.y] (a few extra rays at both ends)
-        const int s0 = min(max((int)floorf((bb.x + (float)kHalfPi) * (kPitchLut / (float)kPi)), 0), kPitchLut - 1);
-        const int s1 = min(max((int)floorf((bb.y + (float)kHalfPi) * (kPitchLut / (float)kPi)) + 2, 0), kPitchLut);
-        const unsigned jbeg = kSmem ? sm.ras.plut[s0] : __ldg(rp.grid_plut + s0);
-        const unsigned jend = kSmem ? sm.ras.plut[s1] : __ldg(rp.grid_plut + s1);
+        unsigned jbeg, jend;
+        if (kSmem) {   // worked out when the copy was projected
+            const unsigned int jr = sm.jrange[e];
+            jbeg = jr & 0xffffu, jend = jr >> 16;
+        } else {
+            const int s0 = min(max((int)floorf((bb.x + (float)kHalfPi) * (kPitchLut / (float)kPi)), 0), kPitchLut - 1);
+            const int s1 = min(max((int)floorf((bb.y + (float)kHalfPi) * (kPitchLut / (float)kPi)) + 2, 0), kPitchLut);
+            jbeg = __ldg(rp.grid_plut + s0), jend = __ldg(rp.grid_plut + s1);
+        }
         // two rays per lane while more than a warp's worth is left, one ray per lane for the tail
         unsigned jb = jbeg;
         for (; jb + 32 * (kRU - 1) < jend; jb += 32 * kRU) {   // warp-uniform trip count

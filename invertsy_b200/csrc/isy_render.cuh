@@ -23,11 +23,18 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
     const bool yaw_only = !rp.vquat;
     const bool raster_ok = yaw_only && rp.grid_sorted && !(rp.flags & ISY_FLAG_BRUTE_FORCE);
     const bool smem_grid = raster_ok && !gbest;
-    bool grid_loaded = false;
 
     if (perez) {
         for (int i = tid; i < 2 * (kGTab + 1); i += kThreads) sm.gtab[i] = rp.sky_gtab[i];
         if (tid == 0) sm.sun0 = rp.sun[0];
+    }
+    if (smem_grid) {   // the eye's static tables: nothing else uses this memory in a yaw-only launch
+        for (int i = tid; i <= kPitchLut; i += kThreads) sm.ras.plut[i] = rp.grid_plut[i];
+        for (int i = tid; i < rp.R; i += kThreads) {
+            sm.ras.sorted[i] = reinterpret_cast<const float2*>(rp.grid_sorted)[i];
+            sm.ras.cell_list[i] = (unsigned short)rp.cells_list[i];
+        }
+        for (int i = tid; i <= rp.cells_rows * rp.cells_cols; i += kThreads) sm.ras.cell_start[i] = rp.cells_start[i];
     }
     long long t_phase[4] = {0, 0, 0, 0};   // project, accel (bins / raster), final ray pass, positions
 #ifdef ISY_PHASE_DETAIL
@@ -53,10 +60,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 #else
         long long t_sub[3] = {t0, t0, t0};   // end of the cull; (mode 2) position loaded; candidate rows listed
 #endif
-        const int E = cull_and_project(rp, p, vis, entries, exacts, sm, &s_count, &s_nent, s_band, t_sub);
+        const int E = smem_grid ? cull_and_project<true>(rp, p, vis, entries, exacts, sm, &s_count, &s_nent, s_band, t_sub)
+                                : cull_and_project<false>(rp, p, vis, entries, exacts, sm, &s_count, &s_nent, s_band, t_sub);
         const long long g_detail_t = t_sub[0];
 #else
-        const int E = cull_and_project(rp, p, vis, entries, exacts, sm, &s_count, &s_nent, s_band);
+        const int E = smem_grid ? cull_and_project<true>(rp, p, vis, entries, exacts, sm, &s_count, &s_nent, s_band)
+                                : cull_and_project<false>(rp, p, vis, entries, exacts, sm, &s_count, &s_nent, s_band);
 #endif
         long long t1 = clock64();
 #ifdef ISY_PHASE_DETAIL
@@ -73,18 +82,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
         if (!(rp.flags & ISY_FLAG_BRUTE_FORCE) && E <= kMaxE) {
             if (raster_ok) {
                 mode = kModeRaster;
-                if (smem_grid && !grid_loaded) {   // the bins path shares this memory: (re)load when needed
-                    for (int i = tid; i <= kPitchLut; i += kThreads) sm.ras.plut[i] = rp.grid_plut[i];
-                    for (int i = tid; i < rp.R; i += kThreads) {
-                        sm.ras.sorted[i] = reinterpret_cast<const float2*>(rp.grid_sorted)[i];
-                        sm.ras.cell_list[i] = (unsigned short)rp.cells_list[i];
-                    }
-                    for (int i = tid; i <= rp.cells_rows * rp.cells_cols; i += kThreads) sm.ras.cell_start[i] = rp.cells_start[i];
-                    grid_loaded = true;
-                }
             } else if (build_bins(sm, grid, E, s_band, s_warp)) {
                 mode = kModeBins;
-                grid_loaded = false;
             }
         }
         long long t2 = clock64();
