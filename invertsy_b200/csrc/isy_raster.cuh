@@ -252,13 +252,13 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
             const int s1 = min(max((int)floorf((bb.y + (float)kHalfPi) * (kPitchLut / (float)kPi)) + 2, 0), kPitchLut);
             jbeg = __ldg(rp.grid_plut + s0), jend = __ldg(rp.grid_plut + s1);
         }
-        // two rays per lane while more than a warp's worth is left, one ray per lane for the tail
+        // kRU rays per lane while that many warps' worth are left, then one ray per lane for the tail
         unsigned jb = jbeg;
-        for (; jb + 32 * (kRU - 1) < jend; jb += 32 * kRU) {   // warp-uniform trip count
+        for (; jb + 32 * (kRU - 1) < jend; jb += 32 * kRU) {   // warp-uniform trip counts
             __syncwarp();                                       // keep the lanes converged across iterations
             walk_chunk<kSmem, kUniform, kRU>(rp, sm, gbest, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur);
         }
-        if (jb < jend) {
+        for (; jb < jend; jb += 32) {
             __syncwarp();
             walk_chunk<kSmem, kUniform, 1>(rp, sm, gbest, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur);
         }
