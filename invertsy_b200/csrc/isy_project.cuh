@@ -71,6 +71,10 @@ template <bool kRuns>
 __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* entries, Exact* exacts,
                                 SmemLayout& sm, int* s_count, int* s_nent, int* s_band, long long* t_mid = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31;
+    if (rp.T == 0) {   // no world (sky-only calls): nothing to cull
+        if (tid == 0) s_band[0] = float_key(CUDART_INF_F), s_band[1] = float_key(-CUDART_INF_F);
+        return 0;
+    }
     const double px = rp.pos[3 * p + 0], py = rp.pos[3 * p + 1], pz = rp.pos[3 * p + 2];
     const double h = rp.horizon;
     const double h2_max = rp.horizon_sq_max;     // sqrt_rn(s) <= horizon  <=>  s <= h2_max (set by the host)

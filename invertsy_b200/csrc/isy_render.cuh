@@ -138,14 +138,18 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 
             if (mode == kModeRaster && !kF64 && rp.S == 1 && !rp.init_c) {
                 const bool all_out = rp.out.rgb && rp.out.hit && rp.out.depth && rp.out.Y && rp.out.dop && rp.out.aop;
-                if (smem_grid) {
-                    // the common shapes get their own instantiations; everything else takes the general one
-                    if (!rp.sun_per_view && all_out) final_pass_fast<true, true, true>(rp, sm, gbest, p, grp, Hcur);
-                    else if (!rp.sun_per_view) final_pass_fast<true, true, false>(rp, sm, gbest, p, grp, Hcur);
-                    else final_pass_fast<true, false, false>(rp, sm, gbest, p, grp, Hcur);
+                // the common shapes get their own instantiations; everything else takes the general ones
+                if (smem_grid && Hcur > 1 && !rp.sun_per_view && all_out) {   // scans of a small eye, everything asked for
+                    final_pass_fast<true, true, true, kShadeU>(rp, sm, gbest, p, grp, Hcur);
+                } else if (Hcur == 1) {   // single views, sun sweeps: one heading per trip
+                    if (smem_grid) final_pass_fast<true, false, false, 1>(rp, sm, gbest, p, grp, Hcur);
+                    else final_pass_fast<false, false, false, 1>(rp, sm, gbest, p, grp, Hcur);
+                } else if (smem_grid) {
+                    if (!rp.sun_per_view) final_pass_fast<true, true, false, kShadeU>(rp, sm, gbest, p, grp, Hcur);
+                    else final_pass_fast<true, false, false, kShadeU>(rp, sm, gbest, p, grp, Hcur);
                 } else {
-                    if (!rp.sun_per_view) final_pass_fast<false, true, false>(rp, sm, gbest, p, grp, Hcur);
-                    else final_pass_fast<false, false, false>(rp, sm, gbest, p, grp, Hcur);
+                    if (!rp.sun_per_view) final_pass_fast<false, true, false, kShadeU>(rp, sm, gbest, p, grp, Hcur);
+                    else final_pass_fast<false, false, false, kShadeU>(rp, sm, gbest, p, grp, Hcur);
                 }
                 t_phase[2] += clock64() - t4;
                 continue;

@@ -14,11 +14,13 @@ namespace isy {
 #ifndef ISY_SHADE_U
 #define ISY_SHADE_U 2
 #endif
-constexpr int kSU = ISY_SHADE_U;      // headings per lane and trip in the final pass
+constexpr int kShadeU = ISY_SHADE_U;  // headings per lane and trip in the final pass (positions with several headings)
 
 // kOneSun: every view shares one sun, its constants are read from shared memory (a compile-time address space).
 // kAllOut: all six outputs were asked for (the usual call): no per-store null checks.
-template <bool kSmem, bool kOneSun, bool kAllOut>
+// kSU: headings per lane and trip (2 hides the latency of the fp64 chain; 1 for single-heading positions, where a
+// second slot would only repeat the first)
+template <bool kSmem, bool kOneSun, bool kAllOut, int kSU>
 __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const unsigned int* gbest, int p, int grp,
                                 int Hcur) {
     const int R = rp.R, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -73,7 +75,7 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
                 if (perez) {
                     const double hsn = sm.head_sin[hh], hcs = sm.head_cos[hh];
                     const double sy = t4v.z * hcs + t4v.w * hsn, cy = t4v.w * hcs - t4v.z * hsn;   // yaw_e + heading
-                    const SunConst& sc = kOneSun ? sm.sun0 : rp.sun[view[q]];
+                    const SunConst& sc = kOneSun ? sm.sun0 : rp.sun[rp.sun_per_view ? view[q] : 0];
                     sky_eval<false>(rp.sky, sc, t4v.y * cy, t4v.y * sy, -t4v.x, e_pitch + kHalfPi, f_theta, Y[q], P[q], A[q],
                                     false, sm.gtab);
                 } else if (uniform) {
