@@ -162,8 +162,7 @@ __device__ __forceinline__ void write_view(const RenderParams& rp, size_t b, int
     if (S > 1) {
         // weighted cone average over the S consecutive lanes of one ommatidium
         float w = valid ? rp.eye_w[r] : 0.f;
-        double sA, cA;
-        sincos(o.A, &sA, &cA);
+        const double sA = o.sA, cA = o.cA;
         double wr = w * o.r, wg = w * o.g, wb = w * o.b;
         double wY = w * o.Y, wP = w * o.P, wS = w * sA, wC = w * cA;
         for (int off = S >> 1; off > 0; off >>= 1) {
@@ -176,8 +175,8 @@ __device__ __forceinline__ void write_view(const RenderParams& rp, size_t b, int
             wC += __shfl_xor_sync(0xffffffffu, wC, off);
         }
         o.r = wr, o.g = wg, o.b = wb, o.Y = wY, o.P = wP;
-        o.A = atan2(wS, wC);
         if (!valid || (r % S) != 0) return;
+        o.A = kF64 ? atan2(wS, wC) : (double)atan2f((float)wS, (float)wC);   // circular mean of the samples' angles
         r /= S;
     } else if (!valid) {
         return;

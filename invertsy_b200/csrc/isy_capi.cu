@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cmath>
 #include <cstring>
@@ -233,6 +234,7 @@ int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int3
         int gp = 4;
         while (gp < 512 && (size_t)gp * gp < R) gp *= 2;
         if ((size_t)gp * 2 * gp > (size_t)kCellsSmem && R <= (size_t)kGridRaysSmem) gp = 32;   // shared-memory budget
+        if (const char* ov = std::getenv("ISY_CELLS_GP")) gp = std::max(4, std::atoi(ov));      // (tuning experiments)
         e->cells_rows = gp, e->cells_cols = 2 * gp;
         const size_t ncell = (size_t)gp * 2 * gp;
         std::vector<unsigned int> cstart(ncell + 1, 0), cell_of(R), clist(R);

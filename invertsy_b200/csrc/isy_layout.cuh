@@ -24,6 +24,7 @@ constexpr int kGridRaysSmem = 1280;   // eyes up to this many rays keep their pi
 constexpr int kPitchLut = 1024;       // slots of the pitch -> first sorted ray look-up table
 constexpr int kHeadLut = 1024;        // slots of the azimuth -> first sorted heading look-up table
 constexpr int kCellsSmem = 2048;      // cells of the eye's (pitch, yaw) ray grid kept in shared memory
+constexpr int kMaxGiants = 254;       // (copy, heading) pairs the cell walk can set aside per group
 constexpr int kSmallH = 4;            // up to this many headings per group the rasteriser walks the ray grid
 
 struct SmemBins {
@@ -54,6 +55,8 @@ struct SmemLayout {
     SunConst sun0;                    // sun constants when all views share one sun (copied once per CTA)
     unsigned short order[kMaxE];      // rasterisation order: tall copies from the front, the rest from the back
     int order_n[2];                   // ... and how many of each
+    unsigned short giants[kMaxGiants]; // cell walk: (copy, heading) pairs set aside for the whole CTA
+    int n_giants;
     unsigned int jrange[kMaxE];       // pitch run of each copy in the eye's sorted rays: first | (end << 16) (smem-grid eyes)
     union {
         SmemBins bins;
@@ -65,6 +68,7 @@ static_assert(sizeof(SmemLayout) <= 192 * 1024, "leave some of the 228 KB for L1
 struct RayOut {
     double r, g, b;
     double Y, P, A;
+    double sA, cA;   // sin / cos of A for the cone average (S > 1), formed without the angle itself
 };
 
 template <typename T>

@@ -271,18 +271,16 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
 // cells of the eye's static (pitch, yaw) ray grid under the copy's bounding box, shifted by the
 // heading.  Lanes hold different pairs; the work per position is a few thousand warp instructions.
 // ------------------------------------------------------------------------------------------
-// tests the rays stored in one cell of the eye's ray grid against one projected copy at one heading
+// tests rays [i0, i1) of the grid's ray list (every `step`-th from i0 + first) against one projected copy at one heading
 template <bool kSmem>
-__device__ __forceinline__ void raster_cell(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest,
-                                            const Exact* exacts, int cell, const Entry& ent, double dist, int e, int hh,
-                                            int hs, float hf) {
+__device__ __forceinline__ void raster_list(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest,
+                                            const Exact* exacts, unsigned i0, unsigned i1, unsigned first, unsigned step,
+                                            const Entry& ent, double dist, int e, int hh, int hs, float hf) {
     const int R = rp.R;
     const float2* gsorted = reinterpret_cast<const float2*>(rp.grid_sorted);
     const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
     const unsigned int best_s = (unsigned int)__cvta_generic_to_shared(sm.ras.best);
-    const unsigned i0 = kSmem ? sm.ras.cell_start[cell] : __ldg(rp.cells_start + cell);
-    const unsigned i1 = kSmem ? sm.ras.cell_start[cell + 1] : __ldg(rp.cells_start + cell + 1);
-    for (unsigned i = i0; i < i1; ++i) {
+    for (unsigned i = i0 + first; i < i1; i += step) {
         const unsigned j = kSmem ? (unsigned)sm.ras.cell_list[i] : __ldg(rp.cells_list + i);
         const float2 py = kSmem ? sm.ras.sorted[j] : __ldg(gsorted + j);
         float fy = py.y + hf;                                  // both in (-pi, pi]: one shift wraps
@@ -310,14 +308,109 @@ __device__ __forceinline__ void raster_cell(const RenderParams& rp, SmemLayout& 
     }
 }
 
+// the cells of one grid row under a pair's window are ncols consecutive columns from c0 (modulo the circle):
+// one or two contiguous ranges of the grid's ray list
+template <bool kSmem>
+__device__ __forceinline__ void raster_row(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest,
+                                           const Exact* exacts, int row, int c0, int ncols, unsigned first, unsigned step,
+                                           const Entry& ent, double dist, int e, int hh, int hs, float hf) {
+    const int Gy = rp.cells_cols;
+    const int n1 = min(ncols, Gy - c0);            // columns before the wrap
+    const int cellA = row * Gy + c0;
+    const unsigned a0 = kSmem ? sm.ras.cell_start[cellA] : __ldg(rp.cells_start + cellA);
+    const unsigned a1 = kSmem ? sm.ras.cell_start[cellA + n1] : __ldg(rp.cells_start + cellA + n1);
+    raster_list<kSmem>(rp, sm, gbest, exacts, a0, a1, first, step, ent, dist, e, hh, hs, hf);
+    if (n1 < ncols) {                              // the window wraps: columns 0 .. ncols - n1 - 1 of the same row
+        const int cellB = row * Gy;
+        const unsigned b0 = kSmem ? sm.ras.cell_start[cellB] : __ldg(rp.cells_start + cellB);
+        const unsigned b1 = kSmem ? sm.ras.cell_start[cellB + ncols - n1] : __ldg(rp.cells_start + cellB + ncols - n1);
+        raster_list<kSmem>(rp, sm, gbest, exacts, b0, b1, first, step, ent, dist, e, hh, hs, hf);
+    }
+}
+
+// The same for a whole warp, all rows of the window at once: lanes first fetch the list ranges of 32 (row, half)
+// units, a prefix sum lines their rays up, and every lane then takes every 32nd ray of the concatenation -- the
+// lanes stay busy whether a row holds one ray (small eyes) or hundreds (dense eyes).  Units are taken from
+// ub0 in steps of ustep (one warp: 0, 32; all warps of the CTA on one pair: 32 * warp, 32 * kWarps).
+template <bool kSmem>
+__device__ __forceinline__ void raster_rows_flat(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest,
+                                                 const Exact* exacts, int r0, int nrows, int c0, int ncols, int ub0, int ustep,
+                                                 const Entry& ent, double dist, int e, int hh, int hs, float hf) {
+    const int lane = threadIdx.x & 31, Gy = rp.cells_cols;
+    const int n1 = min(ncols, Gy - c0);            // columns before the wrap
+    const bool wraps = n1 < ncols;
+    const int nunits = wraps ? 2 * nrows : nrows;
+    for (int ub = ub0; ub < nunits; ub += ustep) {
+        const int u = ub + lane;
+        unsigned a0 = 0, a1 = 0;
+        if (u < nunits) {
+            const int row = r0 + (wraps ? (u >> 1) : u);
+            const bool second = wraps && (u & 1);
+            const int cell = row * Gy + (second ? 0 : c0), n = second ? ncols - n1 : n1;
+            a0 = kSmem ? sm.ras.cell_start[cell] : __ldg(rp.cells_start + cell);
+            a1 = kSmem ? sm.ras.cell_start[cell + n] : __ldg(rp.cells_start + cell + n);
+        }
+        const unsigned len = a1 - a0;
+        unsigned inc = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += v;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, inc, 31), exc = inc - len;
+        for (unsigned tb = 0; tb < total; tb += 32) {          // warp-uniform trip count
+            const unsigned t = tb + lane;
+            int k = 0;                                         // the unit that holds ray t: smallest k with inc_k > t
+#pragma unroll
+            for (int b = 16; b > 0; b >>= 1) {
+                const unsigned v = __shfl_sync(0xffffffffu, inc, k + b - 1);
+                if (v <= t) k += b;
+            }
+            k = min(k, 31);
+            const unsigned ek = __shfl_sync(0xffffffffu, exc, k), ak = __shfl_sync(0xffffffffu, a0, k);
+            if (t < total) {
+                const unsigned i = ak + (t - ek);
+                raster_list<kSmem>(rp, sm, gbest, exacts, i, i + 1, 0, 1, ent, dist, e, hh, hs, hf);
+            }
+        }
+    }
+}
+
+// window of pair (copy e, heading hh) in the eye's static ray grid: rows [r0, r0 + nrows), columns ncols from c0
+__device__ __forceinline__ void pair_window(const RenderParams& rp, const SmemLayout& sm, int e, int hh, int& r0, int& nrows,
+                                            int& c0, int& ncols) {
+    const int Gp = rp.cells_rows, Gy = rp.cells_cols;
+    const float pi_f = (float)kPi;
+    const float inv_dp = (float)Gp / pi_f, inv_dy = (float)Gy / (float)kTwoPi;
+    r0 = 0, nrows = 0, c0 = 0, ncols = 0;
+    const float4 bb = sm.bbox[e];
+    const float glo = fmaxf(bb.z, -pi_f - kBinMargin) - kBinMargin, ghi = fminf(bb.w, pi_f + kBinMargin) + kBinMargin;
+    if (glo > ghi) return;
+    const float hf = (float)sm.head_val[hh];
+    // eye-frame azimuth window [glo - h, ghi - h], as a run of grid columns modulo the circle
+    const int c_first = (int)floorf((glo - hf + pi_f) * inv_dy);
+    ncols = min((int)floorf((ghi - hf + pi_f) * inv_dy) - c_first + 1, Gy);
+    c0 = c_first % Gy;
+    if (c0 < 0) c0 += Gy;
+    r0 = max((int)floorf((bb.x + (float)kHalfPi) * inv_dp), 0);
+    nrows = max(min((int)floorf((bb.y + (float)kHalfPi) * inv_dp), Gp - 1) - r0 + 1, 0);
+}
+
+// Work sharing: pairs covering a few cells take one lane each; larger ones are walked by their warp, row by row
+// (the rays of a row's window are contiguous in the grid's list); the few giants (a blade right in front of the
+// eye, or a degenerate copy that may contain any ray) are set aside and walked by the whole CTA afterwards, so
+// that no warp is left alone with them.
 template <bool kSmem>
 __device__ void raster_cells(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest, const Exact* exacts, int E,
                              int Hcur, int* s_next) {
-    const int lane = threadIdx.x & 31, Gp = rp.cells_rows, Gy = rp.cells_cols;
-    const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
-    const float inv_dp = (float)Gp / pi_f, inv_dy = (float)Gy / twopi_f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int items = E * Hcur;
-    constexpr int kBigItem = 12;    // pairs that cover more cells than this are walked by the whole warp
+    constexpr int kBigItem = 12;      // cells: above this the warp shares the pair
+    constexpr int kGiantItem = 1024;  // cells: above this the CTA shares the pair
+    unsigned short* giants = sm.giants;
+    int* n_giant = &sm.n_giants;
+    if (threadIdx.x == 0) *n_giant = 0;
+    __syncthreads();
     for (;;) {
         int base = 0;
         if (lane == 0) base = smem_atomic_add(s_next, 32);
@@ -327,54 +420,52 @@ __device__ void raster_cells(const RenderParams& rp, SmemLayout& sm, unsigned in
         int e = 0, hh = 0, r0 = 0, nrows = 0, c0 = 0, ncols = 0;
         if (item < items) {
             e = item / Hcur, hh = item - e * Hcur;
-            const float4 bb = sm.bbox[e];
-            const float glo = fmaxf(bb.z, -pi_f - kBinMargin) - kBinMargin, ghi = fminf(bb.w, pi_f + kBinMargin) + kBinMargin;
-            if (glo <= ghi) {
-                const float hf = (float)sm.head_val[hh];
-                // eye-frame azimuth window [glo - h, ghi - h], as a run of grid columns modulo the circle
-                const int c_first = (int)floorf((glo - hf + pi_f) * inv_dy);
-                ncols = min((int)floorf((ghi - hf + pi_f) * inv_dy) - c_first + 1, Gy);
-                c0 = c_first % Gy;
-                if (c0 < 0) c0 += Gy;
-                r0 = max((int)floorf((bb.x + (float)kHalfPi) * inv_dp), 0);
-                nrows = max(min((int)floorf((bb.y + (float)kHalfPi) * inv_dp), Gp - 1) - r0 + 1, 0);
-            }
+            pair_window(rp, sm, e, hh, r0, nrows, c0, ncols);
         }
-        const int ncell = nrows * ncols;
+        int ncell = nrows * ncols;
+        if (ncell > kGiantItem && item < 65536) {      // set aside (if the list is full the warp keeps it)
+            const int slot = smem_atomic_add(n_giant, 1);
+            if (slot < kMaxGiants) giants[slot] = (unsigned short)item, ncell = 0;
+        }
         // small pairs: one lane each
         if (ncell > 0 && ncell <= kBigItem) {
             const Entry ent = sm.tile[e];
             const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
             const float hf = (float)sm.head_val[hh];
             const int hs = sm.ras.hinv[hh];
-            for (int q = 0; q < ncell; ++q) {
-                const int row = r0 + q / ncols;
-                int c = c0 + q % ncols;
-                if (c >= Gy) c -= Gy;
-                raster_cell<kSmem>(rp, sm, gbest, exacts, row * Gy + c, ent, dist, e, hh, hs, hf);
-            }
+            for (int row = r0; row < r0 + nrows; ++row)
+                raster_row<kSmem>(rp, sm, gbest, exacts, row, c0, ncols, 0, 1, ent, dist, e, hh, hs, hf);
         }
-        // large pairs (a blade right in front of the eye): the warp shares their cells
+        // large pairs: the warp shares their rows
         unsigned int big = __ballot_sync(0xffffffffu, ncell > kBigItem);
         while (big) {
             const int src = __ffs(big) - 1;
             big &= big - 1;
             const int be = __shfl_sync(0xffffffffu, e, src), bh = __shfl_sync(0xffffffffu, hh, src);
-            const int br0 = __shfl_sync(0xffffffffu, r0, src), bc0 = __shfl_sync(0xffffffffu, c0, src);
-            const int bnc = __shfl_sync(0xffffffffu, ncols, src), bn = __shfl_sync(0xffffffffu, ncell, src);
+            const int br0 = __shfl_sync(0xffffffffu, r0, src), bnr = __shfl_sync(0xffffffffu, nrows, src);
+            const int bc0 = __shfl_sync(0xffffffffu, c0, src), bnc = __shfl_sync(0xffffffffu, ncols, src);
             const Entry ent = sm.tile[be];
             const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
             const float hf = (float)sm.head_val[bh];
             const int hs = sm.ras.hinv[bh];
-            for (int q = lane; q < bn; q += 32) {
-                const int row = br0 + q / bnc;
-                int c = bc0 + q % bnc;
-                if (c >= Gy) c -= Gy;
-                raster_cell<kSmem>(rp, sm, gbest, exacts, row * Gy + c, ent, dist, be, bh, hs, hf);
-            }
+            raster_rows_flat<kSmem>(rp, sm, gbest, exacts, br0, bnr, bc0, bnc, 0, 32, ent, dist, be, bh, hs, hf);
             __syncwarp();
         }
         __syncwarp();
+    }
+    __syncthreads();
+    // giants: batches of 32 rows dealt to the warps
+    const int ng = min(*n_giant, kMaxGiants);
+    for (int g = 0; g < ng; ++g) {
+        const int item = giants[g];
+        const int e = item / Hcur, hh = item - e * Hcur;
+        int r0, nrows, c0, ncols;
+        pair_window(rp, sm, e, hh, r0, nrows, c0, ncols);
+        const Entry ent = sm.tile[e];
+        const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
+        const float hf = (float)sm.head_val[hh];
+        const int hs = sm.ras.hinv[hh];
+        raster_rows_flat<kSmem>(rp, sm, gbest, exacts, r0, nrows, c0, ncols, 32 * warp, 32 * kWarps, ent, dist, e, hh, hs, hf);
     }
 }
 

@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                 } else if (smem_grid) {
                     if (uniform) raster_copies<true, true>(rp, sm, gbest, exacts, E, Hcur, &s_count);
                     else raster_copies<true, false>(rp, sm, gbest, exacts, E, Hcur, &s_count);
+                } else if (Hcur <= kSmallH) {
+                    raster_cells<false>(rp, sm, gbest, exacts, E, Hcur, &s_count);
                 } else {
                     if (uniform) raster_copies<false, true>(rp, sm, gbest, exacts, E, Hcur, &s_count);
                     else raster_copies<false, false>(rp, sm, gbest, exacts, E, Hcur, &s_count);
@@ -239,10 +241,17 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                     }
 
                     RayOut o;
-                    o.Y = 0, o.P = 0, o.A = CUDART_NAN;
+                    o.Y = 0, o.P = 0, o.A = CUDART_NAN, o.sA = CUDART_NAN, o.cA = CUDART_NAN;
                     if (perez) {
                         const SunConst sc = rp.sun[rp.sun_per_view ? b : 0];
                         sky_eval<kF64>(rp.sky, sc, dx, dy, dz, ray.pitch + kHalfPi, f_theta, o.Y, o.P, o.A, false, sm.gtab);
+                        if (rp.S > 1) {
+                            // A = atan2(dy - sy, dx - sx) + pi/2 (sky.py:323)  =>  (sin A, cos A) = (X, -Y) / |(X, Y)|
+                            const double X = dx - sc.sx, Yd = dy - sc.sy, h2 = X * X + Yd * Yd;
+                            const double ih = h2 > 0.0 ? rsqrt(h2) : 0.0;
+                            o.sA = h2 > 0.0 ? X * ih : 1.0;        // atan2(0, 0) = 0 -> A = pi/2
+                            o.cA = -Yd * ih;
+                        }
                     } else if (want_sky) {
                         o.Y = rp.sky.luminance;   // UniformSky: y = luminance, p = 0, a = nan (sky.py:77-79)
                     }
