@@ -200,10 +200,16 @@ int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int3
             float pitch, yaw;
             int32_t ray;
         };
+        // Small eyes are one band. Large eyes are cut into bands of kBandRays consecutive rays (whole ommatidia:
+        // the cone samples of one stay together), each sorted by pitch on its own with its own look-up table:
+        // the render kernel then treats a large eye as a sequence of small ones that fit shared memory.
+        const size_t band = R > (size_t)kGridRaysSmem ? (size_t)kBandRays : R;
+        const size_t nbands = (R + band - 1) / band;
         std::vector<SortedRay> sorted(R);
         for (size_t r = 0; r < R; ++r) sorted[r] = SortedRay{(float)py[2 * r], (float)py[2 * r + 1], (int32_t)r};
-        std::stable_sort(sorted.begin(), sorted.end(),
-                         [](const SortedRay& a, const SortedRay& b) { return a.pitch < b.pitch; });
+        for (size_t b = 0; b < nbands; ++b)
+            std::stable_sort(sorted.begin() + b * band, sorted.begin() + std::min(R, (b + 1) * band),
+                             [](const SortedRay& a, const SortedRay& b2) { return a.pitch < b2.pitch; });
         std::vector<int> pos_of(R), ray_of(R);
         std::vector<float> hot(2 * R);
         for (size_t j = 0; j < R; ++j) {
@@ -213,20 +219,23 @@ int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int3
             hot[2 * j + 1] = sorted[j].yaw;
         }
         const double pi = 3.141592653589793238462643383279502884;
-        std::vector<unsigned int> plut(kPitchLut + 1);
-        size_t j = 0;
-        for (int sl = 0; sl <= kPitchLut; ++sl) {
-            const float edge = (float)(-pi / 2 + sl * (pi / kPitchLut)) - 1e-5f;   // conservative slot start
-            while (j < R && sorted[j].pitch < edge) ++j;
-            plut[sl] = (unsigned int)j;
+        std::vector<unsigned int> plut(nbands * (kPitchLut + 1));   // per band, indices local to the band
+        for (size_t b = 0; b < nbands; ++b) {
+            const size_t j0 = b * band, j1 = std::min(R, j0 + band);
+            size_t j = j0;
+            for (int sl = 0; sl <= kPitchLut; ++sl) {
+                const float edge = (float)(-pi / 2 + sl * (pi / kPitchLut)) - 1e-5f;   // conservative slot start
+                while (j < j1 && sorted[j].pitch < edge) ++j;
+                plut[b * (kPitchLut + 1) + sl] = (unsigned int)(j - j0);
+            }
+            plut[b * (kPitchLut + 1) + kPitchLut] = (unsigned int)(j1 - j0);   // the end bound of every run
         }
-        plut[kPitchLut] = (unsigned int)R;   // the end bound of every run
-        CUDA_TRY(cudaMalloc(&e->d_plut, (kPitchLut + 1) * sizeof(unsigned int)));
+        CUDA_TRY(cudaMalloc(&e->d_plut, plut.size() * sizeof(unsigned int)));
         CUDA_TRY(cudaMalloc(&e->d_sorted, 2 * R * sizeof(float)));
         CUDA_TRY(cudaMalloc(&e->d_pos_of, R * sizeof(int)));
         CUDA_TRY(cudaMalloc(&e->d_sorted_ray, R * sizeof(int)));
         CUDA_TRY(cudaMemcpy(e->d_sorted_ray, ray_of.data(), R * sizeof(int), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(e->d_plut, plut.data(), (kPitchLut + 1) * sizeof(unsigned int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(e->d_plut, plut.data(), plut.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(e->d_sorted, hot.data(), 2 * R * sizeof(float), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(e->d_pos_of, pos_of.data(), R * sizeof(int), cudaMemcpyHostToDevice));
 
@@ -305,12 +314,17 @@ Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
     Plan pl;
     const int max_ctas = device_sms(w->device);  // one persistent CTA per SM (~210 KB of shared memory, 512 threads)
     // headings per group: what the rasteriser's shared-memory winner buffer holds
-    pl.global_best = e->R > kBestCap || e->R > kGridRaysSmem;
-    int64_t hg_max = pl.global_best ? 1 : std::min<int64_t>(kBestCap / e->R, kMaxH);
+    // Large eyes: scans (more than kSmallH headings per group) are rendered band by band through the same
+    // shared-memory winner buffer; single views and short batches walk the ray grid with a winner buffer in HBM,
+    // one heading at a time.
+    pl.global_best = e->R > kGridRaysSmem;
+    const int64_t rows = pl.global_best ? kBandRays : e->R;
+    int64_t hg_max = std::min<int64_t>(kBestCap / rows, kMaxH);
     int64_t splits = 1;
     if (P < max_ctas) splits = std::min<int64_t>(H, (max_ctas + std::max<int64_t>(P, 1) - 1) / std::max<int64_t>(P, 1));
     int64_t ngroups = std::max<int64_t>((H + hg_max - 1) / hg_max, splits);
     pl.Hg = (int)((H + ngroups - 1) / ngroups);
+    if (pl.global_best && pl.Hg <= kSmallH) pl.Hg = 1;
     pl.ngroups = (int)((H + pl.Hg - 1) / pl.Hg);
     pl.splits = (int)std::max<int64_t>(1, std::min<int64_t>(splits, pl.ngroups));
     int64_t items = P * pl.splits;
@@ -403,13 +417,23 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
         }
     }
     size_t smem = sizeof(SmemLayout);
-    if (flags & ISY_FLAG_OUT_F64) {
-        CUDA_TRY(cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        render_kernel<true><<<pl.grid, kThreads, smem, st>>>(rp);
+    const int eye_kind = (vquat || !e->d_sorted) ? kEyeAny : (pl.global_best ? kEyeLarge : kEyeSmall);
+    const bool f64 = (flags & ISY_FLAG_OUT_F64) != 0;
+#define ISY_LAUNCH(F64, EYE)                                                                                              \
+    do {                                                                                                                  \
+        CUDA_TRY(cudaFuncSetAttribute(render_kernel<F64, EYE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        render_kernel<F64, EYE><<<pl.grid, kThreads, smem, st>>>(rp);                                                     \
+    } while (0)
+    if (f64) {
+        if (eye_kind == kEyeAny) ISY_LAUNCH(true, kEyeAny);
+        else if (eye_kind == kEyeSmall) ISY_LAUNCH(true, kEyeSmall);
+        else ISY_LAUNCH(true, kEyeLarge);
     } else {
-        CUDA_TRY(cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        render_kernel<false><<<pl.grid, kThreads, smem, st>>>(rp);
+        if (eye_kind == kEyeAny) ISY_LAUNCH(false, kEyeAny);
+        else if (eye_kind == kEyeSmall) ISY_LAUNCH(false, kEyeSmall);
+        else ISY_LAUNCH(false, kEyeLarge);
     }
+#undef ISY_LAUNCH
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return ISY_OK;

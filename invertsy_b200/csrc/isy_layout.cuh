@@ -20,6 +20,7 @@ constexpr float kTallCopy = ISY_TALL;    // rad of pitch: copies taller than thi
 constexpr float kBinReject = -1e-5f;  // a bin is dropped only if an edge function is below this on all of it
 
 constexpr int kBestCap = 36864;       // (heading, ray) slots of the rasteriser's winner buffer (u16 copy slots, 72 KB)
+constexpr int kBandRays = 1024;       // larger eyes are rendered in bands of this many consecutive rays (a multiple of 32)
 constexpr int kGridRaysSmem = 1280;   // eyes up to this many rays keep their pitch-sorted ray table in shared memory
 constexpr int kPitchLut = 1024;       // slots of the pitch -> first sorted ray look-up table
 constexpr int kHeadLut = 1024;        // slots of the azimuth -> first sorted heading look-up table

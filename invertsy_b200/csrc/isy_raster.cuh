@@ -114,8 +114,9 @@ __device__ bool sort_headings(SmemLayout& sm, int Hcur) {
 template <bool kSmem, bool kUniform, int RU>
 __device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest, const Exact* exacts,
                                            const Entry& ent, const float4 bb, double dist, int e, unsigned jb, unsigned jend,
-                                           float glo, float width, int Hcur) {
-    const int R = rp.R, lane = threadIdx.x & 31, H2 = 2 * Hcur;
+                                           float glo, float width, int Hcur, int R, unsigned jbase) {
+    // R: rays per row of the winner buffer (the eye, or the band of a large eye); jbase: first sorted position of the band
+    const int lane = threadIdx.x & 31, H2 = 2 * Hcur;
     const float2* gsorted = reinterpret_cast<const float2*>(rp.grid_sorted);
     const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
     const float uh0 = sm.ras.uni[0], udelta = sm.ras.uni[1], uinv = sm.ras.uni[2];
@@ -188,7 +189,7 @@ __device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& s
             // redo the query in fp64 exactly as the reference composes it
             if (act[u] && (seam || (m[u] >= -kEdgeEps && m[u] <= kEdgeEps))) {
                 const int hh = sm.ras.hperm[ks[u]];
-                const int ray = __ldg(rp.grid_sorted_ray + j);
+                const int ray = __ldg(rp.grid_sorted_ray + jbase + j);
                 double yg = rp.eye_py[2 * (size_t)ray + 1] + sm.head_val[hh];
                 if (yg > kPi) yg -= kTwoPi;
                 else if (yg <= -kPi) yg += kTwoPi;
@@ -217,14 +218,14 @@ __device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& s
     }
 }
 
-// kSmem: the eye's sorted ray table and the winner buffer live in shared memory (u16 slots);
-// otherwise both are in global memory (u32 slots), for eyes too large for that.
+// The pitch-run walk of one group of headings over one band of rays (a small eye is one band): the band's sorted
+// ray table and the winner buffer (u16 slots, Rrow per heading) live in shared memory.
 // The hot path is fp32: query azimuth = fl(yaw_f + heading_f) wrapped in fp32; kEdgeEps covers that
 // rounding.  Rays that land within 3e-6 rad of the +-pi seam, and rays inside the rounding band of
 // an edge, redo the query in fp64 exactly as the reference composes it.
-template <bool kSmem, bool kUniform>
-__device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest, const Exact* exacts, int E,
-                              int Hcur, int* s_next) {
+template <bool kUniform>
+__device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, const Exact* exacts, int E, int Hcur, int* s_next,
+                              int Rrow, unsigned jbase) {
     const int lane = threadIdx.x & 31;
     const float pi_f = (float)kPi;
     const int ntall = sm.order_n[0];
@@ -235,6 +236,11 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
         e = __shfl_sync(0xffffffffu, e, 0);
         if (e >= E) break;
         e = sm.order[e < ntall ? e : kMaxE - 1 - (e - ntall)];   // tall copies first: no long straggler at the end
+        // run of pitch-sorted rays that covers the copy's pitch range (a few extra rays at both ends),
+        // worked out when the copy was projected (small eyes) or when the band was loaded
+        const unsigned int jr = sm.jrange[e];
+        const unsigned jbeg = jr & 0xffffu, jend = jr >> 16;
+        if (jbeg >= jend) continue;                // no ray of this band in the copy's pitch range
         const float4 bb = sm.bbox[e];
         // azimuth window of the copy clipped to the query domain (-pi, pi]
         const float glo = fmaxf(bb.z, -pi_f - kBinMargin) - kBinMargin, ghi = fminf(bb.w, pi_f + kBinMargin) + kBinMargin;
@@ -242,26 +248,26 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, unsigned i
         const float width = ghi - glo;
         const Entry ent = sm.tile[e];
         const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
-        // run of pitch-sorted rays that covers [bb.x, bb.y] (a few extra rays at both ends)
-        unsigned jbeg, jend;
-        if (kSmem) {   // worked out when the copy was projected
-            const unsigned int jr = sm.jrange[e];
-            jbeg = jr & 0xffffu, jend = jr >> 16;
-        } else {
-            const int s0 = min(max((int)floorf((bb.x + (float)kHalfPi) * (kPitchLut / (float)kPi)), 0), kPitchLut - 1);
-            const int s1 = min(max((int)floorf((bb.y + (float)kHalfPi) * (kPitchLut / (float)kPi)) + 2, 0), kPitchLut);
-            jbeg = __ldg(rp.grid_plut + s0), jend = __ldg(rp.grid_plut + s1);
-        }
         // kRU rays per lane while that many warps' worth are left, then one ray per lane for the tail
         unsigned jb = jbeg;
         for (; jb + 32 * (kRU - 1) < jend; jb += 32 * kRU) {   // warp-uniform trip counts
             __syncwarp();                                       // keep the lanes converged across iterations
-            walk_chunk<kSmem, kUniform, kRU>(rp, sm, gbest, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur);
+            walk_chunk<true, kUniform, kRU>(rp, sm, nullptr, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur, Rrow, jbase);
         }
         for (; jb < jend; jb += 32) {
             __syncwarp();
-            walk_chunk<kSmem, kUniform, 1>(rp, sm, gbest, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur);
+            walk_chunk<true, kUniform, 1>(rp, sm, nullptr, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur, Rrow, jbase);
         }
+    }
+}
+
+// pitch runs of all copies in the band whose look-up table is resident (large eyes: once per band)
+__device__ __forceinline__ void band_runs(SmemLayout& sm, int E) {
+    for (int e = threadIdx.x; e < E; e += kThreads) {
+        const float4 bb = sm.bbox[e];
+        const int s0 = min(max((int)floorf((bb.x + (float)kHalfPi) * (kPitchLut / (float)kPi)), 0), kPitchLut - 1);
+        const int s1 = min(max((int)floorf((bb.y + (float)kHalfPi) * (kPitchLut / (float)kPi)) + 2, 0), kPitchLut);
+        sm.jrange[e] = sm.ras.plut[s0] | (sm.ras.plut[s1] << 16);
     }
 }
 

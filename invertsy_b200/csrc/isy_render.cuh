@@ -6,7 +6,13 @@ namespace isy {
 
 enum { kModeBrute = 0, kModeBins = 1, kModeRaster = 2 };
 
-template <bool kF64>
+// kEye picks what is compiled in, so that each shape of call gets a kernel allocated and scheduled for it alone:
+//   kEyeAny   any orientation (quaternion views), transient eyes without ray tables: per-position bins, or brute force
+//   kEyeSmall yaw-only views of an eye whose tables fit shared memory: ray grid / pitch-run rasterisers
+//   kEyeLarge yaw-only views of a larger eye: the same, band by band, or the ray grid with tables in HBM
+enum { kEyeAny = 0, kEyeSmall = 1, kEyeLarge = 2 };
+
+template <bool kF64, int kEye>
 __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams rp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
@@ -20,9 +26,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
     unsigned int* gbest = rp.slab_best ? rp.slab_best + (size_t)blockIdx.x * rp.R : nullptr;
     const bool want_sky = rp.sky.kind != ISY_SKY_NONE;
     const bool perez = rp.sky.kind == ISY_SKY_PEREZ;
-    const bool yaw_only = !rp.vquat;
-    const bool raster_ok = yaw_only && rp.grid_sorted && !(rp.flags & ISY_FLAG_BRUTE_FORCE);
-    const bool smem_grid = raster_ok && !gbest;
+    const bool yaw_only = kEye != kEyeAny || !rp.vquat;   // (kEyeAny also serves yaw-only eyes without ray tables)
+    const bool raster_ok = kEye != kEyeAny && !(rp.flags & ISY_FLAG_BRUTE_FORCE);
+    const bool smem_grid = kEye == kEyeSmall && raster_ok;                // its tables stay in shared memory
+    const bool banded = kEye == kEyeLarge && raster_ok && rp.Hg > kSmallH;   // scan plan: rendered in bands
 
     if (perez) {
         for (int i = tid; i < 2 * (kGTab + 1); i += kThreads) sm.gtab[i] = rp.sky_gtab[i];
@@ -80,7 +87,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
         int mode = kModeBrute;
         BinGrid grid;
         if (!(rp.flags & ISY_FLAG_BRUTE_FORCE) && E <= kMaxE) {
-            if (raster_ok) {
+            if (kEye != kEyeAny) {
                 mode = kModeRaster;
             } else if (build_bins(sm, grid, E, s_band, s_warp)) {
                 mode = kModeBins;
@@ -102,71 +109,90 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                 sm.head_val[tid] = hw;
                 sincos(hw, &sm.head_sin[tid], &sm.head_cos[tid]);
             }
-            if (mode == kModeRaster) {
-                if (smem_grid) {
+            // A large eye under a scan plan is rendered band by band (kBandRays consecutive rays, sorted by pitch on
+            // their own): each band goes through the shared-memory winner buffer like a small eye.  Everything
+            // else is a single pass over all rays.
+            const bool is_raster = kEye != kEyeAny && mode == kModeRaster;
+            const bool walk_bands = banded && is_raster;
+            const int nbands = walk_bands ? (rp.R + kBandRays - 1) / kBandRays : 1;
+            bool uniform = false;
+            for (int band = 0; band < nbands; ++band) {
+            const int r_lo = walk_bands ? band * kBandRays : 0;
+            const int r_n = walk_bands ? min(kBandRays, rp.R - r_lo) : rp.R;
+            const bool best_smem = kEye == kEyeSmall || walk_bands;
+            long long t3b = clock64();
+            if (is_raster) {
+                if (band > 0) __syncthreads();     // the previous band's final pass is done with the buffers
+                if (best_smem) {
                     unsigned int* b32 = reinterpret_cast<unsigned int*>(sm.ras.best);
-                    for (int i = tid; i < (Hcur * rp.R + 1) / 2; i += kThreads) b32[i] = 0xffffffffu;
+                    for (int i = tid; i < (Hcur * r_n + 1) / 2; i += kThreads) b32[i] = 0xffffffffu;
                 } else {
                     for (int i = tid; i < Hcur * rp.R; i += kThreads) gbest[i] = kNoCopy;
                 }
+                if (walk_bands) {                  // this band's sorted rays and pitch look-up table
+                    const float2* gs = reinterpret_cast<const float2*>(rp.grid_sorted) + r_lo;
+                    for (int i = tid; i < r_n; i += kThreads) sm.ras.sorted[i] = gs[i];
+                    const unsigned int* gp = rp.grid_plut + (size_t)band * (kPitchLut + 1);
+                    for (int i = tid; i <= kPitchLut; i += kThreads) sm.ras.plut[i] = gp[i];
+                }
                 __syncthreads();
                 if (tid == 0) s_count = 0;     // (the cull's counter is free again: next copy to rasterise)
-                const bool uniform = sort_headings(sm, Hcur);
+                if (band == 0) uniform = sort_headings(sm, Hcur);
+                if (walk_bands) band_runs(sm, E);
                 __syncthreads();
 #ifdef ISY_PHASE_DETAIL
                 t_walk = clock64();
 #endif
-                if (Hcur <= kSmallH && smem_grid) {
-                    // (large eyes keep the pitch-run walk: their cells hold many rays and the lanes of a run stay full)
+                if (kEye == kEyeSmall ? Hcur > kSmallH : walk_bands) {
+                    if (uniform) raster_copies<true>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo);
+                    else raster_copies<false>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo);
+                } else if (kEye == kEyeSmall) {
                     raster_cells<true>(rp, sm, gbest, exacts, E, Hcur, &s_count);
-                } else if (smem_grid) {
-                    if (uniform) raster_copies<true, true>(rp, sm, gbest, exacts, E, Hcur, &s_count);
-                    else raster_copies<true, false>(rp, sm, gbest, exacts, E, Hcur, &s_count);
-                } else if (Hcur <= kSmallH) {
+                } else {   // large eye, one heading at a time
                     raster_cells<false>(rp, sm, gbest, exacts, E, Hcur, &s_count);
-                } else {
-                    if (uniform) raster_copies<false, true>(rp, sm, gbest, exacts, E, Hcur, &s_count);
-                    else raster_copies<false, false>(rp, sm, gbest, exacts, E, Hcur, &s_count);
                 }
             }
             __syncthreads();
             long long t4 = clock64();
-            t_phase[1] += t4 - t3;
+            t_phase[1] += t4 - t3b;
 #ifdef ISY_PHASE_DETAIL
 #if ISY_PHASE_DETAIL == 1
-            t_detail[2] += t_walk - t3;
+            t_detail[2] += t_walk - t3b;
 #endif
 #endif
 
-            if (mode == kModeRaster && !kF64 && rp.S == 1 && !rp.init_c) {
+            if (is_raster && !kF64 && rp.S == 1 && !rp.init_c) {
                 const bool all_out = rp.out.rgb && rp.out.hit && rp.out.depth && rp.out.Y && rp.out.dop && rp.out.aop;
                 // the common shapes get their own instantiations; everything else takes the general ones
-                if (smem_grid && Hcur > 1 && !rp.sun_per_view && all_out) {   // scans of a small eye, everything asked for
-                    final_pass_fast<true, true, true, kShadeU>(rp, sm, gbest, p, grp, Hcur);
+                if (kEye == kEyeLarge) {
+                    if (walk_bands) {   // a band of a large eye
+                        if (Hcur > 1) final_pass_fast<true, false, false, kShadeU, true>(rp, sm, gbest, p, grp, Hcur, r_lo, r_n);
+                        else final_pass_fast<true, false, false, 1, true>(rp, sm, gbest, p, grp, Hcur, r_lo, r_n);
+                    } else {            // one heading at a time, winner buffer in HBM
+                        final_pass_fast<false, false, false, 1, false>(rp, sm, gbest, p, grp, Hcur, 0, 0);
+                    }
+                } else if (Hcur > 1 && !rp.sun_per_view && all_out) {   // scans of a small eye, everything asked for
+                    final_pass_fast<true, true, true, kShadeU, false>(rp, sm, gbest, p, grp, Hcur, 0, 0);
                 } else if (Hcur == 1) {   // single views, sun sweeps: one heading per trip
-                    if (smem_grid) final_pass_fast<true, false, false, 1>(rp, sm, gbest, p, grp, Hcur);
-                    else final_pass_fast<false, false, false, 1>(rp, sm, gbest, p, grp, Hcur);
-                } else if (smem_grid) {
-                    if (!rp.sun_per_view) final_pass_fast<true, true, false, kShadeU>(rp, sm, gbest, p, grp, Hcur);
-                    else final_pass_fast<true, false, false, kShadeU>(rp, sm, gbest, p, grp, Hcur);
+                    final_pass_fast<true, false, false, 1, false>(rp, sm, gbest, p, grp, Hcur, 0, 0);
                 } else {
-                    if (!rp.sun_per_view) final_pass_fast<false, true, false, kShadeU>(rp, sm, gbest, p, grp, Hcur);
-                    else final_pass_fast<false, false, false, kShadeU>(rp, sm, gbest, p, grp, Hcur);
+                    if (!rp.sun_per_view) final_pass_fast<true, true, false, kShadeU, false>(rp, sm, gbest, p, grp, Hcur, 0, 0);
+                    else final_pass_fast<true, false, false, kShadeU, false>(rp, sm, gbest, p, grp, Hcur, 0, 0);
                 }
                 t_phase[2] += clock64() - t4;
                 continue;
             }
             // ---- generic final pass: warp units = (block of 32 consecutive rays) x (chunk of headings);
             //      the eye data of a ray are loaded once per unit and reused for its headings
-            const int nb = (rp.R + 31) >> 5;
+            const int nb = (r_n + 31) >> 5;
             int nch = min(Hcur, max(1, (2 * kWarps + nb - 1) / nb));
             const int hper = (Hcur + nch - 1) / nch;
             nch = (Hcur + hper - 1) / hper;
             for (int u = warp; u < nb * nch; u += kWarps) {
                 const int rb = u / nch, hc = u - rb * nch;
-                const int r = rb * 32 + lane;
-                const bool valid = r < rp.R;
-                const int rr = valid ? r : rp.R - 1;
+                const int r = r_lo + rb * 32 + lane;
+                const bool valid = r < r_lo + r_n;
+                const int rr = valid ? r : r_lo + r_n - 1;
                 double e_pitch = 0, e_yaw = 0, f_theta = 0;
                 double4 t4v = make_double4(0, 1, 0, 1);
                 int pos = 0;
@@ -177,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                         t4v = *reinterpret_cast<const double4*>(rp.eye_trig + 4 * (size_t)rr);
                         f_theta = rp.eye_ftheta[rr];
                     }
-                    if (mode == kModeRaster) pos = __ldg(rp.grid_pos_of + rr);
+                    if (is_raster) pos = __ldg(rp.grid_pos_of + rr) - (walk_bands ? r_lo : 0);
                 }
                 const int hend = min(Hcur, (hc + 1) * hper);
                 for (int hh = hc * hper; hh < hend; ++hh) {
@@ -214,16 +240,16 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                     ray.best = CUDART_INF;
                     ray.hit = -1;
 
-                    if (mode == kModeRaster) {
+                    if (is_raster) {
                         const int hs = sm.ras.hinv[hh];
-                        const unsigned int rk = smem_grid ? (unsigned)sm.ras.best[hs * rp.R + pos]
+                        const unsigned int rk = best_smem ? (unsigned)sm.ras.best[hs * r_n + pos]
                                                           : gbest[(size_t)hs * rp.R + pos];
                         if (rk != kNoCopy) {
                             const Entry& w = sm.tile[rk];
                             ray.hit = w.tri;
                             ray.best = __hiloint2double(w.dist_hi, w.dist_lo);
                         }
-                    } else if (mode == kModeBins) {
+                    } else if (kEye == kEyeAny && mode == kModeBins) {
                         if (ray.fp >= grid.th_lo && ray.fp <= grid.th_hi) {
                             int row = min((int)((ray.fp - grid.th_lo) * grid.inv_dth), grid.rows - 1);
                             int col = min(max((int)((ray.fy + (float)kPi) * grid.inv_dph), 0), grid.cols - 1);
@@ -273,6 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                 }
             }
             t_phase[2] += clock64() - t4;
+            }   // bands
         }
         t_phase[0] += t1 - t0, t_phase[1] += t2 - t1, t_phase[3] += 1;
     }

@@ -20,10 +20,13 @@ constexpr int kShadeU = ISY_SHADE_U;  // headings per lane and trip in the final
 // kAllOut: all six outputs were asked for (the usual call): no per-store null checks.
 // kSU: headings per lane and trip (2 hides the latency of the fp64 chain; 1 for single-heading positions, where a
 // second slot would only repeat the first)
-template <bool kSmem, bool kOneSun, bool kAllOut, int kSU>
+// kBand: rays [band_lo, band_lo + band_n) only -- one band of a large eye (the winner buffer then has band_n slots
+// per heading and sorted positions count from the band's first); otherwise the whole eye
+template <bool kSmem, bool kOneSun, bool kAllOut, int kSU, bool kBand>
 __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const unsigned int* gbest, int p, int grp,
-                                int Hcur) {
-    const int R = rp.R, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                                int Hcur, int band_lo, int band_n) {
+    const int R = rp.R, r_lo = kBand ? band_lo : 0, r_n = kBand ? band_n : R, Rrow = r_n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool perez = rp.sky.kind == ISY_SKY_PEREZ, uniform = rp.sky.kind == ISY_SKY_UNIFORM;
     const bool from_sky = (rp.flags & ISY_FLAG_INIT_FROM_SKY) && (perez || uniform);
     float* const o_rgb = reinterpret_cast<float*>(rp.out.rgb);
@@ -32,7 +35,7 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
     float* const o_P = reinterpret_cast<float*>(rp.out.dop);
     float* const o_A = reinterpret_cast<float*>(rp.out.aop);
     const float nanf_ = __int_as_float(0x7fc00000);
-    const int nb = (R + 31) >> 5;
+    const int nb = (r_n + 31) >> 5;
     int nch = min(Hcur, max(1, (2 * kWarps + nb - 1) / nb));
 #ifdef ISY_SHADE_NCH
     nch = min(Hcur, ISY_SHADE_NCH);
@@ -41,9 +44,9 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
     nch = (Hcur + hper - 1) / hper;
     for (int u = warp; u < nb * nch; u += kWarps) {
         const int rb = u / nch, hc = u - rb * nch;
-        const int r = rb * 32 + lane;
-        const bool valid = r < R;
-        const int rr = valid ? r : R - 1;
+        const int r = r_lo + rb * 32 + lane;
+        const bool valid = r < r_lo + r_n;
+        const int rr = valid ? r : r_lo + r_n - 1;
         const double e_pitch = rp.eye_py[2 * (size_t)rr];
         const bool ground = e_pitch >= 0;                               // world.py:90
         double4 t4v = make_double4(0, 1, 0, 1);
@@ -52,7 +55,7 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
             t4v = *reinterpret_cast<const double4*>(rp.eye_trig + 4 * (size_t)rr);
             f_theta = rp.eye_ftheta[rr];
         }
-        const int pos = __ldg(rp.grid_pos_of + rr);
+        const int pos = __ldg(rp.grid_pos_of + rr) - r_lo;
         const int hend = min(Hcur, (hc + 1) * hper);
 
         // kSU headings per trip: their sky evaluations are independent instruction streams (the pass is
@@ -71,7 +74,7 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
                 const int hh = min(hh0 + q, hend - 1);
                 view[q] = (size_t)p * rp.H + grp + (size_t)hh * rp.ngroups;   // group = every ngroups-th heading
                 const int hs = sm.ras.hinv[hh];
-                id[q] = kSmem ? (unsigned)sm.ras.best[hs * R + pos] : gbest[(size_t)hs * R + pos];
+                id[q] = kSmem ? (unsigned)sm.ras.best[hs * Rrow + pos] : gbest[(size_t)hs * R + pos];
                 if (perez) {
                     const double hsn = sm.head_sin[hh], hcs = sm.head_cos[hh];
                     const double sy = t4v.z * hcs + t4v.w * hsn, cy = t4v.w * hcs - t4v.z * hsn;   // yaw_e + heading
