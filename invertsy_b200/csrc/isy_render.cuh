@@ -161,13 +161,18 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 #endif
 #endif
 
-            if (is_raster && !kF64 && rp.S == 1 && !rp.init_c) {
+            if (is_raster && !kF64 && !rp.init_c && (rp.S == 1 || walk_bands)) {
                 const bool all_out = rp.out.rgb && rp.out.hit && rp.out.depth && rp.out.Y && rp.out.dop && rp.out.aop;
                 // the common shapes get their own instantiations; everything else takes the general ones
                 if (kEye == kEyeLarge) {
-                    if (walk_bands) {   // a band of a large eye
-                        if (Hcur > 1) final_pass_fast<true, false, false, kShadeU, true>(rp, sm, gbest, p, grp, Hcur, r_lo, r_n);
-                        else final_pass_fast<true, false, false, 1, true>(rp, sm, gbest, p, grp, Hcur, r_lo, r_n);
+                    if (walk_bands && rp.S > 1) {   // a band of a cone-sampled eye
+                        if (Hcur == 1) final_pass_fast<true, false, false, 1, true, true>(rp, sm, gbest, p, grp, Hcur, r_lo, r_n);
+                        else if (rp.sun_per_view) final_pass_fast<true, false, false, kShadeU, true, true>(rp, sm, gbest, p, grp, Hcur, r_lo, r_n);
+                        else final_pass_fast<true, true, false, kShadeU, true, true>(rp, sm, gbest, p, grp, Hcur, r_lo, r_n);
+                    } else if (walk_bands) {        // a band of a large eye
+                        if (Hcur == 1) final_pass_fast<true, false, false, 1, true>(rp, sm, gbest, p, grp, Hcur, r_lo, r_n);
+                        else if (rp.sun_per_view) final_pass_fast<true, false, false, kShadeU, true>(rp, sm, gbest, p, grp, Hcur, r_lo, r_n);
+                        else final_pass_fast<true, true, false, kShadeU, true>(rp, sm, gbest, p, grp, Hcur, r_lo, r_n);
                     } else {            // one heading at a time, winner buffer in HBM
                         final_pass_fast<false, false, false, 1, false>(rp, sm, gbest, p, grp, Hcur, 0, 0);
                     }

@@ -22,7 +22,9 @@ constexpr int kShadeU = ISY_SHADE_U;  // headings per lane and trip in the final
 // second slot would only repeat the first)
 // kBand: rays [band_lo, band_lo + band_n) only -- one band of a large eye (the winner buffer then has band_n slots
 // per heading and sorted positions count from the band's first); otherwise the whole eye
-template <bool kSmem, bool kOneSun, bool kAllOut, int kSU, bool kBand>
+// kCone: S > 1 samples per ommatidium (S consecutive rays = S consecutive lanes): hit and depth stay per ray, the
+// other outputs are the weighted cone averages, written by the first lane of each ommatidium
+template <bool kSmem, bool kOneSun, bool kAllOut, int kSU, bool kBand, bool kCone = false>
 __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const unsigned int* gbest, int p, int grp,
                                 int Hcur, int band_lo, int band_n) {
     const int R = rp.R, r_lo = kBand ? band_lo : 0, r_n = kBand ? band_n : R, Rrow = r_n;
@@ -57,6 +59,7 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
         }
         const int pos = __ldg(rp.grid_pos_of + rr) - r_lo;
         const int hend = min(Hcur, (hc + 1) * hper);
+        const float wray = kCone ? (valid ? __ldg(rp.eye_w + rr) : 0.f) : 1.f;   // cone weight of this sample
 
         // kSU headings per trip: their sky evaluations are independent instruction streams (the pass is
         // bound by the latency of the fp64 chain, not by issue slots)
@@ -64,8 +67,12 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
         // headings of a group are ngroups views apart, so it advances by a constant
         const size_t ostride = (size_t)rp.ngroups * (size_t)R;
         size_t off0 = ((size_t)p * rp.H + grp + (size_t)(hc * hper) * rp.ngroups) * (size_t)R + (size_t)r;
-        for (int hh0 = hc * hper; hh0 < hend; hh0 += kSU, off0 += kSU * ostride) {
+        // ... and of (view, this lane's ommatidium) in the per-ommatidium outputs of a cone-sampled eye
+        const size_t nstride = (size_t)rp.ngroups * (size_t)rp.N;
+        size_t offn0 = ((size_t)p * rp.H + grp + (size_t)(hc * hper) * rp.ngroups) * (size_t)rp.N + (size_t)(r / max(rp.S, 1));
+        for (int hh0 = hc * hper; hh0 < hend; hh0 += kSU, off0 += kSU * ostride, offn0 += kSU * nstride) {
             double Y[kSU], P[kSU], A[kSU];
+            float sA[kSU], cA[kSU];      // (cone-sampled eyes) sin / cos of the polarisation angle
             size_t view[kSU];
             unsigned int id[kSU];
 #pragma unroll
@@ -81,6 +88,14 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
                     const SunConst& sc = kOneSun ? sm.sun0 : rp.sun[rp.sun_per_view ? view[q] : 0];
                     sky_eval<false>(rp.sky, sc, t4v.y * cy, t4v.y * sy, -t4v.x, e_pitch + kHalfPi, f_theta, Y[q], P[q], A[q],
                                     false, sm.gtab);
+                    if (kCone) {
+                        // A = atan2(dy - sy, dx - sx) + pi/2 (sky.py:323)  =>  (sin A, cos A) = (X, -Y) / |(X, Y)|
+                        const float X = (float)(t4v.y * cy - sc.sx), Yd = (float)(t4v.y * sy - sc.sy), h2 = X * X + Yd * Yd;
+                        float ih;
+                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ih) : "f"(fmaxf(h2, 1e-36f)));
+                        sA[q] = h2 > 0.f ? X * ih : 1.f;               // atan2(0, 0) = 0 -> A = pi/2
+                        cA[q] = -Yd * ih;
+                    }
                 } else if (uniform) {
                     Y[q] = rp.sky.luminance;
                 }
@@ -103,7 +118,46 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
                     const float* col = rp.tri_rgb + 3 * (size_t)hit;
                     cr = __ldg(col + 0), cg = __ldg(col + 1), cb = __ldg(col + 2);
                 }
-                if (valid) {
+                if (kCone) {
+                    if (valid) {
+                        const size_t i = off0 + q * ostride;
+                        if (rp.out.hit) __stcs(rp.out.hit + i, hit);
+                        if (o_depth) __stcs(o_depth + i, depth);
+                    }
+                    // weighted cone average over the S consecutive lanes of an ommatidium (S divides 32).
+                    // Luminance (and the 0..255 colours painted from it) in fp64, the rest in fp32.
+                    double wY = (double)wray * Y[q];
+                    double wr = 0, wg = 0, wb = 0;
+                    float fr = wray * cr, fg = wray * cg, fb = wray * cb;
+                    float wP = wray * (float)P[q], wS = wray * sA[q], wC = wray * cA[q];
+                    if (from_sky) wr = (double)wray * cr, wg = (double)wray * cg, wb = (double)wray * cb;
+                    for (int off = rp.S >> 1; off > 0; off >>= 1) {
+                        wY += __shfl_xor_sync(0xffffffffu, wY, off);
+                        wP += __shfl_xor_sync(0xffffffffu, wP, off);
+                        wS += __shfl_xor_sync(0xffffffffu, wS, off);
+                        wC += __shfl_xor_sync(0xffffffffu, wC, off);
+                        if (from_sky) {
+                            wr += __shfl_xor_sync(0xffffffffu, wr, off);
+                            wg += __shfl_xor_sync(0xffffffffu, wg, off);
+                            wb += __shfl_xor_sync(0xffffffffu, wb, off);
+                        } else {
+                            fr += __shfl_xor_sync(0xffffffffu, fr, off);
+                            fg += __shfl_xor_sync(0xffffffffu, fg, off);
+                            fb += __shfl_xor_sync(0xffffffffu, fb, off);
+                        }
+                    }
+                    if (from_sky) fr = (float)wr, fg = (float)wg, fb = (float)wb;
+                    if (valid && (r & (rp.S - 1)) == 0) {
+                        const size_t i = offn0 + q * nstride;
+                        if (o_rgb) {
+                            float* qq = o_rgb + 3 * i;
+                            __stcs(qq, fr), __stcs(qq + 1, fg), __stcs(qq + 2, fb);
+                        }
+                        if (o_Y) __stcs(o_Y + i, (float)wY);
+                        if (o_P) __stcs(o_P + i, wP);
+                        if (o_A) __stcs(o_A + i, perez ? atan2_fast(wS, wC) : nanf_);   // circular mean of the angles
+                    }
+                } else if (valid) {
                     // streaming stores: the views are written once and never read back by the kernel, so they
                     // should leave L2 before the slabs, the world and the eye tables do
                     const size_t i = off0 + q * ostride;

@@ -74,7 +74,7 @@ def test_cone_sampled_eye_scan_in_bands(ib):
     r = ib.Renderer(world, ib.EyeLayout.from_angles(rp, ry, samples=S), sky=ib.Sky(*sun))
     headings = np.deg2rad(np.array([-150., -90., -30., 30., 90., 150.]))
     pos = np.array([[5.1, 4.9, 0.01], [2.2, 7.3, 0.01]])
-    out = _np(r, pos=pos, yaw=np.tile(headings, (2, 1)), outputs=("hit", "rgb", "Y", "dop"))
+    out = _np(r, pos=pos, yaw=np.tile(headings, (2, 1)), outputs=("hit", "rgb", "Y", "dop", "aop"))
     assert out["hit"].shape == (12, N * S) and out["Y"].shape == (12, N)
     samp = o.eye_rotations(rp, ry)
     for p in range(2):
@@ -83,9 +83,11 @@ def test_cone_sampled_eye_scan_in_bands(ib):
             ref = c_oracle.world_hits(world.polygons, 2.0, pos[p], rp, _global_yaw(ry, headings[h]))[0]
             assert np.array_equal(out["hit"][b], ref)
     # one view in full: cone averages of the reference's per-sample values
-    y, dop, _ = o.sky_render(sun[0], sun[1], o.view_rotations(np.rad2deg(headings[2]), samp))
+    y, dop, aop = o.sky_render(sun[0], sun[1], o.view_rotations(np.rad2deg(headings[2]), samp))
     assert np.abs(out["Y"][2] - y.reshape(N, S).mean(1)).max() < 1e-5
     assert np.abs(out["dop"][2] - dop.reshape(N, S).mean(1)).max() < 1e-5
+    circ = np.arctan2(np.sin(aop).reshape(N, S).mean(1), np.cos(aop).reshape(N, S).mean(1))   # circular mean of the samples
+    assert circ_diff(out["aop"][2], circ).max() < 1e-5
     c = o.world_render(world.polygons, world.colours, 2.0, pos[0:1], o.view_rotations(np.rad2deg(headings[2]), samp))
     avg = c.astype(np.float64).reshape(N, S, 3).mean(1)
     got = out["rgb"][2]
