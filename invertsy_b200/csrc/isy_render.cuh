@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 #endif
 #endif
 
-            if (is_raster && !kF64 && !rp.init_c && (rp.S == 1 || walk_bands)) {
+            if (is_raster && !kF64 && !rp.init_c && (rp.S == 1 || kEye == kEyeLarge)) {
                 const bool all_out = rp.out.rgb && rp.out.hit && rp.out.depth && rp.out.Y && rp.out.dop && rp.out.aop;
                 // the common shapes get their own instantiations; everything else takes the general ones
                 if (kEye == kEyeLarge) {
@@ -173,7 +173,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                         if (Hcur == 1) final_pass_fast<true, false, false, 1, true>(rp, sm, gbest, p, grp, Hcur, r_lo, r_n);
                         else if (rp.sun_per_view) final_pass_fast<true, false, false, kShadeU, true>(rp, sm, gbest, p, grp, Hcur, r_lo, r_n);
                         else final_pass_fast<true, true, false, kShadeU, true>(rp, sm, gbest, p, grp, Hcur, r_lo, r_n);
-                    } else {            // one heading at a time, winner buffer in HBM
+                    } else if (rp.S > 1) {   // one heading at a time, winner buffer in HBM
+                        final_pass_fast<false, false, false, 1, false, true>(rp, sm, gbest, p, grp, Hcur, 0, 0);
+                    } else {
                         final_pass_fast<false, false, false, 1, false>(rp, sm, gbest, p, grp, Hcur, 0, 0);
                     }
                 } else if (Hcur > 1 && !rp.sun_per_view && all_out) {   // scans of a small eye, everything asked for
