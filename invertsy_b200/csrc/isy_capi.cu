@@ -200,10 +200,10 @@ int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int3
             float pitch, yaw;
             int32_t ray;
         };
-        // Small eyes are one band. Large eyes are cut into bands of kBandRays consecutive rays (whole ommatidia:
+        // Small eyes are one band. Large and cone-sampled eyes are cut into bands of kBandRays consecutive rays (whole ommatidia:
         // the cone samples of one stay together), each sorted by pitch on its own with its own look-up table:
         // the render kernel then treats a large eye as a sequence of small ones that fit shared memory.
-        const size_t band = R > (size_t)kGridRaysSmem ? (size_t)kBandRays : R;
+        const size_t band = (R > (size_t)kGridRaysSmem || S > 1) ? std::min<size_t>((size_t)kBandRays, R) : R;
         const size_t nbands = (R + band - 1) / band;
         std::vector<SortedRay> sorted(R);
         for (size_t r = 0; r < R; ++r) sorted[r] = SortedRay{(float)py[2 * r], (float)py[2 * r + 1], (int32_t)r};
@@ -317,7 +317,7 @@ Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
     // Large eyes: scans (more than kSmallH headings per group) are rendered band by band through the same
     // shared-memory winner buffer; single views and short batches walk the ray grid with a winner buffer in HBM,
     // one heading at a time.
-    pl.global_best = e->R > kGridRaysSmem;
+    pl.global_best = e->R > kGridRaysSmem || e->S > 1;   // (cone-sampled eyes take the large-eye kernel whatever their size)
     const int64_t rows = pl.global_best ? kBandRays : e->R;
     int64_t hg_max = std::min<int64_t>(kBestCap / rows, kMaxH);
     int64_t splits = 1;
