@@ -111,13 +111,12 @@ __device__ bool sort_headings(SmemLayout& sm, int Hcur) {
 // One step of the pitch-run walk: RU rays per lane (32 * RU consecutive pitch-sorted rays from jb) against copy e.
 // Their window walks and edge tests are independent instruction streams, which is what hides the
 // shared-memory and branch latencies here.
-template <bool kSmem, bool kUniform, int RU>
-__device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest, const Exact* exacts,
+template <bool kUniform, int RU>
+__device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& sm, const Exact* exacts,
                                            const Entry& ent, const float4 bb, double dist, int e, unsigned jb, unsigned jend,
                                            float glo, float width, int Hcur, int R, unsigned jbase) {
     // R: rays per row of the winner buffer (the eye, or the band of a large eye); jbase: first sorted position of the band
     const int lane = threadIdx.x & 31, H2 = 2 * Hcur;
-    const float2* gsorted = reinterpret_cast<const float2*>(rp.grid_sorted);
     const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
     const float uh0 = sm.ras.uni[0], udelta = sm.ras.uni[1], uinv = sm.ras.uni[2];
     const unsigned int best_s = (unsigned int)__cvta_generic_to_shared(sm.ras.best);
@@ -128,7 +127,7 @@ __device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& s
     for (int u = 0; u < RU; ++u) {
         const unsigned j = jb + u * 32 + lane;
         py[u] = make_float2(4.f, 0.f);                  // pitch 4 rad: outside every band
-        if (j < jend) py[u] = kSmem ? sm.ras.sorted[j] : __ldg(gsorted + j);
+        if (j < jend) py[u] = sm.ras.sorted[j];
     }
 #pragma unroll
     for (int u = 0; u < RU; ++u) {
@@ -203,8 +202,7 @@ __device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& s
             }
             // rows of best[] are SORTED heading slots
             if (in) {
-                if (kSmem) post_copy_u16(best_s, (unsigned)ks[u] * R + j, sm.tile, dist, ent.tri, e);
-                else post_copy_u32(&gbest[(size_t)ks[u] * R + j], sm.tile, dist, ent.tri, e);
+                post_copy_u16(best_s, (unsigned)ks[u] * R + j, sm.tile, dist, ent.tri, e);
             }
             if (kUniform) {
                 if (act[u]) {
@@ -252,11 +250,11 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, const Exac
         unsigned jb = jbeg;
         for (; jb + 32 * (kRU - 1) < jend; jb += 32 * kRU) {   // warp-uniform trip counts
             __syncwarp();                                       // keep the lanes converged across iterations
-            walk_chunk<true, kUniform, kRU>(rp, sm, nullptr, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur, Rrow, jbase);
+            walk_chunk<kUniform, kRU>(rp, sm, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur, Rrow, jbase);
         }
         for (; jb < jend; jb += 32) {
             __syncwarp();
-            walk_chunk<true, kUniform, 1>(rp, sm, nullptr, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur, Rrow, jbase);
+            walk_chunk<kUniform, 1>(rp, sm, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur, Rrow, jbase);
         }
     }
 }
