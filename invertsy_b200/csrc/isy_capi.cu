@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdlib>
 #include <cstdio>
 #include <cmath>
@@ -312,7 +313,7 @@ int device_sms(int device) {
 
 Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
     Plan pl;
-    const int max_ctas = device_sms(w->device);  // one persistent CTA per SM (~210 KB of shared memory, 512 threads)
+    const int max_ctas = device_sms(w->device);  // one persistent CTA per SM (196 KB of shared memory, kThreads threads)
     // headings per group: what the rasteriser's shared-memory winner buffer holds
     // Large eyes: scans (more than kSmallH headings per group) are rendered band by band through the same
     // shared-memory winner buffer; single views and short batches walk the ray grid with a winner buffer in HBM,
@@ -395,6 +396,22 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
     rp.slab_best = pl.global_best ? (unsigned int*)(base + pl.off_best) : nullptr;
     rp.slab_cap = pl.slab_cap, rp.splits = pl.splits, rp.items = (int)(P * pl.splits);
     rp.Hg = pl.Hg, rp.ngroups = pl.ngroups;
+    {   // The fast final pass deals (block of 32 rays) x (chunk of headings) units to the warps round-robin; it is
+        // throughput-bound, so pick the chunking whose busiest warp has the least to do (ties: the coarsest, which
+        // reuses a ray's data most).
+        const int64_t rays = pl.global_best ? std::min<int64_t>(e->R, kBandRays) : e->R;
+        const int nb = (int)((rays + 31) / 32), warps = kThreads / 32, su = pl.Hg > 1 ? 2 : 1;
+        int best_nch = 1;
+        int64_t best_load = INT64_MAX;
+        for (int nch = 1; nch <= pl.Hg; ++nch) {
+            int hper = (pl.Hg + nch - 1) / nch;
+            hper = std::min(pl.Hg, (hper + su - 1) / su * su);
+            const int n = (pl.Hg + hper - 1) / hper;
+            const int64_t load = (int64_t)((nb * n + warps - 1) / warps) * hper;
+            if (load < best_load) best_load = load, best_nch = nch;
+        }
+        rp.shade_nch = best_nch;
+    }
     rp.grid_plut = e->d_plut, rp.grid_sorted = e->d_sorted, rp.grid_pos_of = e->d_pos_of;
     rp.grid_sorted_ray = e->d_sorted_ray;
     rp.cells_start = e->d_cells_start, rp.cells_list = e->d_cells_list;

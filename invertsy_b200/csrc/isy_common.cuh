@@ -112,6 +112,7 @@ struct RenderParams {
     unsigned int* slab_best; // [grid][R] winner buffer in global memory when a heading does not fit smem, else null
     int slab_cap;
     int Hg, ngroups;         // headings per group, number of groups (H = sum of group sizes)
+    int shade_nch;           // fast final pass: heading chunks per ray block (chosen by the host so that the warps finish together)
     int splits;              // CTAs sharing one position (each redoes the cull, takes every splits-th group)
     int items;               // P * splits
 };

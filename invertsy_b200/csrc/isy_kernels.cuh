@@ -19,8 +19,12 @@
 #pragma once
 #include "isy_common.cuh"
 
+// CTA size.  One persistent CTA per SM either way (196 KB of shared memory); 896 threads = 28 warps at 72 registers.
+// The rasteriser is latency-bound and scales with the warps (121 k -> 90 k cycles per position from 512 to 896
+// threads), the final pass is throughput-bound and pays a little for the tighter register budget (73 k -> 81 k):
+// 31.5 -> 27.9 ms per step on the benchmark grid.  640 / 768 / 1024 threads were measured too (README of profiles/).
 #ifndef ISY_THREADS
-#define ISY_THREADS 512
+#define ISY_THREADS 896
 #endif
 
 #include "isy_layout.cuh"

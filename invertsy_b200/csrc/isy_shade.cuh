@@ -38,11 +38,9 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
     float* const o_A = reinterpret_cast<float*>(rp.out.aop);
     const float nanf_ = __int_as_float(0x7fc00000);
     const int nb = (r_n + 31) >> 5;
-    int nch = min(Hcur, max(1, (2 * kWarps + nb - 1) / nb));
-#ifdef ISY_SHADE_NCH
-    nch = min(Hcur, ISY_SHADE_NCH);
-#endif
-    const int hper = (Hcur + nch - 1) / nch;
+    int nch = min(Hcur, max(1, rp.shade_nch));
+    int hper = (Hcur + nch - 1) / nch;
+    hper = min(Hcur, (hper + kSU - 1) / kSU * kSU);      // whole trips
     nch = (Hcur + hper - 1) / hper;
     for (int u = warp; u < nb * nch; u += kWarps) {
         const int rb = u / nch, hc = u - rb * nch;
