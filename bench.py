@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--e2e-positions", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--brute-force", action="store_true")
+    ap.add_argument("--per-view-sky", action="store_true",
+                    help="evaluate the sky for every view instead of once per (heading, ray) of the grid's shared headings")
     ap.add_argument("--sky", default="perez", choices=["perez", "uniform", "none"],
                     help="diagnostic only: the headline workload is 'perez'")
     args = ap.parse_args()
@@ -229,6 +231,11 @@ def main():
     sky = {"perez": ib.Sky(SUN[0], SUN[1]), "uniform": ib.UniformSky(10.), "none": None}[args.sky]
     if args.sky != "perez":
         config["workload"] += " [DIAGNOSTIC sky=%s]" % args.sky
+    if args.sky == "perez":
+        config["sky_evaluation"] = ("per view (--per-view-sky)" if args.per_view_sky else
+                                    "once per (heading, ray) per launch, inside the timed region: every grid position "
+                                    "has the same 36 headings and sun (checked on the device each launch), each view "
+                                    "still gets its own copy written")
     r = ib.Renderer(world, eye, sky=sky, device=local_rank)
 
     pos, yaw = grid_workload(rank, world_size, args.rows, args.cols, args.oris)
@@ -241,7 +248,7 @@ def main():
     out = {}
 
     def step():
-        r.render(pos_d, yaw_d, outputs=names, out=out, brute_force=args.brute_force)
+        r.render(pos_d, yaw_d, outputs=names, out=out, brute_force=args.brute_force, per_view_sky=args.per_view_sky)
 
     def barrier():
         torch.cuda.synchronize()
@@ -293,12 +300,12 @@ def main():
     yaw_h = torch.as_tensor(yaw[sel]).pin_memory()
     host_out = {}
     for _ in range(2):
-        r.render_host(pos_h.numpy(), yaw_h.numpy(), outputs=e_names, out=host_out)
+        r.render_host(pos_h.numpy(), yaw_h.numpy(), outputs=e_names, out=host_out, per_view_sky=args.per_view_sky)
     barrier()
     t0 = time.perf_counter()
     e_steps = max(2, min(args.steps, 5))
     for _ in range(e_steps):
-        r.render_host(pos_h.numpy(), yaw_h.numpy(), outputs=e_names, out=host_out)
+        r.render_host(pos_h.numpy(), yaw_h.numpy(), outputs=e_names, out=host_out, per_view_sky=args.per_view_sky)
     torch.cuda.synchronize()
     e_s = time.perf_counter() - t0
     if world_size > 1:

@@ -297,7 +297,8 @@ struct Plan {
     int Hg, ngroups;
     int slab_cap;
     bool global_best;
-    size_t off_queue, off_status, off_sun, off_ftheta, off_gtab, off_vis, off_entry, off_exact, off_best, total;
+    size_t off_queue, off_status, off_sun, off_ftheta, off_gtab, off_vis, off_entry, off_exact, off_best, off_skytab, total;
+    bool sky_tab;   // room for the launch-wide (heading, ray) sky table
 };
 
 int device_sms(int device) {
@@ -311,9 +312,16 @@ int device_sms(int device) {
     return sms;
 }
 
+constexpr int64_t kSkyTabMinP = 16;            // fewer positions than this do not repay the table
+constexpr size_t kSkyTabMaxBytes = 16u << 20;  // ... and it should stay L2-resident
+
 Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
     Plan pl;
-    const int max_ctas = device_sms(w->device);  // one persistent CTA per SM (196 KB of shared memory, kThreads threads)
+    int max_ctas = device_sms(w->device);  // one persistent CTA per SM (196 KB of shared memory, kThreads threads)
+    if (const char* cap = getenv("ISY_MAX_CTAS")) {   // profiling aid: fewer CTAs = fewer SMs sharing L2 / HBM
+        const int c = atoi(cap);
+        if (c > 0) max_ctas = std::min(max_ctas, c);
+    }
     // headings per group: what the rasteriser's shared-memory winner buffer holds
     // Large eyes: scans (more than kSmallH headings per group) are rendered band by band through the same
     // shared-memory winner buffer; single views and short batches walk the ray grid with a winner buffer in HBM,
@@ -341,6 +349,9 @@ Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
     pl.off_entry = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(Entry));
     pl.off_exact = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(Exact));
     pl.off_best = off, off += pl.global_best ? align_up((size_t)pl.grid * e->R * sizeof(unsigned int)) : 0;
+    // launch-wide sky table of scans whose positions share their headings (small eyes, a few MB at most)
+    pl.sky_tab = !pl.global_best && P >= kSkyTabMinP && (size_t)H * e->R * 3 * sizeof(float) <= kSkyTabMaxBytes;
+    pl.off_skytab = off, off += pl.sky_tab ? align_up((size_t)H * e->R * 3 * sizeof(float)) : 0;
     pl.total = off;
     return pl;
 }
@@ -432,6 +443,30 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
             g_launches++;
             CUDA_TRY(cudaGetLastError());
         }
+    }
+    const int eye_kind0 = (vquat || !e->d_sorted) ? kEyeAny : (pl.global_best ? kEyeLarge : kEyeSmall);
+    if (pl.sky_tab && eye_kind0 == kEyeSmall && sp.kind == ISY_SKY_PEREZ && !rp.sun_per_view && !init_c &&
+        !(flags & (ISY_FLAG_OUT_F64 | ISY_FLAG_INIT_FROM_SKY | ISY_FLAG_BRUTE_FORCE | ISY_FLAG_PER_VIEW_SKY)) && e->S == 1 &&
+        (out->Y || out->dop || out->aop)) {
+        // Positions that share their row of headings (grids, heat maps) share their sky: check, then evaluate it
+        // once per (heading, ray) for the whole launch.  Both kernels are part of every such call.
+        int* differs = (int*)(base + pl.off_queue + 128);
+        float* tab = (float*)(base + pl.off_skytab);
+        if (yaw) {
+            const long long n = (long long)P * H;
+            const int blocks = (int)std::min<long long>((n + 255) / 256, 4 * device_sms(w->device));
+            heading_rows_kernel<<<blocks, 256, 0, st>>>(yaw, n, (int)H, differs);
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+        const int n = (int)(H * e->R);
+        sky_shared_kernel<<<(n + 127) / 128, 128, 0, st>>>(yaw, (int)H, (int)e->R, e->d_py, e->d_trig,
+                                                          (const double*)(base + pl.off_ftheta), sp,
+                                                          (const SunConst*)(base + pl.off_sun),
+                                                          (const double2*)(base + pl.off_gtab), differs, tab);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        rp.sky_tab = tab, rp.sky_tab_off = differs;
     }
     size_t smem = sizeof(SmemLayout);
     const int eye_kind = (vquat || !e->d_sorted) ? kEyeAny : (pl.global_best ? kEyeLarge : kEyeSmall);

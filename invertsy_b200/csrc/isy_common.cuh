@@ -99,6 +99,8 @@ struct RenderParams {
     const SunConst* sun;     // [1] or [B]
     const double2* sky_gtab; // [2][kGTab + 1] Hermite table of exp(D acos c) for this call's sky (workspace)
     int sun_per_view;
+    const float* sky_tab;    // [3][H][R] Y, DoP, AoP of (heading, ray) when the positions share their headings, else null
+    const int* sky_tab_off;  // ... nonzero if they turned out not to (heading_rows_kernel): the table is not filled
     isy_sky_params sky;
     uint32_t flags;
     isy_outputs out;

@@ -2,6 +2,12 @@
 #pragma once
 #include "isy_shade.cuh"
 
+// 16 bytes per lane in the table-fed final pass (final_pass_tab4): measured slower than the ray-per-lane pass
+// (80 k vs 62 k cycles per position: the pass is bound by the SM's global-store path, not by instruction count)
+#ifndef ISY_TAB4
+#define ISY_TAB4 0
+#endif
+
 namespace isy {
 
 enum { kModeBrute = 0, kModeBins = 1, kModeRaster = 2 };
@@ -31,6 +37,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
     const bool smem_grid = kEye == kEyeSmall && raster_ok;                // its tables stay in shared memory
     const bool banded = kEye == kEyeLarge && raster_ok && rp.Hg > kSmallH;   // scan plan: rendered in bands
 
+    // the sky of (heading, ray) was tabulated for the whole launch (positions share their headings, one sun)
+    const bool sky_tab = kEye == kEyeSmall && !kF64 && rp.sky_tab && *rp.sky_tab_off == 0;
     if (perez) {
         for (int i = tid; i < 2 * (kGTab + 1); i += kThreads) sm.gtab[i] = rp.sky_gtab[i];
         if (tid == 0) sm.sun0 = rp.sun[0];
@@ -178,6 +186,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                     } else {
                         final_pass_fast<false, false, false, 1, false>(rp, sm, gbest, p, grp, Hcur, 0, 0);
                     }
+                } else if (sky_tab) {     // grids: the sky comes from the launch's (heading, ray) table
+                    if (ISY_TAB4 && (rp.R & 3) == 0 && all_out) final_pass_tab4<true>(rp, sm, p, grp, Hcur);
+                    else if (ISY_TAB4 && (rp.R & 3) == 0) final_pass_tab4<false>(rp, sm, p, grp, Hcur);
+                    else if (all_out && Hcur > 1) final_pass_tab<true, kShadeU>(rp, sm, p, grp, Hcur);
+                    else if (Hcur > 1) final_pass_tab<false, kShadeU>(rp, sm, p, grp, Hcur);
+                    else final_pass_tab<false, 1>(rp, sm, p, grp, Hcur);
                 } else if (Hcur > 1 && !rp.sun_per_view && all_out) {   // scans of a small eye, everything asked for
                     final_pass_fast<true, true, true, kShadeU, false>(rp, sm, gbest, p, grp, Hcur, 0, 0);
                 } else if (Hcur == 1) {   // single views, sun sweeps: one heading per trip

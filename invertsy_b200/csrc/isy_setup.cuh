@@ -77,4 +77,37 @@ __global__ void sun_setup_kernel(const double* __restrict__ sun, int n, isy_sky_
     out[b] = c;
 }
 
+// Do all positions of the call look along the same row of headings?  (yaw[p][h] == yaw[0][h] bit for bit; grids
+// and heat maps do.)  *differs is left at 0 if so.  One pass over the P*H headings, a few microseconds.
+__global__ void heading_rows_kernel(const double* __restrict__ yaw, long long n, int H, int* __restrict__ differs) {
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        bad |= __double_as_longlong(yaw[i]) != __double_as_longlong(yaw[i % H]);
+    if (bad) *differs = 1;
+}
+
+// The sky of a yaw-only view under one sun depends on (heading, ray) only: when the positions share their
+// headings it is evaluated once per launch -- here, with the arithmetic of the per-view final pass -- into
+// tab[3][H][R] (Y, DoP, AoP as the float outputs), and the render kernel's final pass copies it.
+__global__ void sky_shared_kernel(const double* __restrict__ yaw, int H, int R, const double* __restrict__ eye_py,
+                                  const double* __restrict__ eye_trig, const double* __restrict__ f_theta,
+                                  isy_sky_params sp, const SunConst* __restrict__ sun,
+                                  const double2* __restrict__ gtab, const int* __restrict__ differs,
+                                  float* __restrict__ tab) {
+    if (*differs) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * R) return;
+    const int h = i / R, r = i - h * R;
+    const double hw = wrap_yaw(yaw ? yaw[h] : 0.0);
+    double hsn, hcs;
+    sincos(hw, &hsn, &hcs);
+    const double4 t4v = *reinterpret_cast<const double4*>(eye_trig + 4 * (size_t)r);
+    const double sy = t4v.z * hcs + t4v.w * hsn, cy = t4v.w * hcs - t4v.z * hsn;   // yaw_e + heading
+    double Y = 0, P = 0, A = CUDART_NAN;
+    sky_eval<false>(sp, sun[0], t4v.y * cy, t4v.y * sy, -t4v.x, eye_py[2 * (size_t)r] + kHalfPi, f_theta[r], Y, P, A,
+                    false, gtab);
+    const size_t plane = (size_t)H * (size_t)R;
+    tab[i] = (float)Y, tab[plane + i] = (float)P, tab[2 * plane + i] = (float)A;
+}
+
 }  // namespace isy

@@ -141,8 +141,9 @@ class Renderer(object):
         return self._workspace
 
     def render(self, pos, yaw=None, quat=None, sun=None, outputs=("rgb", "Y", "dop", "aop"), init_from_sky=False,
-               brute_force=False, f64=False, out=None, sky=None):
+               brute_force=False, f64=False, out=None, sky=None, per_view_sky=False):
         """
+        per_view_sky: evaluate the sky for every view even when all positions share their headings (cross-check).
         pos (P,3) metres; yaw (P,H) radians about +Z *or* quat (P,H,4) full eye orientations;
         sun: None (take the sky's), (2,) or (P,H,2) of (theta_s, phi_s).
         Returns {name: CUDA tensor}: rgb (B,N,3), Y/dop/aop (B,N), hit/depth (B,R), B = P*H.
@@ -176,6 +177,8 @@ class Renderer(object):
             flags |= _lib.FLAG_INIT_FROM_SKY
         if brute_force:
             flags |= _lib.FLAG_BRUTE_FORCE
+        if per_view_sky:
+            flags |= _lib.FLAG_PER_VIEW_SKY
         if f64:
             flags |= _lib.FLAG_OUT_F64
         fdt = torch.float64 if f64 else torch.float32
@@ -223,7 +226,7 @@ class Renderer(object):
         return out
 
     def render_host(self, pos, yaw=None, quat=None, sun=None, outputs=("rgb", "Y", "dop", "aop"),
-                    init_from_sky=False, f64=False, out=None, sky=None):
+                    init_from_sky=False, f64=False, out=None, sky=None, per_view_sky=False):
         """
         End-to-end variant with HOST buffers (isy_render_host): inputs are NumPy / CPU tensors,
         results land in (pinned) host tensors; returns {name: CPU tensor}. Blocking.
@@ -254,6 +257,8 @@ class Renderer(object):
             flags |= _lib.FLAG_INIT_FROM_SKY
         if f64:
             flags |= _lib.FLAG_OUT_F64
+        if per_view_sky:
+            flags |= _lib.FLAG_PER_VIEW_SKY
         fdt = torch.float64 if f64 else torch.float32
         N, R = self.eye.nb_ommatidia, self.eye.nb_rays
         res = {} if out is None else out

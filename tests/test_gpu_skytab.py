@@ -1,0 +1,99 @@
+"""
+GPU: calls whose positions all look along the same row of headings under one sun (grids, heat maps) evaluate the
+sky once per (heading, ray) for the whole launch and copy it into every view.  That path must give what the
+per-view evaluation gives (ISY_FLAG_PER_VIEW_SKY), what the oracle gives, and must step aside as soon as one
+position has a heading of its own.
+"""
+import numpy as np
+import pytest
+import torch
+
+import isy_oracle as o
+from conftest import circ_diff
+
+pytestmark = pytest.mark.gpu
+
+ALL = ("rgb", "hit", "depth", "Y", "dop", "aop")
+
+
+@pytest.fixture(scope="module")
+def ib():
+    import invertsy_b200
+    assert torch.cuda.is_available()
+    return invertsy_b200
+
+
+def _positions(n, seed):
+    rng = np.random.RandomState(seed)
+    return np.c_[rng.uniform(1, 9, n), rng.uniform(1, 9, n), np.full(n, 0.01)]
+
+
+def _same(a, b, sky_tol):
+    for k in a:
+        x, y = a[k].cpu().numpy(), b[k].cpu().numpy()
+        if k in ("rgb", "hit", "depth"):
+            assert np.array_equal(x, y, equal_nan=True), k
+        elif k == "aop":
+            assert circ_diff(x, y).max() <= sky_tol, k
+        else:
+            assert np.abs(x - y).max() <= sky_tol * max(1.0, np.abs(y).max()), k
+
+
+@pytest.mark.parametrize("H,outputs,R", [(36, ALL, 1000), (72, ALL, 1000), (5, ("rgb", "Y", "aop"), 1000), (1, ALL, 1000),
+                                         (7, ("hit", "Y", "dop", "aop"), 999), (36, ALL, 1001), (3, ALL, 36)])
+def test_shared_heading_rows_match_the_per_view_sky(ib, H, outputs, R):
+    # (R a multiple of 4: 16 bytes per lane; otherwise the ray-per-lane pass)
+    world = ib.Seville2009()
+    pitch, yaw = o.fibonacci_eye(R)
+    r = ib.Renderer(world, ib.EyeLayout.from_angles(pitch, yaw), ib.Sky(np.deg2rad(60.), np.pi))
+    P = 160
+    pos = _positions(P, 31)
+    heads = (np.arange(H) * 2 * np.pi / H + 0.3 + np.pi) % (2 * np.pi) - np.pi   # 72 headings: two groups of 36
+    yw = np.tile(heads, (P, 1))
+    tab = r.render(pos, yw, outputs=outputs)
+    ref = r.render(pos, yw, outputs=outputs, per_view_sky=True)
+    torch.cuda.synchronize()
+    r.check()
+    _same(tab, ref, 1e-6)
+    # and against the oracle on a few views
+    omm = o.eye_rotations(pitch, yaw)
+    for b in (0, (P // 2) * H + H // 2, P * H - 1):
+        y, dop, aop = o.sky_render(np.deg2rad(60.), np.pi, o.view_rotations(np.rad2deg(heads[b % H]), omm))
+        assert np.abs(tab["Y"][b].cpu().numpy() - y).max() < 1e-5
+        if "dop" in tab:
+            assert np.abs(tab["dop"][b].cpu().numpy() - dop).max() < 1e-5
+        assert circ_diff(tab["aop"][b].cpu().numpy(), aop).max() < 1e-5
+
+
+def test_one_position_with_its_own_heading_turns_the_table_off(ib):
+    world = ib.Seville2009()
+    pitch, yaw = o.fibonacci_eye(600)
+    r = ib.Renderer(world, ib.EyeLayout.from_angles(pitch, yaw), ib.Sky(np.deg2rad(40.), 1.0))
+    P, H = 150, 12
+    pos = _positions(P, 32)
+    yw = np.tile(np.deg2rad(np.arange(H) * 30. - 180.), (P, 1))
+    yw[P - 1, H - 1] = np.nextafter(yw[P - 1, H - 1], 4.0)      # one ulp is enough
+    yw[77, 3] += 0.5
+    a = r.render(pos, yw, outputs=ALL)
+    b = r.render(pos, yw, outputs=ALL, per_view_sky=True)
+    torch.cuda.synchronize()
+    r.check()
+    for k in ALL:   # the same code path: bit-identical
+        assert np.array_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), equal_nan=True), k
+    omm = o.eye_rotations(pitch, yaw)
+    y, dop, aop = o.sky_render(np.deg2rad(40.), 1.0, o.view_rotations(np.rad2deg(yw[77, 3]), omm))
+    assert np.abs(a["Y"][77 * H + 3].cpu().numpy() - y).max() < 1e-5
+    assert circ_diff(a["aop"][77 * H + 3].cpu().numpy(), aop).max() < 1e-5
+
+
+def test_host_buffer_path_uses_the_same_table(ib):
+    world = ib.Seville2009()
+    pitch, yaw = o.fibonacci_eye(1000)
+    r = ib.Renderer(world, ib.EyeLayout.from_angles(pitch, yaw), ib.Sky(np.deg2rad(60.), np.pi))
+    P, H = 96, 36
+    pos = _positions(P, 33)
+    yw = np.tile(np.deg2rad(np.arange(H) * 10. - 180.), (P, 1))
+    h = r.render_host(pos, yw, outputs=ALL)
+    d = r.render(pos, yw, outputs=ALL, per_view_sky=True)
+    torch.cuda.synchronize()
+    _same({k: h[k] for k in ALL}, {k: d[k] for k in ALL}, 1e-6)
