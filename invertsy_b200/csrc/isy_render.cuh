@@ -8,7 +8,16 @@
 #define ISY_TAB4 0
 #endif
 
+#ifndef ISY_SKY_ROWS_EARLY
+#define ISY_SKY_ROWS_EARLY 1
+#endif
+#ifndef ISY_SKY_COPY_WARPS
+#define ISY_SKY_COPY_WARPS 4
+#endif
+
 namespace isy {
+
+constexpr int kSkyCopyWarps = ISY_SKY_COPY_WARPS;   // warps that copy the sky rows of a position while the rest rasterise
 
 enum { kModeBrute = 0, kModeBins = 1, kModeRaster = 2 };
 
@@ -39,6 +48,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 
     // the sky of (heading, ray) was tabulated for the whole launch (positions share their headings, one sun)
     const bool sky_tab = kEye == kEyeSmall && !kF64 && rp.sky_tab && *rp.sky_tab_off == 0;
+    // ... and its rows are copied into the views by a few warps while the others rasterise (16-byte aligned rows)
+    const bool sky_rows_early = sky_tab && ISY_SKY_ROWS_EARLY && (rp.R & 3) == 0 && raster_ok;
     if (perez) {
         for (int i = tid; i < 2 * (kGTab + 1); i += kThreads) sm.gtab[i] = rp.sky_gtab[i];
         if (tid == 0) sm.sun0 = rp.sun[0];
@@ -151,6 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 #ifdef ISY_PHASE_DETAIL
                 t_walk = clock64();
 #endif
+                if (sky_rows_early) copy_sky_rows(rp, p, grp, Hcur, kWarps - kSkyCopyWarps, kSkyCopyWarps);
                 if (kEye == kEyeSmall ? Hcur > kSmallH : walk_bands) {
                     if (uniform) raster_copies<true>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo);
                     else raster_copies<false>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo);
@@ -186,6 +198,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                     } else {
                         final_pass_fast<false, false, false, 1, false>(rp, sm, gbest, p, grp, Hcur, 0, 0);
                     }
+                } else if (sky_tab && sky_rows_early) {   // grids: the sky rows were copied from the launch's table already
+                    if (all_out && Hcur > 1) final_pass_tab<true, kShadeU, false>(rp, sm, p, grp, Hcur);
+                    else if (Hcur > 1) final_pass_tab<false, kShadeU, false>(rp, sm, p, grp, Hcur);
+                    else final_pass_tab<false, 1, false>(rp, sm, p, grp, Hcur);
                 } else if (sky_tab) {     // grids: the sky comes from the launch's (heading, ray) table
                     if (ISY_TAB4 && (rp.R & 3) == 0 && all_out) final_pass_tab4<true>(rp, sm, p, grp, Hcur);
                     else if (ISY_TAB4 && (rp.R & 3) == 0) final_pass_tab4<false>(rp, sm, p, grp, Hcur);

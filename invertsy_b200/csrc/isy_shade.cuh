@@ -216,7 +216,8 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
 // per-view pass, and this pass copies it: per (ray, heading) one winner look-up, three coalesced
 // table loads, the colour, and the stores of the view.
 // ------------------------------------------------------------------------------------------
-template <bool kAllOut, int kSU>
+// kSky = false: Y / DoP / AoP are not this pass's business (copy_sky_rows wrote them while the copies were rasterised)
+template <bool kAllOut, int kSU, bool kSky = true>
 __device__ void final_pass_tab(const RenderParams& rp, SmemLayout& sm, int p, int grp, int Hcur) {
     const int R = rp.R;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -253,8 +254,10 @@ __device__ void final_pass_tab(const RenderParams& rp, SmemLayout& sm, int p, in
             for (int q = 0; q < kSU; ++q) {
                 const int hh = min(hh0 + q, hend - 1);
                 id[q] = (unsigned)sm.ras.best[sm.ras.hinv[hh] * R + pos];
-                const size_t ti = toff + (size_t)(hh - hh0) * tstride;
-                Y[q] = __ldg(tY + ti), P[q] = __ldg(tP + ti), A[q] = __ldg(tA + ti);
+                if (kSky) {
+                    const size_t ti = toff + (size_t)(hh - hh0) * tstride;
+                    Y[q] = __ldg(tY + ti), P[q] = __ldg(tP + ti), A[q] = __ldg(tA + ti);
+                }
             }
 #pragma unroll
             for (int q = 0; q < kSU; ++q) {
@@ -274,11 +277,47 @@ __device__ void final_pass_tab(const RenderParams& rp, SmemLayout& sm, int p, in
                 if (valid) {
                     if (kAllOut || rp.out.hit) __stcs(rp.out.hit + i, hit);
                     if (kAllOut || o_depth) __stcs(o_depth + i, depth);
-                    if (kAllOut || o_Y) __stcs(o_Y + i, Y[q]);
-                    if (kAllOut || o_P) __stcs(o_P + i, P[q]);
-                    if (kAllOut || o_A) __stcs(o_A + i, A[q]);
+                    if (kSky) {
+                        if (kAllOut || o_Y) __stcs(o_Y + i, Y[q]);
+                        if (kAllOut || o_P) __stcs(o_P + i, P[q]);
+                        if (kAllOut || o_A) __stcs(o_A + i, A[q]);
+                    }
                 }
             }
+        }
+    }
+}
+
+// Y / DoP / AoP of the views of (position p, heading group grp) when the launch has a sky table: the rows of the table
+// ARE the rows of those views.  Copied 16 bytes per lane (R a multiple of 4: rows are 16-byte aligned), four
+// independent loads in flight per lane, by the warps [w0, w0 + nw) only: it has nothing to do with the winners, so a
+// few warps do it while the others rasterise -- the SM's store path (32 B/clk, microbench/store_bw.cu) is idle then,
+// and it is what bounds the final pass.
+__device__ void copy_sky_rows(const RenderParams& rp, int p, int grp, int Hcur, int w0, int nw) {
+    const int R4 = rp.R >> 2;
+    const int lane = threadIdx.x & 31, warp = (int)(threadIdx.x >> 5) - w0;
+    if (warp < 0 || warp >= nw) return;
+    const size_t plane4 = (size_t)rp.H * (size_t)R4;
+    const float4* const tab4 = reinterpret_cast<const float4*>(rp.sky_tab);
+    float4* const dY = reinterpret_cast<float4*>(rp.out.Y), * const dP = reinterpret_cast<float4*>(rp.out.dop),
+                * const dA = reinterpret_cast<float4*>(rp.out.aop);
+    constexpr int kU = 4;                                   // loads in flight per lane
+    for (int row = warp; row < 3 * Hcur; row += nw) {       // (plane, heading): one row of R4 float4
+        const int k = row / Hcur, hg = grp + (row - k * Hcur) * rp.ngroups;
+        float4* const dk = k == 0 ? dY : (k == 1 ? dP : dA);
+        if (!dk) continue;
+        const float4* const src = tab4 + (size_t)k * plane4 + (size_t)hg * R4;
+        float4* const dst = dk + ((size_t)p * rp.H + hg) * (size_t)R4;
+        for (int c0 = lane; c0 < R4; c0 += 32 * kU) {
+            float4 v[kU];
+#pragma unroll
+            for (int q = 0; q < kU; ++q) {
+                v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + 32 * q < R4) v[q] = __ldg(src + c0 + 32 * q);
+            }
+#pragma unroll
+            for (int q = 0; q < kU; ++q)
+                if (c0 + 32 * q < R4) __stcs(dst + c0 + 32 * q, v[q]);
         }
     }
 }
