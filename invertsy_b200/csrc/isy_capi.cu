@@ -297,8 +297,8 @@ struct Plan {
     int Hg, ngroups;
     int slab_cap;
     bool global_best;
-    size_t off_queue, off_status, off_sun, off_ftheta, off_gtab, off_vis, off_entry, off_exact, off_best, off_skytab, total;
-    bool sky_tab;   // room for the launch-wide (heading, ray) sky table
+    size_t off_queue, off_status, off_sun, off_ftheta, off_gtab, off_vis, off_entry, off_exact, off_best, off_skytab, off_rowbg, total;
+    bool rows;      // room for the launch-wide row templates, sky table and patch queues (isy_shade.cuh)
 };
 
 int device_sms(int device) {
@@ -312,7 +312,7 @@ int device_sms(int device) {
     return sms;
 }
 
-constexpr int64_t kSkyTabMinP = 16;            // fewer positions than this do not repay the table
+constexpr int64_t kRowsMinP = 16;              // fewer positions than this do not repay the set-up launches
 constexpr size_t kSkyTabMaxBytes = 16u << 20;  // ... and it should stay L2-resident
 
 Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
@@ -349,9 +349,10 @@ Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
     pl.off_entry = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(Entry));
     pl.off_exact = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(Exact));
     pl.off_best = off, off += pl.global_best ? align_up((size_t)pl.grid * e->R * sizeof(unsigned int)) : 0;
-    // launch-wide sky table of scans whose positions share their headings (small eyes, a few MB at most)
-    pl.sky_tab = !pl.global_best && P >= kSkyTabMinP && (size_t)H * e->R * 3 * sizeof(float) <= kSkyTabMaxBytes;
-    pl.off_skytab = off, off += pl.sky_tab ? align_up((size_t)H * e->R * 3 * sizeof(float)) : 0;
+    // launch-wide row templates of small eyes: sky table [3][H][R], template rows [5R]
+    pl.rows = !pl.global_best && P >= kRowsMinP && (size_t)H * e->R * 3 * sizeof(float) <= kSkyTabMaxBytes;
+    pl.off_skytab = off, off += pl.rows ? align_up((size_t)H * e->R * 3 * sizeof(float)) : 0;
+    pl.off_rowbg = off, off += pl.rows ? align_up((size_t)e->R * 5 * sizeof(float)) : 0;
     pl.total = off;
     return pl;
 }
@@ -445,30 +446,42 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
         }
     }
     const int eye_kind0 = (vquat || !e->d_sorted) ? kEyeAny : (pl.global_best ? kEyeLarge : kEyeSmall);
-    if (pl.sky_tab && eye_kind0 == kEyeSmall && sp.kind == ISY_SKY_PEREZ && !rp.sun_per_view && !init_c &&
-        !(flags & (ISY_FLAG_OUT_F64 | ISY_FLAG_INIT_FROM_SKY | ISY_FLAG_BRUTE_FORCE | ISY_FLAG_PER_VIEW_SKY)) && e->S == 1 &&
-        (out->Y || out->dop || out->aop)) {
-        // Positions that share their row of headings (grids, heat maps) share their sky: check, then evaluate it
-        // once per (heading, ray) for the whole launch.  Both kernels are part of every such call.
+    if (pl.rows && eye_kind0 == kEyeSmall && !init_c && e->S == 1 && !(sp.kind == ISY_SKY_PEREZ && rp.sun_per_view) &&
+        !(flags & (ISY_FLAG_OUT_F64 | ISY_FLAG_INIT_FROM_SKY | ISY_FLAG_BRUTE_FORCE | ISY_FLAG_PER_VIEW_SKY))) {
+        // Rows mode (isy_shade.cuh): template rows are streamed into the views while the copies are rasterised and only
+        // the rays that hit something are patched afterwards.  Under a Perez sky that needs every position to look
+        // along the same row of headings (grids, heat maps): checked here, on the device, in every such call; the
+        // sky is then evaluated once per (heading, ray) for the whole launch.
         int* differs = (int*)(base + pl.off_queue + 128);
         float* tab = (float*)(base + pl.off_skytab);
-        if (yaw) {
-            const long long n = (long long)P * H;
-            const int blocks = (int)std::min<long long>((n + 255) / 256, 4 * device_sms(w->device));
-            heading_rows_kernel<<<blocks, 256, 0, st>>>(yaw, n, (int)H, differs);
+        float* bg = (float*)(base + pl.off_rowbg);
+        const bool want_sky = out->Y || out->dop || out->aop;
+        if (sp.kind == ISY_SKY_PEREZ && want_sky) {
+            if (yaw) {
+                const long long n = (long long)P * H;
+                const int blocks = (int)std::min<long long>((n + 255) / 256, 4 * device_sms(w->device));
+                heading_rows_kernel<<<blocks, 256, 0, st>>>(yaw, n, (int)H, differs);
+                g_launches++;
+                CUDA_TRY(cudaGetLastError());
+            }
+            const int n = (int)(H * e->R);
+            sky_shared_kernel<<<(n + 127) / 128, 128, 0, st>>>(yaw, (int)H, (int)e->R, e->d_py, e->d_trig,
+                                                              (const double*)(base + pl.off_ftheta), sp,
+                                                              (const SunConst*)(base + pl.off_sun),
+                                                              (const double2*)(base + pl.off_gtab), differs, tab);
             g_launches++;
             CUDA_TRY(cudaGetLastError());
+            rp.sky_rows_h = (int)H;
+        } else if (sp.kind == ISY_SKY_UNIFORM && want_sky) {
+            rp.sky_rows_h = 1;
         }
-        const int n = (int)(H * e->R);
-        sky_shared_kernel<<<(n + 127) / 128, 128, 0, st>>>(yaw, (int)H, (int)e->R, e->d_py, e->d_trig,
-                                                          (const double*)(base + pl.off_ftheta), sp,
-                                                          (const SunConst*)(base + pl.off_sun),
-                                                          (const double2*)(base + pl.off_gtab), differs, tab);
+        row_templates_kernel<<<(unsigned)((e->R + 127) / 128), 128, 0, st>>>(e->d_py, (int)e->R, sp.kind == ISY_SKY_UNIFORM && want_sky,
+                                                                            (float)sp.luminance, bg, tab);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
-        rp.sky_tab = tab, rp.sky_tab_off = differs;
+        rp.sky_tab = tab, rp.sky_tab_off = differs, rp.row_bg = bg;
     }
-    size_t smem = sizeof(SmemLayout);
+    const size_t smem = rp.row_bg ? sizeof(SmemLayout) : kSmemBase;   // (rows mode adds the tail of the layout)
     const int eye_kind = (vquat || !e->d_sorted) ? kEyeAny : (pl.global_best ? kEyeLarge : kEyeSmall);
     const bool f64 = (flags & ISY_FLAG_OUT_F64) != 0;
 #define ISY_LAUNCH(F64, EYE)                                                                                              \

@@ -99,8 +99,12 @@ struct RenderParams {
     const SunConst* sun;     // [1] or [B]
     const double2* sky_gtab; // [2][kGTab + 1] Hermite table of exp(D acos c) for this call's sky (workspace)
     int sun_per_view;
-    const float* sky_tab;    // [3][H][R] Y, DoP, AoP of (heading, ray) when the positions share their headings, else null
-    const int* sky_tab_off;  // ... nonzero if they turned out not to (heading_rows_kernel): the table is not filled
+    // row templates (isy_shade.cuh, "Row templates + patches"); row_bg == null: not set up for this launch
+    const float* sky_tab;    // [3][sky_rows_h][R] Y, DoP, AoP rows: per heading (Perez sky, positions share their
+                             // headings) or one constant row each (uniform sky)
+    int sky_rows_h;          // H, 1, or 0 = no sky outputs
+    const int* sky_tab_off;  // nonzero: the positions turned out NOT to share their headings (heading_rows_kernel)
+    const float* row_bg;     // [R] hit = -1 | [R] depth = NaN | [3R] ground colour / NaN by the ray's pitch
     isy_sky_params sky;
     uint32_t flags;
     isy_outputs out;

@@ -1,5 +1,6 @@
 // Tunables and the shared-memory layout of the render kernel.
 #pragma once
+#include <cstddef>
 #include "isy_common.cuh"
 
 namespace isy {
@@ -63,8 +64,14 @@ struct SmemLayout {
         SmemBins bins;
         SmemRaster ras;
     };
+    // rows mode only (isy_shade.cuh): what final_pass_patch looks up per hit, so that it issues no global load.
+    // Launches that are not in rows mode do not allocate this tail (kSmemBase bytes of dynamic shared memory).
+    float rgb[kMaxE * 3];                         // colour of each copy's triangle
+    unsigned short sorted_ray16[kGridRaysSmem];   // ray index of each pitch-sorted position
 };
-static_assert(sizeof(SmemLayout) <= 192 * 1024, "leave some of the 228 KB for L1");
+constexpr size_t kSmemBase = offsetof(SmemLayout, rgb);
+static_assert(kSmemBase <= 192 * 1024, "leave some of the 228 KB for L1");
+static_assert(sizeof(SmemLayout) <= 224 * 1024, "rows mode: 227 KB per CTA is the limit");
 
 struct RayOut {
     double r, g, b;

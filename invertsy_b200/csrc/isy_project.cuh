@@ -67,6 +67,10 @@ __device__ __forceinline__ void emit_copy(const double th[3], const double ph[3]
     }
 }
 
+constexpr int kStage = 1792;   // visible triangles whose vertices are staged in shared memory (63 KB)
+static_assert(9 * kStage * sizeof(float) <= sizeof(unsigned short) * kBestCap, "the stage must fit the winner buffer");
+static_assert(9 * kStage * sizeof(float) <= sizeof(SmemBins), "... and the bin lists (built after the projection)");
+
 template <bool kRuns>
 __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* entries, Exact* exacts,
                                 SmemLayout& sm, int* s_count, int* s_nent, int* s_band, long long* t_mid = nullptr) {
@@ -78,6 +82,9 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
     const double px = rp.pos[3 * p + 0], py = rp.pos[3 * p + 1], pz = rp.pos[3 * p + 2];
     const double h = rp.horizon;
     const double h2_max = rp.horizon_sq_max;     // sqrt_rn(s) <= horizon  <=>  s <= h2_max (set by the host)
+    // vertices of the visible triangles, cull -> projection: 9 planes of kStage floats over the winner buffer / bin
+    // lists, which nothing uses before this position is rasterised
+    float* const stage = reinterpret_cast<float*>(&sm.ras);
 
     if (tid == 0) {
         *s_count = 0;
@@ -154,7 +161,7 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
             }
         }
         double s3[2][3];
-        float vx[2][3], vy[2][3];   // raw xy of the vertices: the cell test below files them like the host did
+        float vx[2][3], vy[2][3], vzz[2][3];   // raw vertices: the cell test below files xy like the host did
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int t = (int)(packed[u] & 0x3fffffffu);
@@ -162,8 +169,8 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
             for (int k = 0; k < 3; ++k) {
                 vx[u][k] = __ldg(rp.tri_planes + (size_t)(3 * k + 0) * rp.T + t);
                 vy[u][k] = __ldg(rp.tri_planes + (size_t)(3 * k + 1) * rp.T + t);
-                const float vz = __ldg(rp.tri_planes + (size_t)(3 * k + 2) * rp.T + t);
-                s3[u][k] = norm2_rn((double)vx[u][k] - px, (double)vy[u][k] - py, (double)vz - pz);   // world.py:94-96
+                vzz[u][k] = __ldg(rp.tri_planes + (size_t)(3 * k + 2) * rp.T + t);
+                s3[u][k] = norm2_rn((double)vx[u][k] - px, (double)vy[u][k] - py, (double)vzz[u][k] - pz);   // world.py:94-96
             }
         }
 #if defined(ISY_PHASE_DETAIL) && ISY_PHASE_DETAIL == 3
@@ -194,6 +201,14 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
                 if (visible) {
                     int slot = basei + __popc(m & ((1u << lane) - 1));
                     if (slot < rp.slab_cap) vis[slot] = t;
+                    if (slot < kStage) {   // the projection takes the vertices from here instead of gathering them again
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            stage[(3 * k + 0) * kStage + slot] = vx[u][k];
+                            stage[(3 * k + 1) * kStage + slot] = vy[u][k];
+                            stage[(3 * k + 2) * kStage + slot] = vzz[u][k];
+                        }
+                    }
                 }
             }
         }
@@ -216,7 +231,19 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
     for (int j = tid; j < V; j += kThreads) {
         int t = vis[j];
         double v[3][3];
-        load_vertices(rp.tri_planes, rp.T, t, px, py, pz, v);
+        if (j < kStage) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                v[k][0] = (double)stage[(3 * k + 0) * kStage + j] - px;   // world.py:94
+                v[k][1] = (double)stage[(3 * k + 1) * kStage + j] - py;
+                v[k][2] = (double)stage[(3 * k + 2) * kStage + j] - pz;
+            }
+        } else {
+            load_vertices(rp.tri_planes, rp.T, t, px, py, pz, v);
+        }
+        float col[3] = {0.f, 0.f, 0.f};
+        if (rp.row_bg) col[0] = __ldg(rp.tri_rgb + 3 * (size_t)t), col[1] = __ldg(rp.tri_rgb + 3 * (size_t)t + 1),
+                       col[2] = __ldg(rp.tri_rgb + 3 * (size_t)t + 2);   // rows mode: final_pass_patch reads it from shared memory
         double smin = fmin(norm2_rn(v[0][0], v[0][1], v[0][2]),
                            fmin(norm2_rn(v[1][0], v[1][1], v[1][2]), norm2_rn(v[2][0], v[2][1], v[2][2])));
         double dist = __dsqrt_rn(smin);
@@ -232,6 +259,13 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
         }
         bool seam = (phmax - phmin) >= kPi;                                               // :116
         int slot = atomicAdd(s_nent, seam ? 2 : 1);
+        if (rp.row_bg) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (slot < kMaxE) sm.rgb[3 * slot + c] = col[c];
+                if (seam && slot + 1 < kMaxE) sm.rgb[3 * (slot + 1) + c] = col[c];
+            }
+        }
         if (slot + (seam ? 2 : 1) <= rp.slab_cap) {
             if (seam) {
                 double p1[3], p2[3];

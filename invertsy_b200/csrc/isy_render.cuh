@@ -2,22 +2,13 @@
 #pragma once
 #include "isy_shade.cuh"
 
-// 16 bytes per lane in the table-fed final pass (final_pass_tab4): measured slower than the ray-per-lane pass
-// (80 k vs 62 k cycles per position: the pass is bound by the SM's global-store path, not by instruction count)
-#ifndef ISY_TAB4
-#define ISY_TAB4 0
-#endif
-
-#ifndef ISY_SKY_ROWS_EARLY
-#define ISY_SKY_ROWS_EARLY 1
-#endif
-#ifndef ISY_SKY_COPY_WARPS
-#define ISY_SKY_COPY_WARPS 4
+#ifndef ISY_COPY_WARPS
+#define ISY_COPY_WARPS 4
 #endif
 
 namespace isy {
 
-constexpr int kSkyCopyWarps = ISY_SKY_COPY_WARPS;   // warps that copy the sky rows of a position while the rest rasterise
+constexpr int kCopyWarps = ISY_COPY_WARPS;   // warps that stream the template rows of a position while the rest rasterise
 
 enum { kModeBrute = 0, kModeBins = 1, kModeRaster = 2 };
 
@@ -46,14 +37,15 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
     const bool smem_grid = kEye == kEyeSmall && raster_ok;                // its tables stay in shared memory
     const bool banded = kEye == kEyeLarge && raster_ok && rp.Hg > kSmallH;   // scan plan: rendered in bands
 
-    // the sky of (heading, ray) was tabulated for the whole launch (positions share their headings, one sun)
-    const bool sky_tab = kEye == kEyeSmall && !kF64 && rp.sky_tab && *rp.sky_tab_off == 0;
-    // ... and its rows are copied into the views by a few warps while the others rasterise (16-byte aligned rows)
-    const bool sky_rows_early = sky_tab && ISY_SKY_ROWS_EARLY && (rp.R & 3) == 0 && raster_ok;
+    // row templates + patches (isy_shade.cuh): the host set the launch up for it; a Perez sky also needs every
+    // position to look along the same headings, which heading_rows_kernel has just checked
+    const bool rows_mode = kEye == kEyeSmall && !kF64 && rp.row_bg && raster_ok && (!perez || *rp.sky_tab_off == 0);
     if (perez) {
         for (int i = tid; i < 2 * (kGTab + 1); i += kThreads) sm.gtab[i] = rp.sky_gtab[i];
         if (tid == 0) sm.sun0 = rp.sun[0];
     }
+    if (kEye == kEyeSmall && rp.row_bg)   // rows mode (the tail of the layout is allocated)
+        for (int i = tid; i < rp.R; i += kThreads) sm.sorted_ray16[i] = (unsigned short)rp.grid_sorted_ray[i];
     if (smem_grid) {   // the eye's static tables: nothing else uses this memory in a yaw-only launch
         for (int i = tid; i <= kPitchLut; i += kThreads) sm.ras.plut[i] = rp.grid_plut[i];
         for (int i = tid; i < rp.R; i += kThreads) {
@@ -162,7 +154,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 #ifdef ISY_PHASE_DETAIL
                 t_walk = clock64();
 #endif
-                if (sky_rows_early) copy_sky_rows(rp, p, grp, Hcur, kWarps - kSkyCopyWarps, kSkyCopyWarps);
+                if (rows_mode) {
+                    if ((rp.R & 3) == 0) copy_rows<float4>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
+                    else copy_rows<float>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
+                }
                 if (kEye == kEyeSmall ? Hcur > kSmallH : walk_bands) {
                     if (uniform) raster_copies<true>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo);
                     else raster_copies<false>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo);
@@ -198,16 +193,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                     } else {
                         final_pass_fast<false, false, false, 1, false>(rp, sm, gbest, p, grp, Hcur, 0, 0);
                     }
-                } else if (sky_tab && sky_rows_early) {   // grids: the sky rows were copied from the launch's table already
-                    if (all_out && Hcur > 1) final_pass_tab<true, kShadeU, false>(rp, sm, p, grp, Hcur);
-                    else if (Hcur > 1) final_pass_tab<false, kShadeU, false>(rp, sm, p, grp, Hcur);
-                    else final_pass_tab<false, 1, false>(rp, sm, p, grp, Hcur);
-                } else if (sky_tab) {     // grids: the sky comes from the launch's (heading, ray) table
-                    if (ISY_TAB4 && (rp.R & 3) == 0 && all_out) final_pass_tab4<true>(rp, sm, p, grp, Hcur);
-                    else if (ISY_TAB4 && (rp.R & 3) == 0) final_pass_tab4<false>(rp, sm, p, grp, Hcur);
-                    else if (all_out && Hcur > 1) final_pass_tab<true, kShadeU>(rp, sm, p, grp, Hcur);
-                    else if (Hcur > 1) final_pass_tab<false, kShadeU>(rp, sm, p, grp, Hcur);
-                    else final_pass_tab<false, 1>(rp, sm, p, grp, Hcur);
+                } else if (rows_mode) {   // the template rows are on their way: only the rays that hit something are left
+                    final_pass_patch(rp, sm, p, grp, Hcur);
                 } else if (Hcur > 1 && !rp.sun_per_view && all_out) {   // scans of a small eye, everything asked for
                     final_pass_fast<true, true, true, kShadeU, false>(rp, sm, gbest, p, grp, Hcur, 0, 0);
                 } else if (Hcur == 1) {   // single views, sun sweeps: one heading per trip

@@ -110,4 +110,21 @@ __global__ void sky_shared_kernel(const double* __restrict__ yaw, int H, int R, 
     tab[i] = (float)Y, tab[plane + i] = (float)P, tab[2 * plane + i] = (float)A;
 }
 
+// Template rows of a launch in rows mode (isy_shade.cuh): what a ray that hits nothing gets -- hit = -1, depth = NaN,
+// the ground colour or NaN by its own pitch (world.py:80, :90) -- and, under a uniform sky, the three constant sky
+// rows (sky.py:77-79: y = luminance, p = 0, a = NaN).
+__global__ void row_templates_kernel(const double* __restrict__ eye_py, int R, int uniform_sky, float luminance,
+                                     float* __restrict__ bg, float* __restrict__ sky_rows) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float nanf_ = __int_as_float(0x7fc00000);
+    bg[r] = __int_as_float(-1);
+    bg[R + r] = nanf_;
+    const bool ground = eye_py[2 * (size_t)r] >= 0;
+    bg[2 * (size_t)R + 3 * r + 0] = ground ? (float)(229.0 / 255.0) : nanf_;
+    bg[2 * (size_t)R + 3 * r + 1] = ground ? (float)(183.0 / 255.0) : nanf_;
+    bg[2 * (size_t)R + 3 * r + 2] = ground ? (float)(90.0 / 255.0) : nanf_;
+    if (uniform_sky) sky_rows[r] = luminance, sky_rows[R + r] = 0.f, sky_rows[2 * (size_t)R + r] = nanf_;
+}
+
 }  // namespace isy

@@ -1,8 +1,9 @@
 """
-GPU: calls whose positions all look along the same row of headings under one sun (grids, heat maps) evaluate the
-sky once per (heading, ray) for the whole launch and copy it into every view.  That path must give what the
-per-view evaluation gives (ISY_FLAG_PER_VIEW_SKY), what the oracle gives, and must step aside as soon as one
-position has a heading of its own.
+GPU: rows mode of the small-eye kernel.  Template rows (what a ray that hits nothing gets; the sky of a uniform sky;
+under a Perez sky the sky of (heading, ray), evaluated once per launch when all positions look along the same row of
+headings under one sun -- grids, heat maps) are streamed into the views while the copies are rasterised, and only the
+rays that hit something are patched afterwards.  It must give what the per-view passes give
+(ISY_FLAG_PER_VIEW_SKY), what the oracle gives, and must step aside as soon as one position has a heading of its own.
 """
 import numpy as np
 import pytest
@@ -97,3 +98,41 @@ def test_host_buffer_path_uses_the_same_table(ib):
     d = r.render(pos, yw, outputs=ALL, per_view_sky=True)
     torch.cuda.synchronize()
     _same({k: h[k] for k in ALL}, {k: d[k] for k in ALL}, 1e-6)
+
+
+@pytest.mark.parametrize("sky", ["uniform", "none"])
+@pytest.mark.parametrize("H,R", [(36, 1000), (3, 250), (72, 999)])
+def test_uniform_and_no_sky_rows_match_the_per_view_passes(ib, sky, H, R):
+    world = ib.Seville2009()
+    pitch, yaw = o.fibonacci_eye(R)
+    r = ib.Renderer(world, ib.EyeLayout.from_angles(pitch, yaw), ib.UniformSky(10.) if sky == "uniform" else None)
+    P = 150
+    pos = _positions(P, 34)
+    rng = np.random.RandomState(3)
+    yw = rng.uniform(-np.pi, np.pi, (P, H))          # every position its own headings: no sky table involved
+    outs = ALL if sky == "uniform" else ("rgb", "hit", "depth")
+    a = r.render(pos, yw, outputs=outs)
+    b = r.render(pos, yw, outputs=outs, per_view_sky=True)
+    torch.cuda.synchronize()
+    r.check()
+    for k in outs:
+        assert np.array_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), equal_nan=True), k
+    if sky == "uniform":
+        assert torch.all(a["Y"] == 10.) and torch.all(a["dop"] == 0.) and torch.all(torch.isnan(a["aop"]))
+    assert (a["hit"] >= 0).float().mean() > 0.01
+
+
+def test_empty_and_sparse_worlds_in_rows_mode(ib):
+    # positions that see nothing at all (no copies, stale tile) and the sparse world
+    world = ib.SimpleWorld()
+    pitch, yaw = o.fibonacci_eye(1000)
+    r = ib.Renderer(world, ib.EyeLayout.from_angles(pitch, yaw), ib.Sky(np.deg2rad(30.), 0.5))
+    P, H = 64, 8
+    rng = np.random.RandomState(4)
+    pos = np.c_[rng.uniform(-30, 40, P), rng.uniform(-30, 40, P), np.full(P, 0.01)]   # most of them far outside
+    yw = np.tile(np.deg2rad(np.arange(H) * 45. - 180.), (P, 1))
+    a = r.render(pos, yw, outputs=ALL)
+    b = r.render(pos, yw, outputs=ALL, per_view_sky=True)
+    torch.cuda.synchronize()
+    r.check()
+    _same(a, b, 1e-6)

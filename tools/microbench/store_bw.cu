@@ -15,7 +15,18 @@ __global__ void __launch_bounds__(kThreads, 1) store_kernel(float* out, size_t b
     __syncthreads();
     unsigned char* base = reinterpret_cast<unsigned char*>(out) + (size_t)blockIdx.x * bytes_per_cta;
     const long long t0 = clock64();
-    if (kVariant < 4) {
+    if (kVariant == 5 || kVariant == 6) {
+        // 5: 4 B per lane, every warp store starting 32 B into a 128-byte line (rows of 1000 floats are like that)
+        // 6: the colour pattern -- three stores of 4 B per lane at a 12-byte stride (96 floats per warp trip)
+        const size_t per_warp_trip = kVariant == 5 ? 128 : 384;
+        for (size_t off = (size_t)warp * per_warp_trip; off + per_warp_trip + 32 <= bytes_per_cta; off += (size_t)warps * per_warp_trip) {
+            if (kVariant == 5) __stcs(reinterpret_cast<float*>(base + 32 + off) + lane, 1.f);
+            else {
+                float* q = reinterpret_cast<float*>(base + off) + 3 * lane;
+                __stcs(q, 1.f), __stcs(q + 1, 2.f), __stcs(q + 2, 3.f);
+            }
+        }
+    } else if (kVariant < 4) {
         constexpr int kB = (kVariant < 2) ? 16 : 4;                 // bytes per lane
         const size_t per_warp_trip = 32 * kB;
         for (size_t off = (size_t)warp * per_warp_trip; off < bytes_per_cta; off += (size_t)warps * per_warp_trip) {
@@ -69,13 +80,15 @@ int main() {
     unsigned long long* d_cycles;
     cudaMalloc(&buf, bytes_per_cta * 148);
     cudaMalloc(&d_cycles, 148 * sizeof(unsigned long long));
-    for (int ctas : {148, 37, 1}) {
+    for (int ctas : {148, 1}) {
         run<0>("st.global.v4 (16 B/lane)", buf, bytes_per_cta, ctas, 4096, d_cycles);
         run<1>("st.global.cs.v4 (16 B/lane, streaming)", buf, bytes_per_cta, ctas, 4096, d_cycles);
         run<2>("st.global.b32 (4 B/lane)", buf, bytes_per_cta, ctas, 4096, d_cycles);
         run<3>("st.global.cs.b32 (4 B/lane, streaming)", buf, bytes_per_cta, ctas, 4096, d_cycles);
         run<4>("TMA bulk smem->global", buf, bytes_per_cta, ctas, 4096, d_cycles);
         run<4>("TMA bulk smem->global", buf, bytes_per_cta, ctas, 16384, d_cycles);
+        run<5>("st.global.cs.b32, 32 B off the line", buf, bytes_per_cta, ctas, 4096, d_cycles);
+        run<6>("3 x st.global.cs.b32, 12-byte stride", buf, bytes_per_cta, ctas, 4096, d_cycles);
     }
     return 0;
 }
