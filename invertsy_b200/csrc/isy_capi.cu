@@ -297,7 +297,8 @@ struct Plan {
     int Hg, ngroups;
     int slab_cap;
     bool global_best;
-    size_t off_queue, off_status, off_sun, off_ftheta, off_gtab, off_vis, off_entry, off_exact, off_best, off_skytab, off_rowbg, total;
+    size_t off_queue, off_status, off_sun, off_ftheta, off_gtab, off_vis, off_entry, off_exact, off_best, off_skytab, off_rowbg, off_stage, total;
+    int stage_cap;
     bool rows;      // room for the launch-wide row templates, sky table and patch queues (isy_shade.cuh)
 };
 
@@ -353,6 +354,8 @@ Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
     pl.rows = !pl.global_best && P >= kRowsMinP && (size_t)H * e->R * 3 * sizeof(float) <= kSkyTabMaxBytes;
     pl.off_skytab = off, off += pl.rows ? align_up((size_t)H * e->R * 3 * sizeof(float)) : 0;
     pl.off_rowbg = off, off += pl.rows ? align_up((size_t)e->R * 5 * sizeof(float)) : 0;
+    pl.stage_cap = std::min(pl.slab_cap, 4096);   // vertices of a position culled ahead (9 planes per CTA)
+    pl.off_stage = off, off += pl.rows ? align_up((size_t)pl.grid * 9 * pl.stage_cap * sizeof(float)) : 0;
     pl.total = off;
     return pl;
 }
@@ -480,6 +483,7 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
         g_launches++;
         CUDA_TRY(cudaGetLastError());
         rp.sky_tab = tab, rp.sky_tab_off = differs, rp.row_bg = bg;
+        rp.slab_stage = (float*)(base + pl.off_stage), rp.stage_cap = pl.stage_cap;
     }
     const size_t smem = rp.row_bg ? sizeof(SmemLayout) : kSmemBase;   // (rows mode adds the tail of the layout)
     const int eye_kind = (vquat || !e->d_sorted) ? kEyeAny : (pl.global_best ? kEyeLarge : kEyeSmall);

@@ -115,6 +115,8 @@ struct RenderParams {
     int* slab_vis;           // [grid][slab_cap] visible triangle ids
     Entry* slab_entry;       // [grid][slab_cap]
     Exact* slab_exact;       // [grid][slab_cap]
+    float* slab_stage;       // [grid][9][stage_cap] vertices of the visible triangles of a position culled ahead (rows mode) or null
+    int stage_cap;
     unsigned int* slab_best; // [grid][R] winner buffer in global memory when a heading does not fit smem, else null
     int slab_cap;
     int Hg, ngroups;         // headings per group, number of groups (H = sum of group sizes)

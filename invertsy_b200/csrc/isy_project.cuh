@@ -67,34 +67,32 @@ __device__ __forceinline__ void emit_copy(const double th[3], const double ph[3]
     }
 }
 
-constexpr int kStage = 1792;   // visible triangles whose vertices are staged in shared memory (63 KB)
-static_assert(9 * kStage * sizeof(float) <= sizeof(unsigned short) * kBestCap, "the stage must fit the winner buffer");
-static_assert(9 * kStage * sizeof(float) <= sizeof(SmemBins), "... and the bin lists (built after the projection)");
+// scratch of one cull in shared memory
+struct CullScratch {
+    int count;                         // visible triangles so far
+    unsigned int rowbeg[16], rowoff[17];
+};
 
-template <bool kRuns>
-__device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* entries, Exact* exacts,
-                                SmemLayout& sm, int* s_count, int* s_nent, int* s_band, long long* t_mid = nullptr) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (rp.T == 0) {   // no world (sky-only calls): nothing to cull
-        if (tid == 0) s_band[0] = float_key(CUDART_INF_F), s_band[1] = float_key(-CUDART_INF_F);
-        return 0;
-    }
+// barrier among the kNT threads that run a cull: the CTA (kBar = 0) or a named barrier
+template <int kNT, int kBar>
+__device__ __forceinline__ void group_sync() {
+    if (kBar == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"n"(kBar), "n"(kNT) : "memory");
+}
+
+// A1: the visible triangles of position p -> vis[] (triangle ids) and stage[] (their vertices, 9 planes of stage_cap
+// floats; shared or global memory), by a group of kNT threads (gt = this thread's index in it; the group starts at
+// a warp boundary).  Returns their number.  The CTA runs it for the position it is about to render; in rows mode the
+// copy warps also run it for the NEXT position while the others rasterise (vis / stage in the workspace), so that
+// the latency of its three dependent trips to L2 (cell rows -> cell lists -> vertices) is off the critical path.
+template <int kNT, int kBar>
+__device__ int cull_position(const RenderParams& rp, int p, int gt, int* vis, float* stage, int stage_cap, CullScratch& sc) {
+    const int lane = gt & 31;
     const double px = rp.pos[3 * p + 0], py = rp.pos[3 * p + 1], pz = rp.pos[3 * p + 2];
     const double h = rp.horizon;
     const double h2_max = rp.horizon_sq_max;     // sqrt_rn(s) <= horizon  <=>  s <= h2_max (set by the host)
-    // vertices of the visible triangles, cull -> projection: 9 planes of kStage floats over the winner buffer / bin
-    // lists, which nothing uses before this position is rasterised
-    float* const stage = reinterpret_cast<float*>(&sm.ras);
-
-    if (tid == 0) {
-        *s_count = 0;
-        *s_nent = 0;
-        sm.order_n[0] = 0, sm.order_n[1] = 0;
-        s_band[0] = float_key(CUDART_INF_F);
-        s_band[1] = float_key(-CUDART_INF_F);
-    }
-    __syncthreads();
-
+    if (gt == 0) sc.count = 0;
+    group_sync<kNT, kBar>();
     // ---- A1: cull (world.py:97-98) ----
     // Candidates come from the world's xy cell grid (isy_world_create): a visible triangle has a vertex
     // within the horizon, so it is listed in a cell that meets the disc around the eye.  A triangle is
@@ -110,12 +108,11 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
     // the candidate cells form one contiguous list range per grid row: flatten the (<= 16) rows.
     // One lane per row: the row keeps only the columns that meet the disc of radius h around the eye
     // (a visible triangle's nearest vertex is within h in xy), then a warp scan gives the offsets.
-    __shared__ unsigned int s_rowbeg[16], s_rowoff[17];
     const int nrows = min(cy1 - cy0 + 1, 16);   // cell = horizon / 4 or larger: at most 10 rows
-    if (tid < 32) {
+    if (gt < 32) {
         unsigned int beg = 0, cnt = 0;
-        if (tid < nrows) {
-            const int row = cy0 + tid;
+        if (gt < nrows) {
+            const int row = cy0 + gt;
             int rx0 = cx0, rx1 = cx1;
             if (row > 0 && row < ny - 1) {   // (border rows also hold whatever lies beyond the grid: keep the full span)
                 const double cell = 1.0 / (double)ginv;
@@ -134,30 +131,25 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
             const unsigned int up = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += up;
         }
-        if (tid < nrows) s_rowbeg[tid] = beg, s_rowoff[tid] = incl - cnt;
-        if (tid == nrows - 1) s_rowoff[nrows] = incl;
+        if (gt < nrows) sc.rowbeg[gt] = beg, sc.rowoff[gt] = incl - cnt;
+        if (gt == nrows - 1) sc.rowoff[nrows] = incl;
     }
-    __syncthreads();
-    const unsigned int ncand = s_rowoff[nrows];
+    group_sync<kNT, kBar>();
+    const unsigned int ncand = sc.rowoff[nrows];
     // two candidates per thread and trip: their list reads and vertex gathers (two dependent trips to L2
     // each) overlap
-    for (unsigned int base = 0; base < ncand; base += 2 * kThreads) {   // block-uniform trip count
-#if defined(ISY_PHASE_DETAIL) && ISY_PHASE_DETAIL == 3
-        long long c0, c1;
-        const long long cs = clock64();
-        if (base == 0) t_mid[3] = cs;
-#endif
+    for (unsigned int base = 0; base < ncand; base += 2 * kNT) {   // block-uniform trip count
         unsigned int packed[2];
         bool have[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            const unsigned int c = base + u * kThreads + tid;
+            const unsigned int c = base + u * kNT + gt;
             have[u] = c < ncand;
             packed[u] = 0;
             if (have[u]) {
                 int rr = 0;
-                while (rr + 1 < nrows && c >= s_rowoff[rr + 1]) ++rr;
-                packed[u] = __ldg(rp.wg_cell_tris + s_rowbeg[rr] + (c - s_rowoff[rr]));
+                while (rr + 1 < nrows && c >= sc.rowoff[rr + 1]) ++rr;
+                packed[u] = __ldg(rp.wg_cell_tris + sc.rowbeg[rr] + (c - sc.rowoff[rr]));
             }
         }
         double s3[2][3];
@@ -173,9 +165,6 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
                 s3[u][k] = norm2_rn((double)vx[u][k] - px, (double)vy[u][k] - py, (double)vzz[u][k] - pz);   // world.py:94-96
             }
         }
-#if defined(ISY_PHASE_DETAIL) && ISY_PHASE_DETAIL == 3
-        asm volatile("mov.u64 %0, %%clock64;" : "=l"(c0) : "d"(s3[0][0] + s3[1][0] + s3[0][1] + s3[1][1] + s3[0][2] + s3[1][2]));
-#endif
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int t = (int)(packed[u] & 0x3fffffffu), tag = (int)(packed[u] >> 30);
@@ -196,32 +185,68 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
             unsigned m = __ballot_sync(0xffffffffu, visible);
             if (m) {
                 int basei = 0;
-                if (lane == 0) basei = atomicAdd(s_count, __popc(m));
+                if (lane == 0) basei = atomicAdd(&sc.count, __popc(m));
                 basei = __shfl_sync(0xffffffffu, basei, 0);
                 if (visible) {
                     int slot = basei + __popc(m & ((1u << lane) - 1));
                     if (slot < rp.slab_cap) vis[slot] = t;
-                    if (slot < kStage) {   // the projection takes the vertices from here instead of gathering them again
+                    if (slot < stage_cap) {   // the projection takes the vertices from here instead of gathering them again
 #pragma unroll
                         for (int k = 0; k < 3; ++k) {
-                            stage[(3 * k + 0) * kStage + slot] = vx[u][k];
-                            stage[(3 * k + 1) * kStage + slot] = vy[u][k];
-                            stage[(3 * k + 2) * kStage + slot] = vzz[u][k];
+                            stage[(3 * k + 0) * stage_cap + slot] = vx[u][k];
+                            stage[(3 * k + 1) * stage_cap + slot] = vy[u][k];
+                            stage[(3 * k + 2) * stage_cap + slot] = vzz[u][k];
                         }
                     }
                 }
             }
         }
-#if defined(ISY_PHASE_DETAIL) && ISY_PHASE_DETAIL == 3
-        c1 = clock64();
-        t_mid[1] += c0 - cs, t_mid[2] += c1 - c0;   // summed over the trips of this position
-#endif
+    }
+    group_sync<kNT, kBar>();
+    group_sync<kNT, kBar>();
+    return sc.count;
+}
+
+constexpr int kStage = 1792;   // visible triangles whose vertices are staged in shared memory (63 KB)
+static_assert(9 * kStage * sizeof(float) <= sizeof(unsigned short) * kBestCap, "the stage must fit the winner buffer");
+static_assert(9 * kStage * sizeof(float) <= sizeof(SmemBins), "... and the bin lists (built after the projection)");
+
+template <bool kRuns>
+__device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* entries, Exact* exacts,
+                                SmemLayout& sm, CullScratch* sc, const CullScratch* ahead, const float* ahead_stage,
+                                int ahead_cap, int* s_nent, int* s_band, long long* t_mid = nullptr) {
+    // ahead != null: position p was culled ahead (vis[] filled, vertices in ahead_stage, ahead->count of them)
+    const int tid = threadIdx.x;
+    if (rp.T == 0) {   // no world (sky-only calls): nothing to cull
+        if (tid == 0) s_band[0] = float_key(CUDART_INF_F), s_band[1] = float_key(-CUDART_INF_F);
+        return 0;
+    }
+    const double px = rp.pos[3 * p + 0], py = rp.pos[3 * p + 1], pz = rp.pos[3 * p + 2];
+    const double h = rp.horizon;
+    // vertices of the visible triangles, cull -> projection: 9 planes of kStage floats over the winner buffer / bin
+    // lists, which nothing uses before this position is rasterised
+    const float* stage = reinterpret_cast<float*>(&sm.ras);
+    int stage_cap = kStage;
+
+    if (tid == 0) {
+        *s_nent = 0;
+        sm.order_n[0] = 0, sm.order_n[1] = 0;
+        s_band[0] = float_key(CUDART_INF_F);
+        s_band[1] = float_key(-CUDART_INF_F);
     }
     __syncthreads();
+
+    // ---- A1: cull (world.py:97-98), unless the copy warps did it while the previous position was rasterised ----
+    int V;
+    if (ahead) {
+        V = ahead->count;
+        stage = ahead_stage, stage_cap = ahead_cap;
+    } else {
+        V = cull_position<kThreads, 0>(rp, p, tid, vis, reinterpret_cast<float*>(&sm.ras), kStage, *sc);
+    }
 #ifdef ISY_PHASE_DETAIL
     *t_mid = clock64();   // (profiling build only) end of the cull
 #endif
-    int V = *s_count;
     if (V > rp.slab_cap) {
         if (tid == 0) atomicExch(rp.status, (int)ISY_ERR_OVERFLOW);
         V = rp.slab_cap;
@@ -231,12 +256,12 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
     for (int j = tid; j < V; j += kThreads) {
         int t = vis[j];
         double v[3][3];
-        if (j < kStage) {
+        if (j < stage_cap) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                v[k][0] = (double)stage[(3 * k + 0) * kStage + j] - px;   // world.py:94
-                v[k][1] = (double)stage[(3 * k + 1) * kStage + j] - py;
-                v[k][2] = (double)stage[(3 * k + 2) * kStage + j] - pz;
+                v[k][0] = (double)stage[(3 * k + 0) * stage_cap + j] - px;   // world.py:94
+                v[k][1] = (double)stage[(3 * k + 1) * stage_cap + j] - py;
+                v[k][2] = (double)stage[(3 * k + 2) * stage_cap + j] - pz;
             }
         } else {
             load_vertices(rp.tri_planes, rp.T, t, px, py, pz, v);

@@ -223,16 +223,21 @@ __device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& s
 // an edge, redo the query in fp64 exactly as the reference composes it.
 template <bool kUniform>
 __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, const Exact* exacts, int E, int Hcur, int* s_next,
-                              int Rrow, unsigned jbase) {
+                              int Rrow, unsigned jbase, int stop_after = 0x7fffffff) {
+    // stop_after: the warp leaves once it has taken a copy at or beyond this place in the queue (the copy warps of
+    // rows mode step out in mid-rasterisation to write the template rows, then come back)
     const int lane = threadIdx.x & 31;
     const float pi_f = (float)kPi;
     const int ntall = sm.order_n[0];
+    bool last = false;
     for (;;) {
+        if (last) break;
         // copies differ a lot in size (a near blade spans hundreds of rays): warps pull them from a counter
         int e = 0;
         if (lane == 0) e = smem_atomic_add(s_next, 1);
         e = __shfl_sync(0xffffffffu, e, 0);
         if (e >= E) break;
+        last = e >= stop_after;
         e = sm.order[e < ntall ? e : kMaxE - 1 - (e - ntall)];   // tall copies first: no long straggler at the end
         // run of pitch-sorted rays that covers the copy's pitch range (a few extra rays at both ends),
         // worked out when the copy was projected (small eyes) or when the band was loaded

@@ -2,12 +2,22 @@
 #pragma once
 #include "isy_shade.cuh"
 
+// The copy warps can also cull the NEXT position while the others rasterise (cull_position on a named barrier).  It
+// halves the projection phase (32.7 k -> 16.4 k cycles per position) but keeps four warps out of the issue-bound
+// rasteriser for another 35 k cycles (104 k -> 121 k): 23.4 -> 24.2 ms per step on the benchmark grid.  Off.
+#ifndef ISY_CULL_AHEAD
+#define ISY_CULL_AHEAD 0
+#endif
+#ifndef ISY_LATE_ROWS_PCT
+#define ISY_LATE_ROWS_PCT 70
+#endif
 #ifndef ISY_COPY_WARPS
 #define ISY_COPY_WARPS 4
 #endif
 
 namespace isy {
 
+constexpr int kLateRowsPct = ISY_LATE_ROWS_PCT;   // the template rows are written once this share of the copies is taken
 constexpr int kCopyWarps = ISY_COPY_WARPS;   // warps that stream the template rows of a position while the rest rasterise
 
 enum { kModeBrute = 0, kModeBins = 1, kModeRaster = 2 };
@@ -23,7 +33,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
     __shared__ int s_count, s_nent, s_band[2];
-    __shared__ unsigned int s_item, s_warp[kWarps];
+    __shared__ unsigned int s_item, s_item_next, s_warp[kWarps];
+    __shared__ CullScratch s_cull, s_cull_ahead;   // this position's cull; the next position's, run ahead by the copy warps
+    __shared__ unsigned int s_ahead_item;          // item whose cull is in s_cull_ahead / the workspace stage
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int* vis = rp.slab_vis + (size_t)blockIdx.x * rp.slab_cap;
@@ -44,6 +56,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
         for (int i = tid; i < 2 * (kGTab + 1); i += kThreads) sm.gtab[i] = rp.sky_gtab[i];
         if (tid == 0) sm.sun0 = rp.sun[0];
     }
+    float* const ahead_stage = (ISY_CULL_AHEAD && rp.slab_stage) ? rp.slab_stage + (size_t)blockIdx.x * 9 * rp.stage_cap : nullptr;
+    if (tid == 0) s_ahead_item = 0xffffffffu;
     if (kEye == kEyeSmall && rp.row_bg)   // rows mode (the tail of the layout is allocated)
         for (int i = tid; i < rp.R; i += kThreads) sm.sorted_ray16[i] = (unsigned short)rp.grid_sorted_ray[i];
     if (smem_grid) {   // the eye's static tables: nothing else uses this memory in a yaw-only launch
@@ -70,6 +84,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
         if (item >= (unsigned)rp.items) break;
         if (tid == 0) pulled = atomicAdd(rp.queue, 1u);
         const int p = item / rp.splits, split = item % rp.splits;
+        // was this item culled while the previous one was rasterised?
+        const CullScratch* const ahead = (ahead_stage && s_ahead_item == item) ? &s_cull_ahead : nullptr;
         long long t0 = clock64();
 
 #ifdef ISY_PHASE_DETAIL
@@ -78,13 +94,14 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 #else
         long long t_sub[3] = {t0, t0, t0};   // end of the cull; (mode 2) position loaded; candidate rows listed
 #endif
-        const int E = smem_grid ? cull_and_project<true>(rp, p, vis, entries, exacts, sm, &s_count, &s_nent, s_band, t_sub)
-                                : cull_and_project<false>(rp, p, vis, entries, exacts, sm, &s_count, &s_nent, s_band, t_sub);
+        const int E = smem_grid ? cull_and_project<true>(rp, p, vis, entries, exacts, sm, &s_cull, ahead, ahead_stage, rp.stage_cap, &s_nent, s_band, t_sub)
+                                : cull_and_project<false>(rp, p, vis, entries, exacts, sm, &s_cull, ahead, ahead_stage, rp.stage_cap, &s_nent, s_band, t_sub);
         const long long g_detail_t = t_sub[0];
 #else
-        const int E = smem_grid ? cull_and_project<true>(rp, p, vis, entries, exacts, sm, &s_count, &s_nent, s_band)
-                                : cull_and_project<false>(rp, p, vis, entries, exacts, sm, &s_count, &s_nent, s_band);
+        const int E = smem_grid ? cull_and_project<true>(rp, p, vis, entries, exacts, sm, &s_cull, ahead, ahead_stage, rp.stage_cap, &s_nent, s_band)
+                                : cull_and_project<false>(rp, p, vis, entries, exacts, sm, &s_cull, ahead, ahead_stage, rp.stage_cap, &s_nent, s_band);
 #endif
+        if (tid == 0) s_item_next = pulled;   // (the item after this one: requested when this one started)
         long long t1 = clock64();
 #ifdef ISY_PHASE_DETAIL
 #if ISY_PHASE_DETAIL == 3
@@ -154,11 +171,34 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 #ifdef ISY_PHASE_DETAIL
                 t_walk = clock64();
 #endif
-                if (rows_mode) {
-                    if ((rp.R & 3) == 0) copy_rows<float4>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
-                    else copy_rows<float>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
+                // rows mode: the copy warps write the sky rows now and the template rows of hit / depth / rgb when 70 %
+                // of the copies have been taken (scans) -- the later, the likelier the patches find them in L2
+                const bool scan = kEye == kEyeSmall ? Hcur > kSmallH : walk_bands;
+                const bool copy_warp = rows_mode && warp >= kWarps - kCopyWarps;
+                if (copy_warp) {
+                    if ((rp.R & 3) == 0) copy_rows<float4, true, false>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
+                    else copy_rows<float, true, false>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
+#if ISY_CULL_AHEAD
+                    // ... and cull the NEXT position before they join the rasterisation
+                    if (ahead_stage && grp == split && rp.T > 0) {
+                        const unsigned int nxt = s_item_next;
+                        if (nxt < (unsigned)rp.items) {
+                            const int gt = tid - (kWarps - kCopyWarps) * 32;
+                            cull_position<kCopyWarps * 32, 1>(rp, (int)(nxt / rp.splits), gt, vis, ahead_stage, rp.stage_cap,
+                                                              s_cull_ahead);
+                            if (gt == 0) s_ahead_item = nxt;
+                        }
+                    }
+#endif
+                    if (scan) {
+                        const int half = (int)((long long)E * kLateRowsPct / 100);
+                        if (uniform) raster_copies<true>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo, half);
+                        else raster_copies<false>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo, half);
+                    }
+                    if ((rp.R & 3) == 0) copy_rows<float4, false, true>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
+                    else copy_rows<float, false, true>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
                 }
-                if (kEye == kEyeSmall ? Hcur > kSmallH : walk_bands) {
+                if (scan) {
                     if (uniform) raster_copies<true>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo);
                     else raster_copies<false>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo);
                 } else if (kEye == kEyeSmall) {

@@ -205,8 +205,9 @@ __device__ __forceinline__ float4 zero_of<float4>() { return make_float4(0.f, 0.
 //   B. rows that are the same for every heading (templates of hit / depth / rgb, the sky rows of a uniform sky):
 //      a warp takes a column of 32 elements, loads it once and stores it into the Hcur views -- a pure store stream.
 // Sky rows are never touched again: streaming stores.  The hit / depth / rgb rows will be patched by final_pass_patch a
-// few tens of microseconds later: normal stores, so that the patches meet them in L2.
-template <typename T>
+// few tens of microseconds later: normal stores, and written as late in the rasterisation as there is time for, so
+// that the patches meet them in L2 (kTemplates picks the part: the render kernel calls it twice).
+template <typename T, bool kSky, bool kTemplates>
 __device__ void copy_rows(const RenderParams& rp, int p, int grp, int Hcur, int w0, int nw) {
     constexpr int kPer = sizeof(T) / sizeof(float);
     const int nR = rp.R / kPer;                              // elements per row of R floats
@@ -215,7 +216,7 @@ __device__ void copy_rows(const RenderParams& rp, int p, int grp, int Hcur, int 
     const size_t view0 = (size_t)p * rp.H + grp;             // views of the group: view0 + hh * ngroups
     const T* const tab = reinterpret_cast<const T*>(rp.sky_tab);
     T* const o_sky[3] = {reinterpret_cast<T*>(rp.out.Y), reinterpret_cast<T*>(rp.out.dop), reinterpret_cast<T*>(rp.out.aop)};
-    if (rp.sky_rows_h > 1) {                                 // A
+    if (kSky && rp.sky_rows_h > 1) {                         // A
         constexpr int kU = 8;
         const size_t plane = (size_t)rp.sky_rows_h * (size_t)nR;
         for (int it = warp; it < 3 * Hcur; it += nw) {
@@ -240,9 +241,10 @@ __device__ void copy_rows(const RenderParams& rp, int p, int grp, int Hcur, int 
     // B: columns of [hit | depth | rgb (3 rows long) | Y | DoP | AoP of a uniform sky]
     const int cR = (nR + 31) >> 5, cC = (3 * nR + 31) >> 5;
     const int nB = 2 * cR + cC + (rp.sky_rows_h == 1 ? 3 * cR : 0);
+    const int cB0 = kTemplates ? 0 : 2 * cR + cC, cB1 = kSky ? nB : 2 * cR + cC;   // the columns of this call
     const T* const bg = reinterpret_cast<const T*>(rp.row_bg);
     const size_t vstride = (size_t)rp.ngroups;
-    for (int c = warp; c < nB; c += nw) {
+    for (int c = cB0 + warp; c < cB1; c += nw) {
         const T* src;
         T* dst;
         int len, e;
