@@ -17,7 +17,7 @@ What is pinned to the reference and what is not:
 
 Everything is torch on whatever device the tensors live on.  The M x Q distance matrix is a plain GEMM
 (|q - m|^2 = |q|^2 + |m|^2 - 2 q.m, cuBLAS through torch.matmul), evaluated in blocks of queries so that it
-never has to exist as a whole; on several GPUs every rank evaluates the views it rendered and only the
+never has to exist as a whole, and used only to pick the nearest stored vector; on several GPUs every rank evaluates the views it rendered and only the
 familiarity rows travel (`distributed.gather_views`, NCCL over NVLink) -- the one collective of the design.
 """
 import numpy as np
@@ -91,7 +91,10 @@ class PerfectMemory:
         for a in range(0, q.shape[0], self.block):
             qb = q[a:a + self.block]
             d2 = (qb * qb).sum(dim=1, keepdim=True) + m2[None, :] - 2.0 * (qb @ db.T)    # (block, M) GEMM
-            out[a:a + self.block] = 1.0 - torch.sqrt(d2.min(dim=1).values.clamp_min(0) / q.shape[1])
+            # the GEMM form only picks the nearest stored vector; its distance is then formed from the difference
+            # itself (no cancellation: a stored view is exactly familiar with itself)
+            diff = qb - db[d2.argmin(dim=1)]
+            out[a:a + self.block] = 1.0 - torch.sqrt((diff * diff).sum(dim=1) / q.shape[1])
         return out
 
 

@@ -83,3 +83,25 @@ def test_dataset_writer_matches_per_view_calls_and_schema(ib, tmp_path):
     blk = datasets.collect_familiarity_dataset(route, eye, world, sky, method="parallel", nb_orientations=3, nb_parallel=3,
                                                block=(2, 5))
     assert np.array_equal(blk["ommatidia"], par["ommatidia"][2 * 3:5 * 3])
+
+
+def test_familiarity_of_a_small_grid_on_the_gpu(ib):
+    """N3 end to end on the device: dataset (N2) -> PN responses -> PCA whitening -> perfect memory -> heat map."""
+    from invertsy_b200 import familiarity as fam
+    world = ib.Seville2009()
+    eye = ib.CompoundEye(nb_input=400, omm_rho=np.deg2rad(4.), omm_res=5., c_sensitive=[0, 0., 1., 0., 0.])
+    route = ib.Seville2009.load_routes(degrees=True)["path"][0][::8]      # 102 views: a well-conditioned calibration set
+    stats = ib.datasets.collect_familiarity_dataset(route, eye, world, sky=ib.UniformSky(10.), method="grid",
+                                                    nb_orientations=4, nb_rows=5, nb_cols=5)
+    views = torch.as_tensor(stats["ommatidia"]).cuda()
+    rviews = torch.as_tensor(stats["ommatidia_out"]).cuda()
+    wh = fam.Whitening(nb_output=8).fit(fam.pn_responses(rviews))
+    f = fam.evaluate(views, rviews, whitening=wh)
+    assert f.is_cuda and f.shape == (5 * 5 * 4,) and torch.isfinite(f).all() and (f <= 1 + 1e-6).all()
+    # the same on the CPU in float64
+    ref = fam.evaluate(views.cpu().double(), rviews.cpu().double(),
+                       whitening=fam.Whitening(nb_output=8, dtype=torch.float64).fit(fam.pn_responses(rviews.cpu().double())))
+    assert np.abs(f.cpu().numpy() - ref.numpy()).max() < 5e-3, np.abs(f.cpu().numpy() - ref.numpy()).max()
+    # a route view is fully familiar with itself
+    assert np.allclose(fam.evaluate(rviews, rviews, whitening=wh).cpu().numpy(), 1.0, atol=1e-3)
+    assert fam.familiarity_map(f, 5, 5, 4).shape == (5, 5, 4)
