@@ -65,6 +65,7 @@ struct SunConst {
 struct RenderParams {
     // world (SoA planes: x0 y0 z0 x1 y1 z1 x2 y2 z2, each T floats) and colours T*3
     const float* tri_planes;
+    const float4* tri_aos;   // the same vertices, 3 float4 per triangle (x0 y0 z0 x1 | y1 z1 x2 y2 | z2 - - -)
     const float* tri_rgb;
     int T;
     double horizon;

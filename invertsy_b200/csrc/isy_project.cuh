@@ -157,13 +157,15 @@ __device__ int cull_position(const RenderParams& rp, int p, int gt, int* vis, fl
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int t = (int)(packed[u] & 0x3fffffffu);
+            // candidates are gathered by index: three 16-byte loads from the triangle-major copy of the world
+            const float4 a = __ldg(rp.tri_aos + 3 * (size_t)t), b = __ldg(rp.tri_aos + 3 * (size_t)t + 1),
+                         c = __ldg(rp.tri_aos + 3 * (size_t)t + 2);
+            vx[u][0] = a.x, vy[u][0] = a.y, vzz[u][0] = a.z;
+            vx[u][1] = a.w, vy[u][1] = b.x, vzz[u][1] = b.y;
+            vx[u][2] = b.z, vy[u][2] = b.w, vzz[u][2] = c.x;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                vx[u][k] = __ldg(rp.tri_planes + (size_t)(3 * k + 0) * rp.T + t);
-                vy[u][k] = __ldg(rp.tri_planes + (size_t)(3 * k + 1) * rp.T + t);
-                vzz[u][k] = __ldg(rp.tri_planes + (size_t)(3 * k + 2) * rp.T + t);
+            for (int k = 0; k < 3; ++k)
                 s3[u][k] = norm2_rn((double)vx[u][k] - px, (double)vy[u][k] - py, (double)vzz[u][k] - pz);   // world.py:94-96
-            }
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -222,7 +224,6 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
         return 0;
     }
     const double px = rp.pos[3 * p + 0], py = rp.pos[3 * p + 1], pz = rp.pos[3 * p + 2];
-    const double h = rp.horizon;
     // vertices of the visible triangles, cull -> projection: 9 planes of kStage floats over the winner buffer / bin
     // lists, which nothing uses before this position is rasterised
     const float* stage = reinterpret_cast<float*>(&sm.ras);

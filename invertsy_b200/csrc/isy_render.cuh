@@ -89,11 +89,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
         long long t0 = clock64();
 
 #ifdef ISY_PHASE_DETAIL
-#if ISY_PHASE_DETAIL == 3
-        long long t_sub[4] = {t0, 0, 0, t0};  // end of the cull; sum(wait for vertices + norms); sum(visibility + compaction); loop start
-#else
-        long long t_sub[3] = {t0, t0, t0};   // end of the cull; (mode 2) position loaded; candidate rows listed
-#endif
+        long long t_sub[1] = {t0};   // end of the cull
         const int E = smem_grid ? cull_and_project<true>(rp, p, vis, entries, exacts, sm, &s_cull, ahead, ahead_stage, rp.stage_cap, &s_nent, s_band, t_sub)
                                 : cull_and_project<false>(rp, p, vis, entries, exacts, sm, &s_cull, ahead, ahead_stage, rp.stage_cap, &s_nent, s_band, t_sub);
         const long long g_detail_t = t_sub[0];
@@ -104,13 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
         if (tid == 0) s_item_next = pulled;   // (the item after this one: requested when this one started)
         long long t1 = clock64();
 #ifdef ISY_PHASE_DETAIL
-#if ISY_PHASE_DETAIL == 3
-        t_detail[0] += t_sub[1], t_detail[1] += t_sub[2], t_detail[2] += g_detail_t - t_sub[3] - t_sub[1] - t_sub[2];
-#elif ISY_PHASE_DETAIL == 2
-        t_detail[0] += t_sub[1] - t0, t_detail[1] += t_sub[2] - t_sub[1], t_detail[2] += g_detail_t - t_sub[2];
-#else
         t_detail[0] += g_detail_t - t0, t_detail[1] += t1 - g_detail_t;
-#endif
 #endif
         int mode = kModeBrute;
         BinGrid grid;
@@ -211,9 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
             long long t4 = clock64();
             t_phase[1] += t4 - t3b;
 #ifdef ISY_PHASE_DETAIL
-#if ISY_PHASE_DETAIL == 1
             t_detail[2] += t_walk - t3b;
-#endif
 #endif
 
             if (is_raster && !kF64 && !rp.init_c && (rp.S == 1 || kEye == kEyeLarge)) {
