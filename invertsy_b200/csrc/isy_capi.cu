@@ -366,7 +366,7 @@ Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
     pl.off_skytab = off, off += pl.rows ? align_up((size_t)H * e->R * 3 * sizeof(float)) : 0;
     pl.off_rowbg = off, off += pl.rows ? align_up((size_t)e->R * 5 * sizeof(float)) : 0;
     pl.stage_cap = std::min(pl.slab_cap, 4096);   // vertices of a position culled ahead (9 planes per CTA)
-    pl.off_stage = off, off += pl.rows ? align_up((size_t)pl.grid * 9 * pl.stage_cap * sizeof(float)) : 0;
+    pl.off_stage = off, off += (ISY_CULL_AHEAD && pl.rows) ? align_up((size_t)pl.grid * 9 * pl.stage_cap * sizeof(float)) : 0;
     pl.total = off;
     return pl;
 }
@@ -495,7 +495,7 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
         g_launches++;
         CUDA_TRY(cudaGetLastError());
         rp.sky_tab = tab, rp.sky_tab_off = differs, rp.row_bg = bg;
-        rp.slab_stage = (float*)(base + pl.off_stage), rp.stage_cap = pl.stage_cap;
+        rp.slab_stage = ISY_CULL_AHEAD ? (float*)(base + pl.off_stage) : nullptr, rp.stage_cap = pl.stage_cap;
     }
     const size_t smem = rp.row_bg ? sizeof(SmemLayout) : kSmemBase;   // (rows mode adds the tail of the layout)
     const int eye_kind = (vquat || !e->d_sorted) ? kEyeAny : (pl.global_best ? kEyeLarge : kEyeSmall);

@@ -47,7 +47,7 @@ def test_shared_heading_rows_match_the_per_view_sky(ib, H, outputs, R):
     world = ib.Seville2009()
     pitch, yaw = o.fibonacci_eye(R)
     r = ib.Renderer(world, ib.EyeLayout.from_angles(pitch, yaw), ib.Sky(np.deg2rad(60.), np.pi))
-    P = 160
+    P = max(160, -(-4200 // H))      # rows mode starts at 4096 views
     pos = _positions(P, 31)
     heads = (np.arange(H) * 2 * np.pi / H + 0.3 + np.pi) % (2 * np.pi) - np.pi   # 72 headings: two groups of 36
     yw = np.tile(heads, (P, 1))
@@ -70,7 +70,7 @@ def test_one_position_with_its_own_heading_turns_the_table_off(ib):
     world = ib.Seville2009()
     pitch, yaw = o.fibonacci_eye(600)
     r = ib.Renderer(world, ib.EyeLayout.from_angles(pitch, yaw), ib.Sky(np.deg2rad(40.), 1.0))
-    P, H = 150, 12
+    P, H = 400, 12
     pos = _positions(P, 32)
     yw = np.tile(np.deg2rad(np.arange(H) * 30. - 180.), (P, 1))
     yw[P - 1, H - 1] = np.nextafter(yw[P - 1, H - 1], 4.0)      # one ulp is enough
@@ -91,7 +91,7 @@ def test_host_buffer_path_uses_the_same_table(ib):
     world = ib.Seville2009()
     pitch, yaw = o.fibonacci_eye(1000)
     r = ib.Renderer(world, ib.EyeLayout.from_angles(pitch, yaw), ib.Sky(np.deg2rad(60.), np.pi))
-    P, H = 96, 36
+    P, H = 128, 36
     pos = _positions(P, 33)
     yw = np.tile(np.deg2rad(np.arange(H) * 10. - 180.), (P, 1))
     h = r.render_host(pos, yw, outputs=ALL)
@@ -106,7 +106,7 @@ def test_uniform_and_no_sky_rows_match_the_per_view_passes(ib, sky, H, R):
     world = ib.Seville2009()
     pitch, yaw = o.fibonacci_eye(R)
     r = ib.Renderer(world, ib.EyeLayout.from_angles(pitch, yaw), ib.UniformSky(10.) if sky == "uniform" else None)
-    P = 150
+    P = max(150, -(-4200 // H))      # rows mode starts at 4096 views
     pos = _positions(P, 34)
     rng = np.random.RandomState(3)
     yw = rng.uniform(-np.pi, np.pi, (P, H))          # every position its own headings: no sky table involved
@@ -127,7 +127,7 @@ def test_empty_and_sparse_worlds_in_rows_mode(ib):
     world = ib.SimpleWorld()
     pitch, yaw = o.fibonacci_eye(1000)
     r = ib.Renderer(world, ib.EyeLayout.from_angles(pitch, yaw), ib.Sky(np.deg2rad(30.), 0.5))
-    P, H = 64, 8
+    P, H = 600, 8
     rng = np.random.RandomState(4)
     pos = np.c_[rng.uniform(-30, 40, P), rng.uniform(-30, 40, P), np.full(P, 0.01)]   # most of them far outside
     yw = np.tile(np.deg2rad(np.arange(H) * 45. - 180.), (P, 1))

@@ -30,6 +30,15 @@ run("small eye, scan (pitch-run walk)", small, positions(P), heads6)
 run("small eye, single heading (ray grid)", small, positions(P), heads6[:, :1])
 run("small eye, irregular headings", small, positions(P), np.sort(rng.uniform(-3.1, 3.1, (P, 7)), axis=1))
 run("small eye, uniform sky, from sky", small, positions(P), heads6, sky=ib.UniformSky(10.), init_from_sky=True)
+# rows mode (template rows + patches) starts at 4096 views: shared-heading Perez sky, uniform sky, no sky, and a
+# Perez call whose positions have their own headings (falls back to the per-view passes inside the same launch shape)
+PR = int(os.environ.get("ISY_SAN_PROWS", "700"))
+headsR = np.tile(np.deg2rad(np.arange(6) * 60. - 180.), (PR, 1))
+run("small eye, rows mode, sky table", small, positions(PR), headsR)
+run("small eye, rows mode, uniform sky", small, positions(PR), headsR, sky=ib.UniformSky(10.))
+run("small eye, rows mode, no sky", small, positions(PR), headsR, sky=None, outputs=("rgb", "hit", "depth"))
+run("small eye, rows mode set up, own headings", small, positions(PR), headsR + rng.uniform(-.1, .1, headsR.shape))
+run("small eye, rows mode, single heading (ray grid)", small, positions(4200), np.zeros((4200, 1)))
 run("small eye, brute force", small, positions(8), heads6[:8], brute_force=True)
 run("small eye, f64", small, positions(8), heads6[:8], f64=True)
 p, y = ib.fibonacci_lattice(1500)
