@@ -495,6 +495,12 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
         g_launches++;
         CUDA_TRY(cudaGetLastError());
         rp.sky_tab = tab, rp.sky_tab_off = differs, rp.row_bg = bg;
+        {   // 16 bytes per lane needs rows that start on 16-byte boundaries in every buffer that is written
+            const void* ptrs[6] = {out->rgb, out->hit, out->depth, out->Y, out->dop, out->aop};
+            bool aligned = (e->R & 3) == 0;
+            for (const void* q : ptrs) aligned = aligned && ((uintptr_t)q & 15u) == 0;
+            rp.rows_vec4 = aligned ? 1 : 0;
+        }
         rp.slab_stage = ISY_CULL_AHEAD ? (float*)(base + pl.off_stage) : nullptr, rp.stage_cap = pl.stage_cap;
     }
     const size_t smem = rp.row_bg ? sizeof(SmemLayout) : kSmemBase;   // (rows mode adds the tail of the layout)

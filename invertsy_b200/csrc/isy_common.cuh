@@ -106,6 +106,7 @@ struct RenderParams {
     int sky_rows_h;          // H, 1, or 0 = no sky outputs
     const int* sky_tab_off;  // nonzero: the positions turned out NOT to share their headings (heading_rows_kernel)
     const float* row_bg;     // [R] hit = -1 | [R] depth = NaN | [3R] ground colour / NaN by the ray's pitch
+    int rows_vec4;           // rows are 16-byte aligned (R a multiple of 4, output buffers aligned): 16 bytes per lane
     isy_sky_params sky;
     uint32_t flags;
     isy_outputs out;

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                 const bool scan = kEye == kEyeSmall ? Hcur > kSmallH : walk_bands;
                 const bool copy_warp = rows_mode && warp >= kWarps - kCopyWarps;
                 if (copy_warp) {
-                    if ((rp.R & 3) == 0) copy_rows<float4, true, false>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
+                    if (rp.rows_vec4) copy_rows<float4, true, false>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
                     else copy_rows<float, true, false>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
 #if ISY_CULL_AHEAD
                     // ... and cull the NEXT position before they join the rasterisation
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                         if (uniform) raster_copies<true>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo, half);
                         else raster_copies<false>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo, half);
                     }
-                    if ((rp.R & 3) == 0) copy_rows<float4, false, true>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
+                    if (rp.rows_vec4) copy_rows<float4, false, true>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
                     else copy_rows<float, false, true>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
                 }
                 if (scan) {

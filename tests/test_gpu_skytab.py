@@ -136,3 +136,28 @@ def test_empty_and_sparse_worlds_in_rows_mode(ib):
     torch.cuda.synchronize()
     r.check()
     _same(a, b, 1e-6)
+
+
+def test_output_buffers_off_the_16_byte_grid(ib):
+    # rows mode copies 16 bytes per lane only when every buffer allows it: buffers that start 4 bytes off get the
+    # 4-byte path and the same views
+    world = ib.Seville2009()
+    pitch, yaw = o.fibonacci_eye(1000)
+    r = ib.Renderer(world, ib.EyeLayout.from_angles(pitch, yaw), ib.Sky(np.deg2rad(60.), np.pi))
+    P, H = 120, 36
+    pos = _positions(P, 35)
+    yw = np.tile(np.deg2rad(np.arange(H) * 10. - 180.), (P, 1))
+    a = r.render(pos, yw, outputs=ALL)
+    B, R = P * H, 1000
+    shapes = {"rgb": (B, R, 3), "hit": (B, R), "depth": (B, R), "Y": (B, R), "dop": (B, R), "aop": (B, R)}
+    off = {}
+    for k, shp in shapes.items():
+        n = int(np.prod(shp))
+        base = torch.empty(n + 1, dtype=torch.int32 if k == "hit" else torch.float32, device="cuda")
+        off[k] = base[1:].view(shp)
+        assert off[k].data_ptr() % 16 == 4
+    b = r.render(pos, yw, outputs=ALL, out=off)
+    torch.cuda.synchronize()
+    r.check()
+    for k in ALL:
+        assert np.array_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), equal_nan=True), k
