@@ -8,8 +8,8 @@
 #ifndef ISY_CULL_AHEAD
 #define ISY_CULL_AHEAD 0
 #endif
-#ifndef ISY_LATE_ROWS_PCT
-#define ISY_LATE_ROWS_PCT 70
+#ifndef ISY_LATE_COPIES
+#define ISY_LATE_COPIES 200
 #endif
 #ifndef ISY_COPY_WARPS
 #define ISY_COPY_WARPS 4
@@ -17,7 +17,9 @@
 
 namespace isy {
 
-constexpr int kLateRowsPct = ISY_LATE_ROWS_PCT;   // the template rows are written once this share of the copies is taken
+// the template rows are written when this many copies are left to take: about what the other warps rasterise in the
+// 25-30 k cycles the rows need on the store path (short positions start at once, long ones later than a fixed share)
+constexpr int kLateCopies = ISY_LATE_COPIES;
 constexpr int kCopyWarps = ISY_COPY_WARPS;   // warps that stream the template rows of a position while the rest rasterise
 
 enum { kModeBrute = 0, kModeBins = 1, kModeRaster = 2 };
@@ -161,8 +163,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 #ifdef ISY_PHASE_DETAIL
                 t_walk = clock64();
 #endif
-                // rows mode: the copy warps write the sky rows now and the template rows of hit / depth / rgb when 70 %
-                // of the copies have been taken (scans) -- the later, the likelier the patches find them in L2
+                // rows mode: the copy warps write the sky rows now and the template rows of hit / depth / rgb when
+                // kLateCopies copies are left (scans) -- the later, the likelier the patches find them in L2
                 const bool scan = kEye == kEyeSmall ? Hcur > kSmallH : walk_bands;
                 const bool copy_warp = rows_mode && warp >= kWarps - kCopyWarps;
                 if (copy_warp) {
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                     }
 #endif
                     if (scan) {
-                        const int half = (int)((long long)E * kLateRowsPct / 100);
+                        const int half = max(E - kLateCopies, 0);
                         if (uniform) raster_copies<true>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo, half);
                         else raster_copies<false>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo, half);
                     }
