@@ -3,8 +3,8 @@
 #include "isy_shade.cuh"
 
 // The copy warps can also cull the NEXT position while the others rasterise (cull_position on a named barrier).  It
-// halves the projection phase (32.7 k -> 16.4 k cycles per position) but keeps four warps out of the issue-bound
-// rasteriser for another 35 k cycles (104 k -> 121 k): 23.4 -> 24.2 ms per step on the benchmark grid.  Off.
+// shortens the projection phase (22 k -> 16 k cycles per position) but keeps four warps out of the issue-bound
+// rasteriser for longer (105 k -> 112 k): 22.1 -> 22.9 ms per step on the benchmark grid.  Off.
 #ifndef ISY_CULL_AHEAD
 #define ISY_CULL_AHEAD 0
 #endif
