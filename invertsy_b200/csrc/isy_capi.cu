@@ -329,7 +329,7 @@ constexpr size_t kSkyTabMaxBytes = 16u << 20;  // ... and it should stay L2-resi
 
 Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
     Plan pl;
-    int max_ctas = device_sms(w->device);  // one persistent CTA per SM (196 KB of shared memory, kThreads threads)
+    int max_ctas = device_sms(w->device);  // one persistent CTA per SM (191 KB of shared memory, 207 KB in rows mode; kThreads threads)
     if (const char* cap = getenv("ISY_MAX_CTAS")) {   // profiling aid: fewer CTAs = fewer SMs sharing L2 / HBM
         const int c = atoi(cap);
         if (c > 0) max_ctas = std::min(max_ctas, c);

@@ -10,7 +10,10 @@
 //                                       best[heading][ray] if it is nearer; fp32 filter + exact fp64 re-check
 //   isy_bins.cuh     phase B1' (general orientations): per-position (theta, phi) bins, rays test their bin
 //   isy_shade.cuh    phase B2 : winner -> colour / ground / background (world.py:79-90, :123), analytic sky
-//                                       (sky.py:304-334), ONE write of the view
+//                                       (sky.py:304-334), ONE write of the view; or, in rows mode (small eyes,
+//                                       sky-less / uniform-sky / shared-heading calls): template and sky-table rows
+//                                       streamed into the views while the copies are rasterised, then patches
+//                                       for the rays that hit something
 //   isy_render.cuh   the persistent kernel that strings the phases together
 //
 // argmin of distance over containing copies == the painter's far->near overwrite (world.py:106-123).
@@ -19,7 +22,7 @@
 #pragma once
 #include "isy_common.cuh"
 
-// CTA size.  One persistent CTA per SM either way (196 KB of shared memory); 896 threads = 28 warps at 72 registers.
+// CTA size.  One persistent CTA per SM either way (191-207 KB of shared memory); 896 threads = 28 warps at 72 registers.
 // The rasteriser is latency-bound and scales with the warps (121 k -> 90 k cycles per position from 512 to 896
 // threads), the final pass is throughput-bound and pays a little for the tighter register budget (73 k -> 81 k):
 // 31.5 -> 27.9 ms per step on the benchmark grid.  640 / 768 / 1024 threads were measured too (README of profiles/).
