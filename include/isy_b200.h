@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ISY_ABI_VERSION 1
+#define ISY_ABI_VERSION 2
 
 typedef enum {
     ISY_OK = 0,
@@ -86,7 +86,25 @@ typedef struct {
     void* Y;        /* [B][N]     sky luminance      (sky.py:313, :334), cone-averaged               */
     void* dop;      /* [B][N]     degree of polarisation (sky.py:317)                                */
     void* aop;      /* [B][N]     angle of polarisation  (sky.py:320-324), circular cone average     */
+    void* resp;     /* [B][N][C]  photoreceptor responses of the eye (needs isy_sensor_params), C = 3 or 1:
+                                  what `eye(sky=, scene=)` leaves in eye.responses (simulation.py:2707, :2721),
+                                  or, with C = 1, the PN input clip(responses.mean(axis=1), 0, 1) (agent.py:744)  */
 } isy_outputs;      /* element type: float, or double with ISY_FLAG_OUT_F64                           */
+
+/* Photoreceptor transform of a CompoundEye-compatible sensor (rows N1 / N2 of SURVEY.md 8f).  The reference takes
+ * its eye from InvertPy (agent.py:20, simulation.py:24), which is not vendored: the transform below is this
+ * library's own, documented one (invertsy_b200/sense.py).  Per cone sample the colour on the 0..1 scale is
+ *     the triangle's colour where one is hit (world.py:123), else the ground colour where pitch >= 0 (world.py:90),
+ *     else luminance2skycolour(Y) / 255 under a sky (world.py:465-479), else 0;
+ * the samples of an ommatidium are averaged with the cone weights; then, per channel c in (R, G, B),
+ *     resp_c = clip(mean_c * w_rgb[c] * gain, 0, 1)                (c_sensitive, omm_res of the eye's constructor)
+ * and with channels == 1 the output is clip((resp_R + resp_G + resp_B) / 3, 0, 1).                            */
+typedef struct {
+    float w_rgb[3];    /* spectral sensitivity to R, G, B: c_sensitive[1:4] of the IRGBU vector (agent.py:590)  */
+    float gain;        /* omm_res / saturation (agent.py:589)                                                    */
+    int32_t channels;  /* 3 or 1                                                                                 */
+    int32_t reserved;
+} isy_sensor_params;
 
 typedef struct isy_world isy_world;
 typedef struct isy_eye isy_eye;
@@ -120,16 +138,18 @@ int64_t isy_eye_rays(const isy_eye* e);
  *                                or NULL when view_quat_dev is given
  *   view_quat_dev[P][H][4] doubles full eye orientation, or NULL for yaw-only views
  *   sun_dev      [2] or [P][H][2] doubles (theta_s = zenith distance, phi_s), NULL unless PEREZ
+ *   sensor       photoreceptor transform, NULL unless out->resp is asked for
  * Global ray orientation = view orientation * eye-frame ommatidium orientation (examples/test_sky.py:25).
  * Views are ordered b = p*H + h.                                                                  */
 size_t isy_render_workspace_bytes(const isy_world* w, const isy_eye* e, int64_t P, int64_t H);
 int isy_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, const double* pos_dev,
                const double* yaw_dev, const double* view_quat_dev, const double* sun_dev,
-               const isy_sky_params* sky, uint32_t flags, const isy_outputs* out_dev, void* workspace_dev,
-               size_t workspace_bytes, void* stream);
+               const isy_sky_params* sky, const isy_sensor_params* sensor, uint32_t flags,
+               const isy_outputs* out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* Synchronises `stream` and returns the sticky device-side status of the renders that used this
- * workspace (ISY_OK, or ISY_ERR_OVERFLOW when a position exceeded the slab).                    */
+ * workspace since the status was last read (ISY_OK, or ISY_ERR_OVERFLOW when a position of ANY of them
+ * exceeded the slab); reading clears it.  A render never clears it.                                */
 int isy_workspace_status(void* workspace_dev, void* stream);
 /* Profiling aid: SM cycles summed over CTAs of the LAST render that used this workspace, spent in
  * out4[0] cull+projection, out4[1] bin build, out4[2] ray phase; out4[3] = positions processed.  */
@@ -140,7 +160,8 @@ int isy_workspace_phase_cycles(void* workspace_dev, void* stream, uint64_t* out4
  * results are in host memory.  This is the end-to-end path bench.py times as `e2e`.            */
 int isy_render_host(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, const double* pos_host,
                     const double* yaw_host, const double* view_quat_host, const double* sun_host,
-                    const isy_sky_params* sky, uint32_t flags, const isy_outputs* out_host);
+                    const isy_sky_params* sky, const isy_sensor_params* sensor, uint32_t flags,
+                    const isy_outputs* out_host);
 
 /* ---- direct replacements of the two reference callables (explicit ray orientations) ----------
  * WorldBase.__call__(pos, ori, init_c, ...) world.py:55-129: N rays given as global quaternions.

@@ -10,6 +10,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ISY_B200_LIB", os.path.join(HERE, "libisy_b200.so"))   # override: profiling builds
 
+ABI_VERSION = 2
 ISY_OK, ISY_ERR_INVALID, ISY_ERR_CUDA, ISY_ERR_WORKSPACE, ISY_ERR_OVERFLOW = 0, -1, -2, -3, -4
 SKY_NONE, SKY_UNIFORM, SKY_PEREZ = 0, 1, 2
 FLAG_INIT_FROM_SKY, FLAG_BRUTE_FORCE, FLAG_SUN_PER_VIEW, FLAG_OUT_F64, FLAG_PER_VIEW_SKY = 1, 2, 4, 8, 16
@@ -33,7 +34,20 @@ class SkyParams(ctypes.Structure):
 
 class Outputs(ctypes.Structure):
     _fields_ = [("rgb", ctypes.c_void_p), ("hit", ctypes.c_void_p), ("depth", ctypes.c_void_p),
-                ("Y", ctypes.c_void_p), ("dop", ctypes.c_void_p), ("aop", ctypes.c_void_p)]
+                ("Y", ctypes.c_void_p), ("dop", ctypes.c_void_p), ("aop", ctypes.c_void_p), ("resp", ctypes.c_void_p)]
+
+
+class SensorParams(ctypes.Structure):
+    """isy_sensor_params: the photoreceptor transform behind the `resp` output (include/isy_b200.h)."""
+    _fields_ = [("w_rgb", ctypes.c_float * 3), ("gain", ctypes.c_float), ("channels", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+    @staticmethod
+    def make(w_rgb=(1., 1., 1.), gain=1., channels=3):
+        sp = SensorParams()
+        sp.w_rgb[0], sp.w_rgb[1], sp.w_rgb[2] = (float(v) for v in w_rgb)
+        sp.gain, sp.channels, sp.reserved = float(gain), int(channels), 0
+        return sp
 
 
 class IsyError(RuntimeError):
@@ -68,13 +82,13 @@ def lib():
     L.isy_eye_rays.restype = i64
     L.isy_render_workspace_bytes.argtypes = [vp, vp, i64, i64]
     L.isy_render_workspace_bytes.restype = ctypes.c_size_t
-    L.isy_render.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, ctypes.POINTER(SkyParams), ctypes.c_uint32,
-                             ctypes.POINTER(Outputs), vp, ctypes.c_size_t, vp]
+    L.isy_render.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, ctypes.POINTER(SkyParams), ctypes.POINTER(SensorParams),
+                             ctypes.c_uint32, ctypes.POINTER(Outputs), vp, ctypes.c_size_t, vp]
     L.isy_workspace_status.argtypes = [vp, vp]
     L.isy_workspace_phase_cycles.argtypes = [vp, vp, vp]
     L.isy_workspace_phase_cycles.restype = ctypes.c_int
-    L.isy_render_host.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, ctypes.POINTER(SkyParams), ctypes.c_uint32,
-                                  ctypes.POINTER(Outputs)]
+    L.isy_render_host.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, ctypes.POINTER(SkyParams),
+                                  ctypes.POINTER(SensorParams), ctypes.c_uint32, ctypes.POINTER(Outputs)]
     L.isy_world_call_host.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
     L.isy_sky_call_host.argtypes = [ctypes.POINTER(SkyParams), dbl, dbl, vp, i64, vp, ctypes.c_int, vp, vp, vp, vp, vp]
     L.isy_spectrum_influence_host.argtypes = [vp, i64, vp, i64, ctypes.c_int, vp, vp]
@@ -82,7 +96,7 @@ def lib():
                  "isy_workspace_status", "isy_render_host", "isy_world_call_host", "isy_sky_call_host",
                  "isy_spectrum_influence_host"):
         getattr(L, name).restype = ctypes.c_int
-    if L.isy_abi_version() != 1:
+    if L.isy_abi_version() != ABI_VERSION:
         raise ImportError("libisy_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -165,7 +165,11 @@ __device__ __forceinline__ void write_view(const RenderParams& rp, size_t b, int
         const double sA = o.sA, cA = o.cA;
         double wr = w * o.r, wg = w * o.g, wb = w * o.b;
         double wY = w * o.Y, wP = w * o.P, wS = w * sA, wC = w * cA;
+        o.sr *= w, o.sg *= w, o.sb *= w;
         for (int off = S >> 1; off > 0; off >>= 1) {
+            o.sr += __shfl_xor_sync(0xffffffffu, o.sr, off);
+            o.sg += __shfl_xor_sync(0xffffffffu, o.sg, off);
+            o.sb += __shfl_xor_sync(0xffffffffu, o.sb, off);
             wr += __shfl_xor_sync(0xffffffffu, wr, off);
             wg += __shfl_xor_sync(0xffffffffu, wg, off);
             wb += __shfl_xor_sync(0xffffffffu, wb, off);
@@ -189,6 +193,7 @@ __device__ __forceinline__ void write_view(const RenderParams& rp, size_t b, int
     if (rp.out.Y) store_val<T>(rp.out.Y, oi, o.Y);
     if (rp.out.dop) store_val<T>(rp.out.dop, oi, o.P);
     if (rp.out.aop) store_val<T>(rp.out.aop, oi, o.A);
+    if (rp.out.resp) sensor_store<T>(rp.sensor, rp.out.resp, oi, o.sr, o.sg, o.sb);
 }
 
 }  // namespace isy

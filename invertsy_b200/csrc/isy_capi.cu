@@ -95,12 +95,26 @@ int isy_abi_version(void) { return ISY_ABI_VERSION; }
 const char* isy_last_error(void) { return g_err.c_str(); }
 int64_t isy_launch_count(void) { return g_launches.load(); }
 
+static int world_fill(isy_world* w, const float* tri_xyz, const float* tri_rgb, int64_t T, double horizon);
+
 int isy_world_create(const float* tri_xyz, const float* tri_rgb, int64_t T, double horizon, int device,
                      isy_world** out) {
     if (!tri_xyz || !tri_rgb || !out || T < 0 || T >= (1 << 30)) return fail(ISY_ERR_INVALID, "isy_world_create: bad argument");
     DeviceGuard g(device);
     if (!g.ok) return fail(ISY_ERR_CUDA, "isy_world_create: cannot select CUDA device %d (no CPU fallback)", device);
-    isy_world* w = new isy_world{device, T, horizon, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, 1.f, 1, 1};
+    isy_world* w = new isy_world{device, T, horizon, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, 1.f, 1, 1, nullptr};
+    const int rc = world_fill(w, tri_xyz, tri_rgb, T, horizon);
+    if (rc != ISY_OK) {          // nothing allocated so far outlives a failed creation
+        const std::string msg = g_err;
+        isy_world_destroy(w);
+        g_err = msg;
+        return rc;
+    }
+    *out = w;
+    return ISY_OK;
+}
+
+static int world_fill(isy_world* w, const float* tri_xyz, const float* tri_rgb, int64_t T, double horizon) {
     size_t n = (size_t)std::max<int64_t>(T, 1);
     std::vector<float> planes(9 * n);
     for (int64_t t = 0; t < T; ++t)
@@ -116,8 +130,6 @@ int isy_world_create(const float* tri_xyz, const float* tri_rgb, int64_t T, doub
         CUDA_TRY(cudaMalloc(&w->d_aos, 12 * n * sizeof(float)));
         CUDA_TRY(cudaMemcpy(w->d_aos, aos.data(), 12 * n * sizeof(float), cudaMemcpyHostToDevice));
     }
-    if (T >= (1 << 30)) return fail(ISY_ERR_INVALID, "isy_world_create: too many triangles");
-
     // ---- xy cell grid over the vertices ----
     {
         float xmin = 0.f, xmax = 1.f, ymin = 0.f, ymax = 1.f;
@@ -164,7 +176,6 @@ int isy_world_create(const float* tri_xyz, const float* tri_rgb, int64_t T, doub
         CUDA_TRY(cudaMemcpy(w->d_cell_start, start.data(), (ncell + 1) * sizeof(unsigned int), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(w->d_cell_tris, list.data(), list.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
     }
-    *out = w;
     return ISY_OK;
 }
 
@@ -182,6 +193,8 @@ int isy_world_destroy(isy_world* w) {
 
 int64_t isy_world_triangles(const isy_world* w) { return w ? w->T : -1; }
 
+static int eye_fill(isy_eye* e, const double* omm_quat, const float* weights, int32_t S);
+
 int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int32_t S, int device, isy_eye** out) {
     if (!omm_quat || !out || N <= 0 || S <= 0) return fail(ISY_ERR_INVALID, "isy_eye_create: bad argument");
     if (S > 32 || (S & (S - 1))) return fail(ISY_ERR_INVALID, "isy_eye_create: samples per ommatidium must be 1,2,4,8,16 or 32 (got %d)", S);
@@ -189,6 +202,18 @@ int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int3
     DeviceGuard g(device);
     if (!g.ok) return fail(ISY_ERR_CUDA, "isy_eye_create: cannot select CUDA device %d (no CPU fallback)", device);
     isy_eye* e = new isy_eye{device, N, S, N * S, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr};
+    const int rc = eye_fill(e, omm_quat, weights, S);
+    if (rc != ISY_OK) {
+        const std::string msg = g_err;
+        isy_eye_destroy(e);
+        g_err = msg;
+        return rc;
+    }
+    *out = e;
+    return ISY_OK;
+}
+
+static int eye_fill(isy_eye* e, const double* omm_quat, const float* weights, int32_t S) {
     size_t R = (size_t)e->R;
     CUDA_TRY(cudaMalloc(&e->d_quat, R * 4 * sizeof(double)));
     CUDA_TRY(cudaMalloc(&e->d_py, R * 2 * sizeof(double)));
@@ -274,7 +299,6 @@ int isy_eye_create(const double* omm_quat, const float* weights, int64_t N, int3
         CUDA_TRY(cudaMemcpy(e->d_cells_start, cstart.data(), (ncell + 1) * sizeof(unsigned int), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(e->d_cells_list, clist.data(), R * sizeof(unsigned int), cudaMemcpyHostToDevice));
     }
-    *out = e;
     return ISY_OK;
 }
 
@@ -361,10 +385,10 @@ Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
     pl.off_entry = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(Entry));
     pl.off_exact = off, off += align_up((size_t)pl.grid * pl.slab_cap * sizeof(Exact));
     pl.off_best = off, off += pl.global_best ? align_up((size_t)pl.grid * e->R * sizeof(unsigned int)) : 0;
-    // launch-wide row templates of small eyes: sky table [3][H][R], template rows [5R]
+    // launch-wide row templates of small eyes: sky table [4][H][R], template rows [6R]
     pl.rows = !pl.global_best && P >= kRowsMinP && P * H >= kRowsMinViews && (size_t)H * e->R * 3 * sizeof(float) <= kSkyTabMaxBytes;
-    pl.off_skytab = off, off += pl.rows ? align_up((size_t)H * e->R * 3 * sizeof(float)) : 0;
-    pl.off_rowbg = off, off += pl.rows ? align_up((size_t)e->R * 5 * sizeof(float)) : 0;
+    pl.off_skytab = off, off += pl.rows ? align_up((size_t)H * e->R * 4 * sizeof(float)) : 0;   // Y, DoP, AoP, response
+    pl.off_rowbg = off, off += pl.rows ? align_up((size_t)e->R * 6 * sizeof(float)) : 0;        // hit, depth, rgb, response
     pl.stage_cap = std::min(pl.slab_cap, 4096);   // vertices of a position culled ahead (9 planes per CTA)
     pl.off_stage = off, off += (ISY_CULL_AHEAD && pl.rows) ? align_up((size_t)pl.grid * 9 * pl.stage_cap * sizeof(float)) : 0;
     pl.total = off;
@@ -373,7 +397,8 @@ Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
 
 int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, const double* pos, const double* yaw,
                   const double* vquat, const double* sun, const double* init_c, const isy_sky_params* sky,
-                  uint32_t flags, const isy_outputs* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                  const isy_sensor_params* sensor, uint32_t flags, const isy_outputs* out, void* ws, size_t ws_bytes,
+                  cudaStream_t st) {
     if (!w || !e || !pos || !out || P < 0 || H <= 0) return fail(ISY_ERR_INVALID, "isy_render: bad argument");
     if (w->device != e->device) return fail(ISY_ERR_INVALID, "isy_render: world and eye live on different devices");
     if (P * H * e->R >= (1ll << 31) * 1024) return fail(ISY_ERR_INVALID, "isy_render: batch too large");
@@ -384,6 +409,8 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
     if (sp.kind == ISY_SKY_PEREZ && !sun) return fail(ISY_ERR_INVALID, "isy_render: Perez sky needs a sun position");
     if ((out->Y || out->dop || out->aop) && sp.kind == ISY_SKY_NONE)
         return fail(ISY_ERR_INVALID, "isy_render: sky outputs requested without a sky");
+    if (out->resp && (!sensor || (sensor->channels != 1 && sensor->channels != 3)))
+        return fail(ISY_ERR_INVALID, "isy_render: photoreceptor responses need isy_sensor_params with 1 or 3 channels");
     Plan pl = make_plan(w, e, P, H);
     if (!ws || ws_bytes < pl.total)
         return fail(ISY_ERR_WORKSPACE, "isy_render: workspace %zu B < required %zu B", ws_bytes, pl.total);
@@ -414,6 +441,7 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
     rp.sun = (const SunConst*)(base + pl.off_sun);
     rp.sun_per_view = (flags & ISY_FLAG_SUN_PER_VIEW) ? 1 : 0;
     rp.sky = sp, rp.flags = flags, rp.out = *out;
+    if (out->resp) rp.sensor = *sensor;
     rp.queue = (unsigned int*)(base + pl.off_queue);
     rp.status = (int*)(base + pl.off_status);
     rp.phase_cycles = (unsigned long long*)(base + pl.off_status + 64);
@@ -444,7 +472,11 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
     rp.cells_start = e->d_cells_start, rp.cells_list = e->d_cells_list;
     rp.cells_rows = e->cells_rows, rp.cells_cols = e->cells_cols;
 
-    CUDA_TRY(cudaMemsetAsync(base, 0, 512, st));
+    // work counter, heading flag and phase cycles start from zero in every launch; the status word is sticky: it is
+    // cleared when it is read (check_status), or when the workspace is seen for the first time
+    ws_reset_kernel<<<1, 32, 0, st>>>(reinterpret_cast<unsigned int*>(base));
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
     if (sp.kind == ISY_SKY_PEREZ) {
         int n = rp.sun_per_view ? (int)(P * H) : 1;
         sun_setup_kernel<<<(n + 127) / 128, 128, 0, st>>>(sun, n, sp, (SunConst*)(base + pl.off_sun));
@@ -462,7 +494,8 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
     }
     const int eye_kind0 = (vquat || !e->d_sorted) ? kEyeAny : (pl.global_best ? kEyeLarge : kEyeSmall);
     if (pl.rows && eye_kind0 == kEyeSmall && !init_c && e->S == 1 && !(sp.kind == ISY_SKY_PEREZ && rp.sun_per_view) &&
-        !(flags & (ISY_FLAG_OUT_F64 | ISY_FLAG_INIT_FROM_SKY | ISY_FLAG_BRUTE_FORCE | ISY_FLAG_PER_VIEW_SKY))) {
+        !(flags & (ISY_FLAG_OUT_F64 | ISY_FLAG_INIT_FROM_SKY | ISY_FLAG_BRUTE_FORCE | ISY_FLAG_PER_VIEW_SKY)) &&
+        !(out->resp && sensor->channels != 1)) {
         // Rows mode (isy_shade.cuh): template rows are streamed into the views while the copies are rasterised and only
         // the rays that hit something are patched afterwards.  Under a Perez sky that needs every position to look
         // along the same row of headings (grids, heat maps): checked here, on the device, in every such call; the
@@ -471,7 +504,8 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
         float* tab = (float*)(base + pl.off_skytab);
         float* bg = (float*)(base + pl.off_rowbg);
         const bool want_sky = out->Y || out->dop || out->aop;
-        if (sp.kind == ISY_SKY_PEREZ && want_sky) {
+        const int want_resp = out->resp ? 1 : 0;
+        if (sp.kind == ISY_SKY_PEREZ && (want_sky || want_resp)) {
             if (yaw) {
                 const long long n = (long long)P * H;
                 const int blocks = (int)std::min<long long>((n + 255) / 256, 4 * device_sms(w->device));
@@ -483,7 +517,8 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
             sky_shared_kernel<<<(n + 127) / 128, 128, 0, st>>>(yaw, (int)H, (int)e->R, e->d_py, e->d_trig,
                                                               (const double*)(base + pl.off_ftheta), sp,
                                                               (const SunConst*)(base + pl.off_sun),
-                                                              (const double2*)(base + pl.off_gtab), differs, tab);
+                                                              (const double2*)(base + pl.off_gtab), differs, tab, want_resp,
+                                                              rp.sensor);
             g_launches++;
             CUDA_TRY(cudaGetLastError());
             rp.sky_rows_h = (int)H;
@@ -491,12 +526,13 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
             rp.sky_rows_h = 1;
         }
         row_templates_kernel<<<(unsigned)((e->R + 127) / 128), 128, 0, st>>>(e->d_py, (int)e->R, sp.kind == ISY_SKY_UNIFORM && want_sky,
-                                                                            (float)sp.luminance, bg, tab);
+                                                                            sp.luminance, bg, tab, want_resp,
+                                                                            sp.kind != ISY_SKY_NONE, rp.sensor);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
-        rp.sky_tab = tab, rp.sky_tab_off = differs, rp.row_bg = bg;
+        rp.sky_tab = tab, rp.sky_tab_off = differs, rp.row_bg = bg, rp.resp_bg = bg + 5 * (size_t)e->R;
         {   // 16 bytes per lane needs rows that start on 16-byte boundaries in every buffer that is written
-            const void* ptrs[6] = {out->rgb, out->hit, out->depth, out->Y, out->dop, out->aop};
+            const void* ptrs[7] = {out->rgb, out->hit, out->depth, out->Y, out->dop, out->aop, out->resp};
             bool aligned = (e->R & 3) == 0;
             for (const void* q : ptrs) aligned = aligned && ((uintptr_t)q & 15u) == 0;
             rp.rows_vec4 = aligned ? 1 : 0;
@@ -530,6 +566,7 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
 int check_status(void* ws, cudaStream_t st) {
     int status = 0;
     CUDA_TRY(cudaMemcpyAsync(&status, (unsigned char*)ws + 256, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemsetAsync((unsigned char*)ws + 256, 0, sizeof(int), st));     // read = cleared
     CUDA_TRY(cudaStreamSynchronize(st));
     if (status == ISY_ERR_OVERFLOW)
         return fail(ISY_ERR_OVERFLOW, "isy_render: a position sees more triangle copies than the workspace slab holds");
@@ -555,11 +592,12 @@ size_t isy_render_workspace_bytes(const isy_world* w, const isy_eye* e, int64_t 
 
 int isy_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, const double* pos_dev,
                const double* yaw_dev, const double* view_quat_dev, const double* sun_dev, const isy_sky_params* sky,
-               uint32_t flags, const isy_outputs* out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+               const isy_sensor_params* sensor, uint32_t flags, const isy_outputs* out_dev, void* workspace_dev,
+               size_t workspace_bytes, void* stream) {
     if (!w) return fail(ISY_ERR_INVALID, "isy_render: null world");
     DeviceGuard g(w->device);
     if (!g.ok) return fail(ISY_ERR_CUDA, "isy_render: cannot select CUDA device %d (no CPU fallback)", w->device);
-    return launch_render(w, e, P, H, pos_dev, yaw_dev, view_quat_dev, sun_dev, nullptr, sky, flags, out_dev,
+    return launch_render(w, e, P, H, pos_dev, yaw_dev, view_quat_dev, sun_dev, nullptr, sky, sensor, flags, out_dev,
                          workspace_dev, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -606,7 +644,10 @@ extern "C" {
 
 int isy_render_host(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, const double* pos_host,
                     const double* yaw_host, const double* view_quat_host, const double* sun_host,
-                    const isy_sky_params* sky, uint32_t flags, const isy_outputs* out_host) {
+                    const isy_sky_params* sky, const isy_sensor_params* sensor, uint32_t flags,
+                    const isy_outputs* out_host) {
+    if (out_host && out_host->resp && (!sensor || (sensor->channels != 1 && sensor->channels != 3)))
+        return fail(ISY_ERR_INVALID, "isy_render_host: photoreceptor responses need isy_sensor_params with 1 or 3 channels");
     if (!w || !e || !pos_host || !out_host || P < 0 || H <= 0) return fail(ISY_ERR_INVALID, "isy_render_host: bad argument");
     if (w->device < 0 || w->device >= 16) return fail(ISY_ERR_INVALID, "isy_render_host: device index out of range");
     DeviceGuard g(w->device);
@@ -628,9 +669,11 @@ int isy_render_host(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, 
     const bool sun_pv = flags & ISY_FLAG_SUN_PER_VIEW;
 
     // positions are processed in chunks so that the compute of chunk c+1 overlaps the D2H of chunk c
-    const size_t per_view[6] = {out_host->rgb ? 3 * (size_t)N * esz : 0, out_host->hit ? (size_t)R * 4 : 0,
-                                out_host->depth ? (size_t)R * esz : 0, out_host->Y ? (size_t)N * esz : 0,
-                                out_host->dop ? (size_t)N * esz : 0, out_host->aop ? (size_t)N * esz : 0};
+    constexpr int kOut = 7;
+    const size_t per_view[kOut] = {out_host->rgb ? 3 * (size_t)N * esz : 0, out_host->hit ? (size_t)R * 4 : 0,
+                                   out_host->depth ? (size_t)R * esz : 0, out_host->Y ? (size_t)N * esz : 0,
+                                   out_host->dop ? (size_t)N * esz : 0, out_host->aop ? (size_t)N * esz : 0,
+                                   out_host->resp ? (size_t)N * sensor->channels * esz : 0};
     size_t bytes_per_pos = 0;
     for (size_t b : per_view) bytes_per_pos += (size_t)H * b;
     int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(P, (int64_t)((96ull << 20) / std::max<size_t>(bytes_per_pos, 1))));
@@ -651,16 +694,17 @@ int isy_render_host(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, 
     if (d_sun) CUDA_TRY(cudaMemcpyAsync(d_sun, sun_host, n_sun * 8, cudaMemcpyHostToDevice, cx.s_comp));
 
     const size_t ws_bytes = align_up(isy_render_workspace_bytes(w, e, chunk, H));
-    size_t off[7];
+    size_t off[kOut + 1];
     size_t total = ws_bytes;
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < kOut; ++k) {
         off[k] = total;
         total += align_up((size_t)chunk * H * per_view[k]);
     }
-    off[6] = total;
+    off[kOut] = total;
     for (int i = 0; i < nslots; ++i) CUDA_TRY(grow(&cx.arena[i], &cx.arena_bytes[i], total));
 
-    void* const host_ptr[6] = {out_host->rgb, out_host->hit, out_host->depth, out_host->Y, out_host->dop, out_host->aop};
+    void* const host_ptr[kOut] = {out_host->rgb, out_host->hit, out_host->depth, out_host->Y, out_host->dop, out_host->aop,
+                                  out_host->resp};
     int rc = ISY_OK, ci = 0;
     for (int64_t p0 = 0; p0 < P && rc == ISY_OK; p0 += chunk, ++ci) {
         const int sl = ci % nslots;
@@ -675,13 +719,14 @@ int isy_render_host(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, 
         o.Y = per_view[3] ? base + off[3] : nullptr;
         o.dop = per_view[4] ? base + off[4] : nullptr;
         o.aop = per_view[5] ? base + off[5] : nullptr;
+        o.resp = per_view[6] ? base + off[6] : nullptr;
         rc = launch_render(w, e, pc, H, d_pos + 3 * p0, d_yaw ? d_yaw + v0 : nullptr, d_vq ? d_vq + 4 * v0 : nullptr,
-                           d_sun ? (sun_pv ? d_sun + 2 * v0 : d_sun) : nullptr, nullptr, sky, flags, &o, base, ws_bytes,
-                           cx.s_comp);
+                           d_sun ? (sun_pv ? d_sun + 2 * v0 : d_sun) : nullptr, nullptr, sky, sensor, flags, &o, base,
+                           ws_bytes, cx.s_comp);
         if (rc != ISY_OK) break;
         CUDA_TRY(cudaEventRecord(cx.done[sl], cx.s_comp));
         CUDA_TRY(cudaStreamWaitEvent(cx.s_copy, cx.done[sl], 0));
-        for (int k = 0; k < 6; ++k) {
+        for (int k = 0; k < kOut; ++k) {
             if (!per_view[k]) continue;
             CUDA_TRY(cudaMemcpyAsync((unsigned char*)host_ptr[k] + v0 * per_view[k], base + off[k], V * per_view[k],
                                      cudaMemcpyDeviceToHost, cx.s_copy));
@@ -785,7 +830,7 @@ int isy_world_call_host(const isy_world* w, const double* pos3_host, const doubl
     if (depth_host) o.depth = d_depth;
     if (hit_host) o.hit = d_hit;
     rc = launch_render(w, &eye, 1, 1, d_in, nullptr, nullptr, nullptr, init_c_host ? d_in + 3 + 4 * n : nullptr, nullptr,
-                       ISY_FLAG_OUT_F64, &o, dev + off_ws, ws_bytes, cx->st);
+                       nullptr, ISY_FLAG_OUT_F64, &o, dev + off_ws, ws_bytes, cx->st);
     if (rc != ISY_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(pin, d_rgb, out_bytes, cudaMemcpyDeviceToHost, cx->st));
     rc = check_status(dev + off_ws, cx->st);   // synchronises the stream

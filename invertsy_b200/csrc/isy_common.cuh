@@ -107,7 +107,10 @@ struct RenderParams {
     const int* sky_tab_off;  // nonzero: the positions turned out NOT to share their headings (heading_rows_kernel)
     const float* row_bg;     // [R] hit = -1 | [R] depth = NaN | [3R] ground colour / NaN by the ray's pitch
     int rows_vec4;           // rows are 16-byte aligned (R a multiple of 4, output buffers aligned): 16 bytes per lane
+    const float* resp_bg;    // rows mode, [R]: photoreceptor response of a ray that hits nothing under no / a uniform sky
+                             // (under a Perez sky it is plane 3 of sky_tab, one row per heading)
     isy_sky_params sky;
+    isy_sensor_params sensor; // photoreceptor transform behind out.resp
     uint32_t flags;
     isy_outputs out;
     // workspace
@@ -126,6 +129,45 @@ struct RenderParams {
     int splits;              // CTAs sharing one position (each redoes the cull, takes every splits-th group)
     int items;               // P * splits
 };
+
+// ---- photoreceptor transform behind out.resp (isy_sensor_params in isy_b200.h) ----
+// colour of one cone sample on the 0..1 scale: triangle colour, else ground, else the sky colour of its luminance
+// (luminance2skycolour / 255, world.py:465-479), else nothing
+__device__ __forceinline__ void sensor_colour(bool hit, float tr, float tg, float tb, bool ground, bool has_sky, double Y,
+                                              float& r, float& g, float& b) {
+    if (hit) {
+        r = tr, g = tg, b = tb;
+    } else if (ground) {
+        r = (float)(229.0 / 255.0), g = (float)(183.0 / 255.0), b = (float)(90.0 / 255.0);
+    } else if (has_sky) {
+        r = (float)(fmin(fmax(19.0 * Y + 13.0, 0.0), 255.0) / 255.0);
+        g = (float)(fmin(fmax(19.0 * Y + 135.0, 0.0), 255.0) / 255.0);
+        b = (float)(fmin(fmax(19.0 * Y + 201.0, 0.0), 255.0) / 255.0);
+    } else {
+        r = 0.f, g = 0.f, b = 0.f;
+    }
+}
+// (cone-averaged) colour -> responses: clip(colour * w * gain, 0, 1) per channel
+__device__ __forceinline__ void sensor_finish(const isy_sensor_params& sp, float& r, float& g, float& b) {
+    r = fminf(fmaxf((r * sp.w_rgb[0]) * sp.gain, 0.f), 1.f);
+    g = fminf(fmaxf((g * sp.w_rgb[1]) * sp.gain, 0.f), 1.f);
+    b = fminf(fmaxf((b * sp.w_rgb[2]) * sp.gain, 0.f), 1.f);
+}
+// PN input of the three responses: clip(mean over channels, 0, 1)  (agent.py:744)
+__device__ __forceinline__ float sensor_pn(float r, float g, float b) {
+    return fminf(fmaxf((r + g + b) * (1.0f / 3.0f), 0.f), 1.f);
+}
+// stores the response(s) of ommatidium `oi` (element index b*N + n) from its cone-averaged 0..1 colour
+template <typename T>
+__device__ __forceinline__ void sensor_store(const isy_sensor_params& sp, void* resp, size_t oi, float r, float g, float b) {
+    sensor_finish(sp, r, g, b);
+    T* q = reinterpret_cast<T*>(resp);
+    if (sp.channels == 1) {
+        __stcs(q + oi, (T)sensor_pn(r, g, b));
+    } else {
+        __stcs(q + 3 * oi, (T)r), __stcs(q + 3 * oi + 1, (T)g), __stcs(q + 3 * oi + 2, (T)b);
+    }
+}
 
 // ---- exact fp64 arithmetic in the reference's order (no FMA contraction) ----
 __device__ __forceinline__ double cross2_rn(double u0, double u1, double v0, double v1) {

@@ -68,6 +68,7 @@ struct SmemLayout {
     // Launches that are not in rows mode do not allocate this tail (kSmemBase bytes of dynamic shared memory).
     float rgb[kMaxE * 3];                         // colour of each copy's triangle
     unsigned short sorted_ray16[kGridRaysSmem];   // ray index of each pitch-sorted position
+    float resp1[kMaxE];                           // PN response of a ray that hits each copy's triangle (out.resp, 1 channel)
 };
 constexpr size_t kSmemBase = offsetof(SmemLayout, rgb);
 static_assert(kSmemBase <= 192 * 1024, "leave some of the 228 KB for L1");
@@ -77,6 +78,7 @@ struct RayOut {
     double r, g, b;
     double Y, P, A;
     double sA, cA;   // sin / cos of A for the cone average (S > 1), formed without the angle itself
+    float sr, sg, sb; // the sample's colour on the 0..1 scale for the photoreceptor transform (out.resp)
 };
 
 template <typename T>

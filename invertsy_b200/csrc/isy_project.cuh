@@ -219,7 +219,7 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
                                 int ahead_cap, int* s_nent, int* s_band, long long* t_mid = nullptr) {
     // ahead != null: position p was culled ahead (vis[] filled, vertices in ahead_stage, ahead->count of them)
     const int tid = threadIdx.x;
-    if (rp.T == 0) {   // no world (sky-only calls): nothing to cull
+    if (rp.T == 0 || rp.horizon_sq_max < 0) {   // no world (sky-only calls) or a negative horizon (world.py:98): nothing to cull
         if (tid == 0) s_band[0] = float_key(CUDART_INF_F), s_band[1] = float_key(-CUDART_INF_F);
         return 0;
     }
@@ -290,6 +290,13 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
             for (int c = 0; c < 3; ++c) {
                 if (slot < kMaxE) sm.rgb[3 * slot + c] = col[c];
                 if (seam && slot + 1 < kMaxE) sm.rgb[3 * (slot + 1) + c] = col[c];
+            }
+            if (rp.out.resp) {   // what a ray that hits this triangle answers (one channel in rows mode)
+                float sr = col[0], sg = col[1], sb = col[2];
+                sensor_finish(rp.sensor, sr, sg, sb);
+                const float pn = sensor_pn(sr, sg, sb);
+                if (slot < kMaxE) sm.resp1[slot] = pn;
+                if (seam && slot + 1 < kMaxE) sm.resp1[slot + 1] = pn;
             }
         }
         if (slot + (seam ? 2 : 1) <= rp.slab_cap) {

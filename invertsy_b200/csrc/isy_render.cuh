@@ -349,6 +349,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                         const float* col = rp.tri_rgb + 3 * (size_t)ray.hit;
                         o.r = __ldg(col + 0), o.g = __ldg(col + 1), o.b = __ldg(col + 2);
                     }
+                    o.sr = 0.f, o.sg = 0.f, o.sb = 0.f;
+                    if (rp.out.resp)
+                        sensor_colour(ray.hit >= 0, (float)o.r, (float)o.g, (float)o.b, ray.pitch >= 0, want_sky, o.Y, o.sr, o.sg, o.sb);
                     write_view<kF64>(rp, b, rr, valid, ray.hit, ray.best, o);
                 }
             }

@@ -4,6 +4,20 @@
 
 namespace isy {
 
+// Head of a render workspace: [0] work counter, [32] "positions differ in their headings" flag (+128 B), [64] sticky
+// status (+256 B), [66..67] cookie, [80..95] phase cycles (+320 B).  Every launch restarts the counter, the flag and
+// the cycle sums; the status survives until it is read (isy_workspace_status), so that an overflow in any launch
+// on this workspace is reported.  A workspace seen for the first time (no cookie) starts with a clean status.
+constexpr unsigned int kWsCookie0 = 0x69737962u, kWsCookie1 = 0x32303062u;
+__global__ void ws_reset_kernel(unsigned int* __restrict__ head) {
+    const int t = threadIdx.x;
+    if (t == 0) {
+        head[0] = 0u, head[32] = 0u;
+        if (head[66] != kWsCookie0 || head[67] != kWsCookie1) head[64] = 0u, head[66] = kWsCookie0, head[67] = kWsCookie1;
+    }
+    if (t < 16) head[80 + t] = 0u;
+}
+
 // eye-frame (pitch, yaw) and their sines / cosines from the ommatidia quaternions, once per eye
 __global__ void eye_setup_kernel(const double* __restrict__ quat, double* __restrict__ py, double* __restrict__ trig,
                                  int R) {
@@ -93,7 +107,7 @@ __global__ void sky_shared_kernel(const double* __restrict__ yaw, int H, int R, 
                                   const double* __restrict__ eye_trig, const double* __restrict__ f_theta,
                                   isy_sky_params sp, const SunConst* __restrict__ sun,
                                   const double2* __restrict__ gtab, const int* __restrict__ differs,
-                                  float* __restrict__ tab) {
+                                  float* __restrict__ tab, int want_resp, isy_sensor_params sensor) {
     if (*differs) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= H * R) return;
@@ -108,13 +122,20 @@ __global__ void sky_shared_kernel(const double* __restrict__ yaw, int H, int R, 
                     false, gtab);
     const size_t plane = (size_t)H * (size_t)R;
     tab[i] = (float)Y, tab[plane + i] = (float)P, tab[2 * plane + i] = (float)A;
+    if (want_resp) {   // plane 3: the PN response of this (heading, ray) when the ray hits nothing
+        float sr, sg, sb;
+        sensor_colour(false, 0.f, 0.f, 0.f, eye_py[2 * (size_t)r] >= 0, true, Y, sr, sg, sb);
+        sensor_finish(sensor, sr, sg, sb);
+        tab[3 * plane + i] = sensor_pn(sr, sg, sb);
+    }
 }
 
 // Template rows of a launch in rows mode (isy_shade.cuh): what a ray that hits nothing gets -- hit = -1, depth = NaN,
 // the ground colour or NaN by its own pitch (world.py:80, :90) -- and, under a uniform sky, the three constant sky
 // rows (sky.py:77-79: y = luminance, p = 0, a = NaN).
-__global__ void row_templates_kernel(const double* __restrict__ eye_py, int R, int uniform_sky, float luminance,
-                                     float* __restrict__ bg, float* __restrict__ sky_rows) {
+__global__ void row_templates_kernel(const double* __restrict__ eye_py, int R, int uniform_sky, double luminance,
+                                     float* __restrict__ bg, float* __restrict__ sky_rows, int want_resp, int has_sky,
+                                     isy_sensor_params sensor) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     const float nanf_ = __int_as_float(0x7fc00000);
@@ -124,7 +145,13 @@ __global__ void row_templates_kernel(const double* __restrict__ eye_py, int R, i
     bg[2 * (size_t)R + 3 * r + 0] = ground ? (float)(229.0 / 255.0) : nanf_;
     bg[2 * (size_t)R + 3 * r + 1] = ground ? (float)(183.0 / 255.0) : nanf_;
     bg[2 * (size_t)R + 3 * r + 2] = ground ? (float)(90.0 / 255.0) : nanf_;
-    if (uniform_sky) sky_rows[r] = luminance, sky_rows[R + r] = 0.f, sky_rows[2 * (size_t)R + r] = nanf_;
+    if (uniform_sky) sky_rows[r] = (float)luminance, sky_rows[R + r] = 0.f, sky_rows[2 * (size_t)R + r] = nanf_;
+    if (want_resp) {   // PN response of a ray that hits nothing under no sky / a uniform sky (constant luminance)
+        float sr, sg, sb;
+        sensor_colour(false, 0.f, 0.f, 0.f, ground, has_sky != 0, luminance, sr, sg, sb);
+        sensor_finish(sensor, sr, sg, sb);
+        bg[5 * (size_t)R + r] = sensor_pn(sr, sg, sb);
+    }
 }
 
 }  // namespace isy

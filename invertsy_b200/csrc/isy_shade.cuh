@@ -116,6 +116,8 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
                     const float* col = rp.tri_rgb + 3 * (size_t)hit;
                     cr = __ldg(col + 0), cg = __ldg(col + 1), cb = __ldg(col + 2);
                 }
+                float sr = 0.f, sg = 0.f, sb = 0.f;      // the sample on the 0..1 scale of the photoreceptor transform
+                if (rp.out.resp) sensor_colour(id[q] != kNoCopy, cr, cg, cb, ground, perez || uniform, Y[q], sr, sg, sb);
                 if (kCone) {
                     if (valid) {
                         const size_t i = off0 + q * ostride;
@@ -129,6 +131,13 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
                     float fr = wray * cr, fg = wray * cg, fb = wray * cb;
                     float wP = wray * (float)P[q], wS = wray * sA[q], wC = wray * cA[q];
                     if (from_sky) wr = (double)wray * cr, wg = (double)wray * cg, wb = (double)wray * cb;
+                    sr *= wray, sg *= wray, sb *= wray;
+                    if (rp.out.resp)
+                        for (int off = rp.S >> 1; off > 0; off >>= 1) {
+                            sr += __shfl_xor_sync(0xffffffffu, sr, off);
+                            sg += __shfl_xor_sync(0xffffffffu, sg, off);
+                            sb += __shfl_xor_sync(0xffffffffu, sb, off);
+                        }
                     for (int off = rp.S >> 1; off > 0; off >>= 1) {
                         wY += __shfl_xor_sync(0xffffffffu, wY, off);
                         wP += __shfl_xor_sync(0xffffffffu, wP, off);
@@ -154,6 +163,7 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
                         if (o_Y) __stcs(o_Y + i, (float)wY);
                         if (o_P) __stcs(o_P + i, wP);
                         if (o_A) __stcs(o_A + i, perez ? atan2_fast(wS, wC) : nanf_);   // circular mean of the angles
+                        if (rp.out.resp) sensor_store<float>(rp.sensor, rp.out.resp, i, sr, sg, sb);
                     }
                 } else {
                     // streaming stores: the views are written once and never read back by the kernel, so they
@@ -169,6 +179,7 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
                     if (kAllOut || o_Y) __stcs(o_Y + i, (float)Y[q]);
                     if (kAllOut || o_P) __stcs(o_P + i, (float)P[q]);
                     if (kAllOut || o_A) __stcs(o_A + i, (float)A[q]);
+                    if (rp.out.resp) sensor_store<float>(rp.sensor, rp.out.resp, i, sr, sg, sb);
                 }
             }
         }
@@ -238,10 +249,23 @@ __device__ void copy_rows(const RenderParams& rp, int p, int grp, int Hcur, int 
             }
         }
     }
-    // B: columns of [hit | depth | rgb (3 rows long) | Y | DoP | AoP of a uniform sky]
+    // A': the per-heading rows of the photoreceptor responses (plane 3 of the table).  They are patched like the
+    // template rows, so they go out with them, late, as normal stores.
+    if (kTemplates && rp.sky_rows_h > 1 && rp.out.resp) {
+        const size_t plane = (size_t)rp.sky_rows_h * (size_t)nR;
+        T* const dk = reinterpret_cast<T*>(rp.out.resp);
+        for (int hh = warp; hh < Hcur; hh += nw) {
+            const T* const src = tab + 3 * plane + (size_t)(grp + hh * rp.ngroups) * nR;
+            T* const dst = dk + (view0 + (size_t)hh * rp.ngroups) * (size_t)nR;
+            for (int c0 = lane; c0 < nR; c0 += 32) dst[c0] = __ldg(src + c0);
+        }
+    }
+    // B: columns of [hit | depth | rgb (3 rows long) | responses (no / uniform sky) | Y | DoP | AoP of a uniform sky]
     const int cR = (nR + 31) >> 5, cC = (3 * nR + 31) >> 5;
-    const int nB = 2 * cR + cC + (rp.sky_rows_h == 1 ? 3 * cR : 0);
-    const int cB0 = kTemplates ? 0 : 2 * cR + cC, cB1 = kSky ? nB : 2 * cR + cC;   // the columns of this call
+    const int cResp = (rp.out.resp && rp.sky_rows_h <= 1) ? cR : 0;
+    const int nT = 2 * cR + cC + cResp;                      // template columns (patched later: normal stores)
+    const int nB = nT + (rp.sky_rows_h == 1 ? 3 * cR : 0);
+    const int cB0 = kTemplates ? 0 : nT, cB1 = kSky ? nB : nT;   // the columns of this call
     const T* const bg = reinterpret_cast<const T*>(rp.row_bg);
     const size_t vstride = (size_t)rp.ngroups;
     for (int c = cB0 + warp; c < cB1; c += nw) {
@@ -258,9 +282,13 @@ __device__ void copy_rows(const RenderParams& rp, int p, int grp, int Hcur, int 
             e = (c - 2 * cR) * 32 + lane, len = 3 * nR;
             src = bg + 2 * (size_t)nR;
             dst = reinterpret_cast<T*>(rp.out.rgb);
+        } else if (c < nT) {
+            e = (c - 2 * cR - cC) * 32 + lane, len = nR;
+            src = bg + 5 * (size_t)nR;
+            dst = reinterpret_cast<T*>(rp.out.resp);
         } else {
-            const int k = (c - 2 * cR - cC) / cR;
-            e = (c - 2 * cR - cC - k * cR) * 32 + lane, len = nR;
+            const int k = (c - nT) / cR;
+            e = (c - nT - k * cR) * 32 + lane, len = nR;
             src = tab + (size_t)k * nR;
             dst = k == 0 ? o_sky[0] : (k == 1 ? o_sky[1] : o_sky[2]);
             stream = true;
@@ -306,6 +334,7 @@ __device__ void final_pass_patch(const RenderParams& rp, SmemLayout& sm, int p, 
             float* qq = o_rgb + 3 * i;
             __stcs(qq, sm.rgb[3 * id]), __stcs(qq + 1, sm.rgb[3 * id + 1]), __stcs(qq + 2, sm.rgb[3 * id + 2]);
         }
+        if (rp.out.resp) __stcs(reinterpret_cast<float*>(rp.out.resp) + i, sm.resp1[id]);
     }
 }
 

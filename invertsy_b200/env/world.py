@@ -39,34 +39,51 @@ class WorldBase(object):
         self.dtype = dtype
         self.name = name
         self.device = device
-        self.__handle = None
-        self.__handle_key = None
+        self.__handles = {}          # device -> (handle, key of the arrays it was built from)
 
-    # ---- device handle (lazy; rebuilt if the arrays were replaced) ----
-    def _device_world(self):
-        key = (id(self.__polygons), id(self.__colours), float(self.__horizon), int(self.device))
-        if self.__handle is None or self.__handle_key != key:
-            self._release()
+    # ---- device handles (lazy, one per device; rebuilt if the arrays were replaced) ----
+    def _device_world(self, device=None):
+        """
+        The isy_world handle of this world on `device` (default: self.device).  Every device keeps its own
+        handle for as long as the world lives, so several Renderers (one per GPU) can share one world.
+        """
+        device = int(self.device if device is None else device)
+        key = (id(self.__polygons), id(self.__colours), float(self.__horizon))
+        have = self.__handles.get(device)
+        if have is None or have[1] != key:
+            poly = np.asarray(self.__polygons)
+            if poly.dtype == np.float64 and not np.array_equal(poly.astype(np.float32).astype(np.float64), poly, equal_nan=True):
+                raise ValueError("float64 polygons that are not exactly representable in float32 are not supported: "
+                                 "the device copy of the world is float32 (the reference's own worlds are, world.py:226)")
             tri = np.ascontiguousarray(self.__polygons, dtype=np.float32).reshape(-1, 9)
             rgb = np.ascontiguousarray(self.__colours, dtype=np.float32).reshape(-1, 3)
             if tri.shape[0] != rgb.shape[0]:
                 raise ValueError("polygons and colours disagree on the number of triangles")
             h = ctypes.c_void_p()
             _lib.check(_lib.lib().isy_world_create(_lib.ptr(tri), _lib.ptr(rgb), tri.shape[0], float(self.__horizon),
-                                                   int(self.device), ctypes.byref(h)))
-            self.__handle, self.__handle_key = h, key
-        return self.__handle
+                                                   device, ctypes.byref(h)))
+            if have is not None:
+                # the arrays were replaced: handles built from the old ones are retired, not destroyed -- a Renderer
+                # may still hold one -- and freed with the world
+                self.__retired = getattr(self, "_WorldBase__retired", []) + [have[0]]
+            self.__handles[device] = (h, key)
+        return self.__handles[device][0]
 
     def _release(self):
-        if self.__handle is not None:
+        handles = [h for h, _ in self.__handles.values()] + getattr(self, "_WorldBase__retired", [])
+        self.__handles = {}
+        self.__retired = []
+        for h in handles:
             try:
-                _lib.lib().isy_world_destroy(self.__handle)
+                _lib.lib().isy_world_destroy(h)
             except Exception:
                 pass
-            self.__handle = None
 
     def __del__(self):
-        self._release()
+        try:
+            self._release()
+        except Exception:
+            pass
 
     def __call__(self, pos, ori=None, init_c=None, noise=0., eta=None, rng=RNG):
         """

@@ -24,6 +24,7 @@ from .env.sky import Sky, UniformSky
 
 _OUT_RAYS = ("hit", "depth")
 _OUT_OMM = ("rgb", "Y", "dop", "aop")
+_OUT_ALL = _OUT_RAYS + _OUT_OMM + ("resp",)
 
 
 def fibonacci_lattice(n, hemisphere=False):
@@ -117,8 +118,7 @@ class Renderer(object):
         self.world = world
         self.eye = eye
         self.sky = sky
-        world.device = self.device
-        self._w = world._device_world()
+        self._w = world._device_world(self.device)   # (the world keeps one handle per device)
         self._e = eye._device_eye(self.device)
         self._workspace = None
         self._inflight = None
@@ -141,9 +141,11 @@ class Renderer(object):
         return self._workspace
 
     def render(self, pos, yaw=None, quat=None, sun=None, outputs=("rgb", "Y", "dop", "aop"), init_from_sky=False,
-               brute_force=False, f64=False, out=None, sky=None, per_view_sky=False):
+               brute_force=False, f64=False, out=None, sky=None, per_view_sky=False, sensor=None):
         """
         per_view_sky: evaluate the sky for every view even when all positions share their headings (cross-check).
+        sensor: _lib.SensorParams for the "resp" output -- (B,N,3) photoreceptor responses, or (B,N) PN inputs with
+        channels=1 (include/isy_b200.h, isy_sensor_params).
         pos (P,3) metres; yaw (P,H) radians about +Z *or* quat (P,H,4) full eye orientations;
         sun: None (take the sky's), (2,) or (P,H,2) of (theta_s, phi_s).
         Returns {name: CUDA tensor}: rgb (B,N,3), Y/dop/aop (B,N), hit/depth (B,R), B = P*H.
@@ -196,6 +198,10 @@ class Renderer(object):
                     res[name] = torch.empty((B, R), dtype=fdt, device=dev)
                 elif name in _OUT_OMM:
                     res[name] = torch.empty((B, N), dtype=fdt, device=dev)
+                elif name == "resp":
+                    if sensor is None:
+                        raise ValueError("the 'resp' output needs sensor=SensorParams")
+                    res[name] = torch.empty((B, N, 3) if sensor.channels == 3 else (B, N), dtype=fdt, device=dev)
                 else:
                     raise ValueError("unknown output %r" % name)
             setattr(o, name, res[name].data_ptr())
@@ -205,8 +211,8 @@ class Renderer(object):
                                          None if yaw is None or quat is not None else yaw.data_ptr(),
                                          None if quat is None else quat.data_ptr(),
                                          None if sun_t is None else sun_t.data_ptr(),
-                                         ctypes.byref(sp), flags, ctypes.byref(o), ws.data_ptr(), ws.numel(),
-                                         ctypes.c_void_p(stream)))
+                                         ctypes.byref(sp), None if sensor is None else ctypes.byref(sensor), flags,
+                                         ctypes.byref(o), ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream)))
         # keep the input tensors alive until the stream has consumed them
         self._inflight = (pos, yaw, quat, sun_t)
         return res
@@ -226,7 +232,7 @@ class Renderer(object):
         return out
 
     def render_host(self, pos, yaw=None, quat=None, sun=None, outputs=("rgb", "Y", "dop", "aop"),
-                    init_from_sky=False, f64=False, out=None, sky=None, per_view_sky=False):
+                    init_from_sky=False, f64=False, out=None, sky=None, per_view_sky=False, sensor=None):
         """
         End-to-end variant with HOST buffers (isy_render_host): inputs are NumPy / CPU tensors,
         results land in (pinned) host tensors; returns {name: CPU tensor}. Blocking.
@@ -265,10 +271,16 @@ class Renderer(object):
         o = _lib.Outputs()
         for name in outputs:
             if name not in res:
-                shape = (B, N, 3) if name == "rgb" else (B, R) if name in _OUT_RAYS else (B, N)
+                if name not in _OUT_ALL:
+                    raise ValueError("unknown output %r" % name)
+                if name == "resp" and sensor is None:
+                    raise ValueError("the 'resp' output needs sensor=SensorParams")
+                shape = (B, N, 3) if name == "rgb" or (name == "resp" and sensor.channels == 3) else \
+                    (B, R) if name in _OUT_RAYS else (B, N)
                 dt = torch.int32 if name == "hit" else fdt
                 res[name] = torch.empty(shape, dtype=dt, pin_memory=True)
             setattr(o, name, res[name].data_ptr())
         _lib.check(_lib.lib().isy_render_host(self._w, self._e, P, H, _lib.ptr(pos), _lib.ptr(yaw), _lib.ptr(quat),
-                                              _lib.ptr(sun_a), ctypes.byref(sp), flags, ctypes.byref(o)))
+                                              _lib.ptr(sun_a), ctypes.byref(sp),
+                                              None if sensor is None else ctypes.byref(sensor), flags, ctypes.byref(o)))
         return res

@@ -14,15 +14,24 @@ unpinned parts explicitly:
   * acceptance cone: `nb_samples` (1, 2, 4, 8, 16, 32) directions per ommatidium: the axis, then rings
     of points at 0.5 * omm_rho and omm_rho/... (see `cone_offsets`), Gaussian weights with
     sigma = omm_rho / 2, normalised per ommatidium;
-  * responses (N, 3): the cone-averaged RGB of `scene` painted over the sky background, with the
-    background brought to the same 0..1 scale (sky colour / 255), multiplied by the R, G, B entries of
-    `c_sensitive` (IRGBU order) and by `omm_res`, clipped to [0, 1].
+  * photoreceptor transform (`isy_sensor_params`, include/isy_b200.h -- evaluated ON THE DEVICE by the final
+    pass of the render kernel, so only responses leave the GPU): per cone sample the colour on the 0..1 scale
+    is the hit triangle's colour, else the ground colour where the sample looks down, else
+    `luminance2skycolour(Y) / 255` under a sky, else 0; the samples are averaged with the cone weights;
+    responses (N, 3) = clip(mean colour * c_sensitive[R, G, B] * omm_res, 0, 1).  `transform_reference` states
+    the same in NumPy (float64) for tests and documentation;
+  * `noise` > 0: a fraction of the ommatidia is blanked per call exactly as the reference's environment does for
+    its own outputs (`env/_helpers.py:10-36` add_noise -> `c[eta] = 0`, world.py:125-127), with the eye's `rng`.
 
-Everything the eye computes per ray goes through `Renderer` (one fused launch per call or per batch).
+Everything the eye computes per ray goes through `Renderer` (one fused launch per call or per batch); a
+yaw-only eye orientation -- every pose the reference's simulations set (`R.from_euler('Z', yaw)`,
+simulation.py:836, 2706) -- takes the rasteriser for yaw-only views, any other orientation the general one.
 """
 import numpy as np
 from scipy.spatial.transform import Rotation as R
 
+from . import _lib
+from .env.occlusion import RNG, add_noise
 from .render import EyeLayout, Renderer, fibonacci_lattice
 
 
@@ -46,10 +55,27 @@ def cone_offsets(nb_samples, rho):
     return d_pitch, d_yaw, w / w.sum()
 
 
+def transform_reference(sample_rgb01, weights, w_rgb, gain):
+    """
+    NumPy (float64) statement of the photoreceptor transform the device evaluates: sample_rgb01 (..., N, S, 3)
+    colours on the 0..1 scale, weights (N, S) cone weights summing to 1 per ommatidium -> responses (..., N, 3).
+    """
+    c = (np.asarray(sample_rgb01, dtype=np.float64) * np.asarray(weights, dtype=np.float64)[..., None]).sum(axis=-2)
+    return np.clip(c * np.asarray(w_rgb, dtype=np.float64) * float(gain), 0., 1.)
+
+
+def yaw_only(rot, tol=0.0):
+    """yaw (rad) if `rot` is a pure rotation about +Z (quaternion x = y = 0 exactly), else None."""
+    x, y, z, w = np.asarray(rot.as_quat(), dtype=np.float64).reshape(4)
+    if abs(x) > tol or abs(y) > tol:
+        return None
+    return 2.0 * np.arctan2(z, w) if w >= 0 else 2.0 * np.arctan2(-z, -w)
+
+
 class CompoundEye(object):
     def __init__(self, nb_input=1000, omm_ori=None, omm_rho=np.deg2rad(5.), omm_res=1., omm_pol_op=0.,
                  c_sensitive=(0., 0., 1., 0., 0.), noise=0., xyz=None, ori=None, nb_samples=1, dtype='float32',
-                 name="compound_eye", device=0):
+                 name="compound_eye", device=0, rng=RNG):
         if omm_ori is None:
             pitch, yaw = fibonacci_lattice(nb_input)
             omm_ori = R.from_euler('ZY', np.c_[yaw, pitch])
@@ -60,6 +86,7 @@ class CompoundEye(object):
         self.omm_pol_op = omm_pol_op
         self.c_sensitive = np.asarray(c_sensitive, dtype=np.float64).reshape(-1)
         self.noise = noise
+        self.rng = rng
         self.nb_samples = int(nb_samples)
         self.dtype = dtype
         self.name = name
@@ -91,6 +118,15 @@ class CompoundEye(object):
             self._renderers[key] = Renderer(scene, self._eye_layout(), sky=sky, device=self.device)
         return self._renderers[key]
 
+    @property
+    def w_rgb(self):
+        """spectral sensitivity to (R, G, B): entries 1..3 of the IRGBU vector `c_sensitive`"""
+        return self.c_sensitive[1:4] if self.c_sensitive.size >= 4 else np.ones(3)
+
+    def sensor_params(self, channels=3):
+        """the eye's photoreceptor transform as the C ABI takes it (isy_sensor_params)"""
+        return _lib.SensorParams.make(self.w_rgb, float(np.max(self.omm_res)), channels)
+
     # ---- pose (reference: eye.xyz = ..., eye.ori = R.from_euler('Z', yaw, degrees=True)) ----
     @property
     def xyz(self):
@@ -121,29 +157,32 @@ class CompoundEye(object):
         return np.rad2deg(self.yaw)
 
     # ---- sensing ----
-    def responses_from(self, rgb, with_sky):
-        """(…, N, 3) cone-averaged world colours -> responses (documented transform, see module docstring)."""
-        rgb = np.array(rgb, dtype=np.float64)
-        if with_sky:
-            sky_px = np.nan_to_num(rgb, nan=0.).max(axis=-1) > 1.     # background on the 0..255 scale
-            rgb[sky_px] /= 255.
-        w = self.c_sensitive[1:4] if self.c_sensitive.size >= 4 else np.ones(3)
-        return np.clip(np.nan_to_num(rgb, nan=0.) * w * self.omm_res, 0., 1.).astype(self.dtype)
-
     def __call__(self, sky=None, scene=None, callback=None):
         if scene is None:
             raise ValueError("CompoundEye needs a scene (a WorldBase) to look at")
         r = self._renderer(scene, sky)
-        q = self._ori.as_quat()
-        out = r.render_host(self._xyz.reshape(1, 3), quat=q.reshape(1, 1, 4), outputs=("rgb",),
-                            init_from_sky=sky is not None)
-        self.responses = self.responses_from(out["rgb"].numpy()[0], sky is not None)
+        yaw = yaw_only(self._ori)
+        if yaw is not None:     # the pose of every simulation step of the reference: rasteriser for yaw-only views
+            out = r.render_host(self._xyz.reshape(1, 3), yaw=np.array([[yaw]]), outputs=("resp",),
+                                sensor=self.sensor_params(3))
+        else:
+            out = r.render_host(self._xyz.reshape(1, 3), quat=self._ori.as_quat().reshape(1, 1, 4), outputs=("resp",),
+                                sensor=self.sensor_params(3))
+        resp = out["resp"].numpy()[0].astype(self.dtype, copy=True)
+        if self.noise:
+            resp[add_noise(noise=self.noise, shape=resp.shape, rng=self.rng)] = 0.      # world.py:125-127
+        self.responses = resp
         if callback is not None:
             callback(self)
         return self.responses
 
-    def render_batch(self, scene, sky, pos, yaw_deg):
-        """Batched equivalent of calling the eye at P positions x H yaw-only headings: (P*H, N, 3) responses."""
+    def render_batch(self, scene, sky, pos, yaw_deg, channels=3, out=None):
+        """
+        Batched equivalent of calling the eye at P positions x H yaw-only headings: (P*H, N, 3) responses, or
+        (P*H, N) PN inputs with channels=1 (agent.py:744), transformed on the device; `out` = a pinned host
+        tensor to fill (re-used by the chunked dataset writer).
+        """
         r = self._renderer(scene, sky)
-        out = r.render_host(pos, np.deg2rad(yaw_deg), outputs=("rgb",), init_from_sky=sky is not None)
-        return self.responses_from(out["rgb"].numpy(), sky is not None)
+        res = {} if out is None else {"resp": out}
+        res = r.render_host(pos, np.deg2rad(yaw_deg), outputs=("resp",), sensor=self.sensor_params(channels), out=res)
+        return res["resp"].numpy()

@@ -18,18 +18,24 @@ def ib():
     return invertsy_b200
 
 
-def _oracle_responses(eye, world, sky_args, pos, ori):
-    """reference world()/sky() on every sample direction, NumPy cone average, the eye's documented transform"""
+def _oracle_responses(eye, world, sky_args, pos, ori, uniform=None):
+    """reference world()/sky() on every sample direction (the oracle port), then the eye's documented transform stated
+    here in NumPy: sample colours on the 0..1 scale (sky background = luminance2skycolour / 255), weighted cone
+    average, clip(colour * c_sensitive[RGB] * omm_res, 0, 1)"""
     lay = eye._eye_layout()
     glob = ori * R.from_quat(lay.quat)
-    init = None
+    c = o.world_render(world.polygons, world.colours, 2.0, pos.reshape(1, 3), glob).astype(np.float64)   # NaN = nothing seen
+    bg = np.zeros_like(c)
     if sky_args is not None:
-        init, _, _ = o.sky_render(sky_args[0], sky_args[1], glob)
-    c = o.world_render(world.polygons, world.colours, 2.0, pos.reshape(1, 3), glob, init_c=init).astype(np.float64)
-    w = lay.weights.astype(np.float64).reshape(eye.nb_ommatidia, eye.nb_samples) if lay.weights is not None else None
-    c = c.reshape(eye.nb_ommatidia, eye.nb_samples, 3)
-    avg = (c * w[:, :, None]).sum(1) if w is not None else c.mean(1)
-    return eye.responses_from(avg, sky_args is not None)
+        y, _, _ = o.sky_render(sky_args[0], sky_args[1], glob)
+        bg = o.luminance2skycolour(y) / 255.
+    elif uniform is not None:
+        bg = o.luminance2skycolour(np.full(c.shape[0], uniform)) / 255.
+    c = np.where(np.isnan(c), bg, c).reshape(eye.nb_ommatidia, eye.nb_samples, 3)
+    w = lay.weights.astype(np.float64).reshape(eye.nb_ommatidia, eye.nb_samples) if lay.weights is not None \
+        else np.full((eye.nb_ommatidia, eye.nb_samples), 1. / eye.nb_samples)
+    avg = (c * w[:, :, None]).sum(1)
+    return np.clip(avg * eye.c_sensitive[1:4] * eye.omm_res, 0., 1.)
 
 
 @pytest.mark.parametrize("nb_samples,with_sky", [(1, False), (4, True), (16, True)])
@@ -49,8 +55,31 @@ def test_compound_eye_matches_reference_composition(ib, nb_samples, with_sky):
         ref = _oracle_responses(eye, world, sky_args, route[k, :3], eye.ori)
         assert np.abs(r - ref).max() < 1e-5
         assert np.allclose(np.clip(r.mean(axis=1), 0, 1), np.clip(ref.mean(axis=1), 0, 1), atol=1e-5)   # agent.py:744
+        # the same pose as a yaw-only orientation (what the reference's simulations set, simulation.py:2706): the
+        # call takes the rasteriser for yaw-only views and must agree with the reference composition too
+        eye.ori = R.from_euler('Z', route[k, 3], degrees=True)
+        r = eye(sky=sky, scene=world)
+        ref = _oracle_responses(eye, world, sky_args, route[k, :3], eye.ori)
+        assert np.abs(r - ref).max() < 1e-5
+        # ... and the one-channel PN output of the device is clip(mean over channels) of the three (agent.py:744)
+        pn = eye.render_batch(world, sky, route[k:k + 1, :3], np.array([[route[k, 3]]]), channels=1)
+        assert pn.shape == (1, 600) and np.abs(pn[0] - np.clip(ref.mean(axis=1), 0, 1)).max() < 1e-5
     assert len(seen) == 3 and seen[0] is eye
     assert abs(eye.yaw_deg - route[700, 3]) < 1e-9 and eye.x == route[700, 0]
+
+
+def test_noise_blanks_ommatidia_like_the_reference_environment(ib):
+    world = ib.Seville2009()
+    clean = ib.CompoundEye(nb_input=500, omm_res=2.)
+    noisy = ib.CompoundEye(nb_input=500, omm_res=2., noise=0.2, rng=np.random.RandomState(5))
+    for e in (clean, noisy):
+        e.xyz = [5., 5., 0.01]
+    a, b = clean(scene=world), noisy(scene=world)
+    rng = np.random.RandomState(5)
+    eta = np.argsort(np.absolute(rng.randn(500, 3)))[:int(0.2 * 500)]          # env/_helpers.py:27-29
+    want = a.copy()
+    want[eta] = 0.
+    assert np.array_equal(b, want)
 
 
 def test_dataset_writer_matches_per_view_calls_and_schema(ib, tmp_path):
@@ -83,6 +112,20 @@ def test_dataset_writer_matches_per_view_calls_and_schema(ib, tmp_path):
     blk = datasets.collect_familiarity_dataset(route, eye, world, sky, method="parallel", nb_orientations=3, nb_parallel=3,
                                                block=(2, 5))
     assert np.array_equal(blk["ommatidia"], par["ommatidia"][2 * 3:5 * 3])
+    # streamed in small chunks straight into the file, nothing kept in memory; one-channel PN variant
+    st = datasets.collect_familiarity_dataset(route, eye, world, sky, method="grid", nb_orientations=4, nb_rows=3, nb_cols=2,
+                                              filename=str(tmp_path / "streamed"), chunk_views=8, keep=False, compressed=False)
+    assert st["ommatidia"] is None
+    with np.load(str(tmp_path / "streamed.npz")) as f:
+        assert np.array_equal(f["ommatidia"], stats["ommatidia"]) and np.array_equal(f["xyz"], stats["xyz"])
+    pn = datasets.collect_familiarity_dataset(route, eye, world, sky, method="grid", nb_orientations=4, nb_rows=3, nb_cols=2,
+                                              channels=1)
+    assert pn["ommatidia"].shape == (24, 300)
+    assert np.abs(pn["ommatidia"] - np.clip(stats["ommatidia"].mean(axis=2), 0, 1)).max() < 1e-6
+    # against the reference composition under the uniform sky of the data-collection simulations
+    eye.xyz, eye.ori = pos[2], R.from_euler('Z', yaw[2, 1], degrees=True)
+    ref = _oracle_responses(eye, world, None, pos[2], eye.ori, uniform=10.)
+    assert np.abs(stats["ommatidia"][2 * 4 + 1] - ref).max() < 1e-5
 
 
 def test_familiarity_of_a_small_grid_on_the_gpu(ib):

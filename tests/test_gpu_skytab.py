@@ -161,3 +161,76 @@ def test_output_buffers_off_the_16_byte_grid(ib):
     r.check()
     for k in ALL:
         assert np.array_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), equal_nan=True), k
+
+
+@pytest.mark.parametrize("sky", ["perez", "uniform", "none"])
+@pytest.mark.parametrize("H,R", [(36, 1000), (5, 999)])
+def test_photoreceptor_rows_match_the_per_view_passes_and_the_reference_composition(ib, sky, H, R):
+    """the `resp` output (PN inputs, one channel) in rows mode -- template / table rows + patches -- against the
+    per-view final pass, the three-channel output, the fp64 generic pass, and the NumPy statement of the transform
+    on the oracle's world / sky"""
+    from invertsy_b200 import _lib
+    world = ib.Seville2009()
+    pitch, yaw = o.fibonacci_eye(R)
+    ths, phs = np.deg2rad(60.), np.pi
+    sk = {"perez": ib.Sky(ths, phs), "uniform": ib.UniformSky(10.), "none": None}[sky]
+    r = ib.Renderer(world, ib.EyeLayout.from_angles(pitch, yaw), sk)
+    P = max(150, -(-4200 // H))
+    pos = _positions(P, 36)
+    heads = (np.arange(H) * 2 * np.pi / H + 0.2 + np.pi) % (2 * np.pi) - np.pi
+    yw = np.tile(heads, (P, 1))
+    w_rgb, gain = (0.2, 1.0, 0.1), 1.5
+    s1, s3 = _lib.SensorParams.make(w_rgb, gain, 1), _lib.SensorParams.make(w_rgb, gain, 3)
+    outs = ("rgb", "hit", "resp") + (("Y",) if sk is not None else ())
+    a = r.render(pos, yw, outputs=outs, sensor=s1)                          # rows mode
+    b = r.render(pos, yw, outputs=outs, sensor=s1, per_view_sky=True)       # per-view fast pass
+    c = r.render(pos, yw, outputs=("resp",), sensor=s3)                     # three channels (per-view pass)
+    d = r.render(pos[:20], yw[:20], outputs=("resp",), sensor=s3, f64=True) # generic pass, fp64
+    torch.cuda.synchronize()
+    r.check()
+    ra, rb, rc, rd = (x["resp"].cpu().numpy() for x in (a, b, c, d))
+    assert ra.shape == (P * H, R) and rc.shape == (P * H, R, 3) and rd.dtype == np.float64
+    assert np.array_equal(a["hit"].cpu().numpy(), b["hit"].cpu().numpy())
+    assert np.abs(ra - rb).max() < 1e-6
+    assert np.abs(ra - np.clip(rc.mean(axis=2), 0, 1)).max() < 1e-6
+    assert np.abs(rc[:20 * H] - rd).max() < 1e-6
+    # reference composition on a few views
+    omm = o.eye_rotations(pitch, yaw)
+    for v in (0, (P // 2) * H + H // 3, P * H - 1):
+        ori = o.view_rotations(np.rad2deg(heads[v % H]), omm)
+        col = o.world_render(world.polygons, world.colours, 2.0, pos[v // H].reshape(1, 3), ori).astype(np.float64)
+        bg = np.zeros_like(col)
+        if sky == "perez":
+            bg = o.luminance2skycolour(o.sky_render(ths, phs, ori)[0]) / 255.
+        elif sky == "uniform":
+            bg = o.luminance2skycolour(np.full(R, 10.)) / 255.
+        col = np.where(np.isnan(col), bg, col)
+        want = np.clip(col * np.asarray(w_rgb) * gain, 0, 1)
+        assert np.abs(rc[v] - want).max() < 1e-5
+        assert np.abs(ra[v] - np.clip(want.mean(axis=1), 0, 1)).max() < 1e-5
+
+
+def test_status_of_a_workspace_is_sticky_across_launches(ib):
+    """an overflow raised by one launch survives later launches on the same workspace until it is read
+    (include/isy_b200.h, isy_workspace_status); reading clears it"""
+    rng = np.random.RandomState(7)
+    T = 135000                                           # slab: min(2 T, 1 << 17) = 131 072 copies per position
+    base = np.c_[rng.uniform(4.5, 5.5, T), rng.uniform(4.5, 5.5, T), np.zeros(T)]
+    tri = np.stack([base, base + [0.01, 0., 0.], base + [0., 0.01, 0.05]], axis=1).astype(np.float32)
+    world = ib.WorldBase(tri, np.full((T, 3), 0.5, dtype=np.float32), horizon=3.)
+    pitch, yaw = o.fibonacci_eye(64)
+    r = ib.Renderer(world, ib.EyeLayout.from_angles(pitch, yaw))
+    seam = np.array([[5.0, 5.0, 0.01]])                  # sees all 135 000 triangles: more than the slab holds
+    calm = np.array([[-40.0, 5.0, 0.01]])                # sees nothing
+    r.render(seam, np.zeros((1, 1)), outputs=("hit",))
+    r.render(calm, np.zeros((1, 1)), outputs=("hit",))   # a later, clean launch on the same workspace
+    with pytest.raises(_lib_error(ib)):
+        r.check()
+    r.check()                                            # read = cleared
+    r.render(calm, np.zeros((1, 1)), outputs=("hit",))
+    r.check()
+
+
+def _lib_error(ib):
+    from invertsy_b200 import _lib
+    return _lib.IsyError
