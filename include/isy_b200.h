@@ -185,6 +185,29 @@ int isy_sky_call_host(const isy_sky_params* sky, double theta_s, double phi_s, c
 int isy_spectrum_influence_host(const double* v_host, int64_t n, const double* irgbu_host, int64_t rows,
                                 int device, double* sum_host, double* channels_host);
 
+/* ---- familiarity of rendered views: the consumer of every view in the reference's heat-map and
+ * parallel-lines runs (agent/agent.py:741-744 -> memory -> sim/simulation.py:3085-3092) ------------------------
+ * A perfect memory stores M vectors of K values (the PN inputs of the route views, i.e. `resp` with one channel):
+ *     familiarity(q) = 1 - min_m sqrt(mean_k (q_k - m_k)^2)
+ * (the memory model is InvertPy's, not vendored by the reference: this definition is the library's own).
+ * isy_memory_create copies the vectors to the device (the caller keeps ownership of vectors_host).              */
+typedef struct isy_memory isy_memory;
+int isy_memory_create(const float* vectors_host, int64_t M, int64_t K, int device, isy_memory** out);
+int isy_memory_destroy(isy_memory* m);
+int64_t isy_memory_size(const isy_memory* m);
+
+/* Familiarity of Q query vectors on the device: queries_dev[q * row_stride + k], k < K; row_stride (in floats) and the
+ * pointer must be multiples of 4 floats / 16 bytes (TMA).  familiarity_dev[Q] and / or nearest_dev[Q] (index of the
+ * nearest stored vector) may be NULL.  A TF32 tensor-core pass (tcgen05, accumulators in TMEM) keeps four candidates
+ * per query, an fp32 pass re-checks them exactly; the Q x M distance matrix is never written.  Asynchronous.      */
+size_t isy_familiarity_workspace_bytes(const isy_memory* m, int64_t Q);
+int isy_familiarity(const isy_memory* m, const float* queries_dev, int64_t Q, int64_t row_stride,
+                    float* familiarity_dev, int32_t* nearest_dev, void* workspace_dev, size_t workspace_bytes,
+                    void* stream);
+/* the same with host buffers ([Q][K] contiguous); blocking */
+int isy_familiarity_host(const isy_memory* m, const float* queries_host, int64_t Q, float* familiarity_host,
+                         int32_t* nearest_host);
+
 #ifdef __cplusplus
 }
 #endif

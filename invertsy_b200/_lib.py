@@ -23,6 +23,8 @@ EXPORTS = (
     "isy_render_workspace_bytes", "isy_render", "isy_workspace_status", "isy_workspace_phase_cycles",
     "isy_render_host",
     "isy_world_call_host", "isy_sky_call_host", "isy_spectrum_influence_host",
+    "isy_memory_create", "isy_memory_destroy", "isy_memory_size",
+    "isy_familiarity_workspace_bytes", "isy_familiarity", "isy_familiarity_host",
 )
 
 
@@ -92,6 +94,16 @@ def lib():
     L.isy_world_call_host.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
     L.isy_sky_call_host.argtypes = [ctypes.POINTER(SkyParams), dbl, dbl, vp, i64, vp, ctypes.c_int, vp, vp, vp, vp, vp]
     L.isy_spectrum_influence_host.argtypes = [vp, i64, vp, i64, ctypes.c_int, vp, vp]
+    L.isy_memory_create.argtypes = [vp, i64, i64, ctypes.c_int, ctypes.POINTER(vp)]
+    L.isy_memory_destroy.argtypes = [vp]
+    L.isy_memory_size.argtypes = [vp]
+    L.isy_memory_size.restype = i64
+    L.isy_familiarity_workspace_bytes.argtypes = [vp, i64]
+    L.isy_familiarity_workspace_bytes.restype = ctypes.c_size_t
+    L.isy_familiarity.argtypes = [vp, vp, i64, i64, vp, vp, vp, ctypes.c_size_t, vp]
+    L.isy_familiarity_host.argtypes = [vp, vp, i64, vp, vp]
+    for name in ("isy_memory_create", "isy_memory_destroy", "isy_familiarity", "isy_familiarity_host"):
+        getattr(L, name).restype = ctypes.c_int
     for name in ("isy_world_create", "isy_world_destroy", "isy_eye_create", "isy_eye_destroy", "isy_render",
                  "isy_workspace_status", "isy_render_host", "isy_world_call_host", "isy_sky_call_host",
                  "isy_spectrum_influence_host"):

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "isy_kernels.cuh"
+#include "isy_fam.cuh"
 
 using namespace isy;
 
@@ -909,6 +910,184 @@ int isy_spectrum_influence_host(const double* v_host, int64_t n, const double* i
     CUDA_TRY(cudaGetLastError());
     if (sum_host) CUDA_TRY(cudaMemcpy(sum_host, d_o.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     if (channels_host) CUDA_TRY(cudaMemcpy(channels_host, d_c.p, (size_t)n * 40, cudaMemcpyDeviceToHost));
+    return ISY_OK;
+}
+
+}  // extern "C"
+
+
+// ================================================================================================
+// familiarity (isy_fam.cuh)
+// ================================================================================================
+struct isy_memory {
+    int device;
+    int64_t M, K;
+    int64_t ldm;        // row stride of the device copies in floats (K rounded up to 4: TMA strides are multiples of 16 B)
+    int64_t Mpad;       // rows of the device copies (M rounded up to the 256-row TMA box, zero rows)
+    float* d_stored;    // [Mpad][ldm] the vectors as given (exact re-check)
+    float* d_centred;   // [Mpad][ldm] vectors minus their mean (operand of the TF32 filter)
+    float* d_cn;        // [Mpad] |m|^2
+    CUtensorMap map_b;  // d_centred, box 32 x 256, 128-byte swizzle
+};
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// [rows][K] floats with row stride ld (floats), box = 32 floats x box_rows, 128-byte swizzle, zero fill
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(ISY_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)fam::kBK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ISY_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return ISY_OK;
+}
+
+int memory_fill(isy_memory* m, const float* v) {
+    const int64_t M = m->M, K = m->K, ld = m->ldm, Mp = m->Mpad;
+    std::vector<double> mean((size_t)K, 0.0);
+    for (int64_t i = 0; i < M; ++i)
+        for (int64_t k = 0; k < K; ++k) mean[k] += v[i * K + k];
+    for (int64_t k = 0; k < K; ++k) mean[k] /= (double)M;
+    std::vector<float> stored((size_t)Mp * ld, 0.f), centred((size_t)Mp * ld, 0.f), cn((size_t)Mp, 0.f);
+    for (int64_t i = 0; i < M; ++i) {
+        double s = 0.0;
+        for (int64_t k = 0; k < K; ++k) {
+            const double x = v[i * K + k];
+            stored[(size_t)i * ld + k] = (float)x;
+            centred[(size_t)i * ld + k] = (float)(x - mean[k]);
+            s += x * x;
+        }
+        cn[i] = (float)s;
+    }
+    CUDA_TRY(cudaMalloc(&m->d_stored, stored.size() * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&m->d_centred, centred.size() * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&m->d_cn, cn.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(m->d_stored, stored.data(), stored.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(m->d_centred, centred.data(), centred.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(m->d_cn, cn.data(), cn.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return make_map(&m->map_b, m->d_centred, Mp, K, ld, fam::kNB);
+}
+
+}  // namespace
+
+extern "C" {
+
+int isy_memory_create(const float* vectors_host, int64_t M, int64_t K, int device, isy_memory** out) {
+    if (!vectors_host || !out || M <= 0 || K <= 0 || M >= (1ll << 30) || K >= (1ll << 24))
+        return fail(ISY_ERR_INVALID, "isy_memory_create: bad argument");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(ISY_ERR_CUDA, "isy_memory_create: cannot select CUDA device %d (no CPU fallback)", device);
+    isy_memory* m = new isy_memory;
+    memset(m, 0, sizeof *m);
+    m->device = device, m->M = M, m->K = K, m->ldm = (K + 3) / 4 * 4, m->Mpad = (M + fam::kNB - 1) / fam::kNB * fam::kNB;
+    const int rc = memory_fill(m, vectors_host);
+    if (rc != ISY_OK) {
+        const std::string msg = g_err;
+        isy_memory_destroy(m);
+        g_err = msg;
+        return rc;
+    }
+    *out = m;
+    return ISY_OK;
+}
+
+int isy_memory_destroy(isy_memory* m) {
+    if (!m) return ISY_OK;
+    DeviceGuard g(m->device);
+    cudaFree(m->d_stored);
+    cudaFree(m->d_centred);
+    cudaFree(m->d_cn);
+    delete m;
+    return ISY_OK;
+}
+
+int64_t isy_memory_size(const isy_memory* m) { return m ? m->M : -1; }
+
+size_t isy_familiarity_workspace_bytes(const isy_memory* m, int64_t Q) {
+    if (!m || Q < 0) return 0;
+    return align_up((size_t)std::max<int64_t>(Q, 1) * sizeof(int4));
+}
+
+int isy_familiarity(const isy_memory* m, const float* queries_dev, int64_t Q, int64_t row_stride, float* familiarity_dev,
+                    int32_t* nearest_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!m || !queries_dev || Q < 0 || (!familiarity_dev && !nearest_dev))
+        return fail(ISY_ERR_INVALID, "isy_familiarity: bad argument");
+    if (Q == 0) return ISY_OK;
+    if (Q >= (1ll << 31) - fam::kBM) return fail(ISY_ERR_INVALID, "isy_familiarity: too many queries for one call");
+    if (row_stride < m->K || (row_stride & 3) || ((uintptr_t)queries_dev & 15))
+        return fail(ISY_ERR_INVALID, "isy_familiarity: queries must be 16-byte aligned with a row stride that is a multiple of 4 floats and at least K");
+    if (!workspace_dev || workspace_bytes < isy_familiarity_workspace_bytes(m, Q))
+        return fail(ISY_ERR_WORKSPACE, "isy_familiarity: workspace %zu B < required %zu B", workspace_bytes,
+                    isy_familiarity_workspace_bytes(m, Q));
+    DeviceGuard g(m->device);
+    if (!g.ok) return fail(ISY_ERR_CUDA, "isy_familiarity: cannot select CUDA device %d (no CPU fallback)", m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUtensorMap map_a;
+    int rc = make_map(&map_a, queries_dev, Q, m->K, row_stride, fam::kBM);
+    if (rc != ISY_OK) return rc;
+    int4* cand = reinterpret_cast<int4*>(workspace_dev);
+    const int ntiles = (int)((Q + fam::kBM - 1) / fam::kBM);
+    const int grid = std::min(ntiles, device_sms(m->device));
+    CUDA_TRY(cudaFuncSetAttribute(fam::fam_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fam::kSmemBytes));
+    fam::fam_filter_kernel<<<grid, fam::kThreads, fam::kSmemBytes, st>>>(map_a, m->map_b, m->d_cn, (int)Q, (int)m->M, (int)m->K, cand);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    const int wpb = 8;
+    fam::fam_recheck_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, st>>>(queries_dev, (long long)row_stride, m->d_stored, (long long)m->ldm,
+                                                                                   (int)Q, (int)m->K, cand, familiarity_dev,
+                                                                                   nearest_dev);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ISY_OK;
+}
+
+int isy_familiarity_host(const isy_memory* m, const float* queries_host, int64_t Q, float* familiarity_host,
+                         int32_t* nearest_host) {
+    if (!m || !queries_host || Q < 0 || (!familiarity_host && !nearest_host))
+        return fail(ISY_ERR_INVALID, "isy_familiarity_host: bad argument");
+    if (Q == 0) return ISY_OK;
+    DeviceGuard g(m->device);
+    if (!g.ok) return fail(ISY_ERR_CUDA, "isy_familiarity_host: cannot select CUDA device %d (no CPU fallback)", m->device);
+    const int64_t ld = m->ldm;
+    DevBuf<float> d_q, d_f;
+    DevBuf<int32_t> d_n;
+    DevBuf<unsigned char> d_ws;
+    const size_t ws = isy_familiarity_workspace_bytes(m, Q);
+    CUDA_TRY(d_q.alloc((size_t)Q * ld));
+    CUDA_TRY(d_f.alloc((size_t)Q));
+    CUDA_TRY(d_n.alloc((size_t)Q));
+    CUDA_TRY(d_ws.alloc(ws));
+    if (ld != m->K) CUDA_TRY(cudaMemset(d_q.p, 0, (size_t)Q * ld * sizeof(float)));
+    CUDA_TRY(cudaMemcpy2D(d_q.p, (size_t)ld * sizeof(float), queries_host, (size_t)m->K * sizeof(float), (size_t)m->K * sizeof(float),
+                          (size_t)Q, cudaMemcpyHostToDevice));
+    const int rc = isy_familiarity(m, d_q.p, Q, ld, d_f.p, d_n.p, d_ws.p, ws, nullptr);
+    if (rc != ISY_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(nullptr));
+    if (familiarity_host) CUDA_TRY(cudaMemcpy(familiarity_host, d_f.p, (size_t)Q * sizeof(float), cudaMemcpyDeviceToHost));
+    if (nearest_host) CUDA_TRY(cudaMemcpy(nearest_host, d_n.p, (size_t)Q * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return ISY_OK;
 }
 

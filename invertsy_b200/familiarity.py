@@ -1,11 +1,13 @@
 """
-Familiarity evaluation of rendered views: views -> PN responses -> PCA whitening ->
+Familiarity evaluation of rendered views: views -> PN responses -> (PCA whitening) ->
 perfect-memory familiarity -> the reference's `familiarity_par[m, k, ori]` / heat-map layout.
 
 What is pinned to the reference and what is not:
 
 * `pn_responses` is the reference's own code: `r = np.clip(omm_responses.mean(axis=1), 0, 1)`
-  (agent/agent.py:742-744, `get_pn_responses`; the same line in `get_omm_responses`, :788).
+  (agent/agent.py:742-744, `get_pn_responses`; the same line in `get_omm_responses`, :788).  The render kernel
+  writes exactly this when asked for one-channel responses (`resp`, include/isy_b200.h), so batches never make
+  the three-channel detour.
 * `familiarity_indices` is the reference's index arithmetic (sim/simulation.py:3085-3090).
 * The whitening and the memory are InvertPy classes (`invertpy.brain.preprocessing.Whitening` with
   `w_method=pca`, `invertpy.brain.memory.PerfectMemory`), which the reference imports (agent/agent.py:30-40,
@@ -13,15 +15,20 @@ What is pinned to the reference and what is not:
     - PCA whitening fitted on S calibration samples x (S, N): m = mean(x, 0); C = (x - m)^T (x - m) / S;
       C = E diag(d) E^T with d descending; W = E[:, :K] / sqrt(d[:K] + eps); y = (x - m) W.
     - Perfect memory over the M stored route vectors: familiarity(q) = 1 - min_k RMSE(q, m_k),
-      RMSE(q, m) = sqrt(mean_i (q_i - m_i)^2).
+      RMSE(q, m) = sqrt(mean_i (q_i - m_i)^2).  `reference_familiarity` states it in NumPy float64 (tests).
 
-Everything is torch on whatever device the tensors live on.  The M x Q distance matrix is a plain GEMM
-(|q - m|^2 = |q|^2 + |m|^2 - 2 q.m, cuBLAS through torch.matmul), evaluated in blocks of queries so that it
-never has to exist as a whole, and used only to pick the nearest stored vector; on several GPUs every rank evaluates the views it rendered and only the
+The memory runs in the CUDA library (`isy_memory_create` / `isy_familiarity`, csrc/isy_fam.cuh): a hand-written
+TF32 tcgen05 kernel (TMA-staged operands, accumulators in TMEM, running top-4 per query in the epilogue) filters
+the M stored vectors down to four candidates per query, an fp32 kernel re-checks those exactly.  The Q x M
+distance matrix never exists in HBM.  On several GPUs every rank evaluates the views it rendered and only the
 familiarity rows travel (`distributed.gather_views`, NCCL over NVLink) -- the one collective of the design.
 """
+import ctypes
+
 import numpy as np
 import torch
+
+from . import _lib
 
 
 def pn_responses(omm_responses):
@@ -38,6 +45,18 @@ def familiarity_indices(nb_views, route_length, nb_orientations):
     """
     j = np.arange(nb_views)
     return (j // nb_orientations) % route_length, j // (route_length * nb_orientations), j % nb_orientations
+
+
+def reference_familiarity(queries, stored):
+    """NumPy float64 statement of the perfect memory: (familiarity (Q,), nearest index (Q,)); blocks of queries."""
+    q = np.asarray(queries, dtype=np.float64)
+    m = np.asarray(stored, dtype=np.float64)
+    fam, idx = np.empty(q.shape[0]), np.empty(q.shape[0], dtype=np.int64)
+    for a in range(0, q.shape[0], 256):
+        d2 = ((q[a:a + 256, None, :] - m[None, :, :]) ** 2).mean(axis=2)
+        idx[a:a + 256] = d2.argmin(axis=1)
+        fam[a:a + 256] = 1.0 - np.sqrt(d2.min(axis=1))
+    return fam, idx
 
 
 class Whitening:
@@ -69,36 +88,83 @@ class Whitening:
 
 
 class PerfectMemory:
-    """Stores every training vector; familiarity(q) = 1 - min over the stored vectors of RMSE(q, m)."""
+    """
+    Stores every training vector; familiarity(q) = 1 - min over the stored vectors of RMSE(q, m).
+    The stored vectors live in an `isy_memory` handle on `device`; queries that are CUDA tensors are evaluated in
+    place (no copy when they are contiguous float32 with a row length that is a multiple of 4), anything else goes
+    through the host-buffer entry point.  No CPU fallback.
+    """
 
-    def __init__(self, block=65536):
-        self.block = block
-        self.database = None
+    def __init__(self, device=0):
+        self.device = int(device)
+        self.database = None          # (M, K) float32 NumPy copy of what is stored
+        self._h = None
+        self._ws = None
 
     def store(self, vectors):
-        v = torch.as_tensor(vectors)
-        v = v.reshape(-1, v.shape[-1])
-        self.database = v if self.database is None else torch.cat([self.database, v.to(self.database.device)], dim=0)
+        v = torch.as_tensor(vectors).detach().to("cpu", torch.float32).numpy()
+        v = np.ascontiguousarray(v.reshape(-1, v.shape[-1]))
+        self.database = v if self.database is None else np.concatenate([self.database, v], axis=0)
+        self._release()
         return self
 
-    def familiarity(self, queries):
+    def _handle(self):
         assert self.database is not None and self.database.shape[0] > 0, "nothing stored"
-        q = torch.as_tensor(queries)
-        q = q.reshape(-1, q.shape[-1])
-        db = self.database.to(device=q.device, dtype=q.dtype)
-        m2 = (db * db).sum(dim=1)
-        out = torch.empty(q.shape[0], dtype=q.dtype, device=q.device)
-        for a in range(0, q.shape[0], self.block):
-            qb = q[a:a + self.block]
-            d2 = (qb * qb).sum(dim=1, keepdim=True) + m2[None, :] - 2.0 * (qb @ db.T)    # (block, M) GEMM
-            # the GEMM form only picks the nearest stored vector; its distance is then formed from the difference
-            # itself (no cancellation: a stored view is exactly familiar with itself)
-            diff = qb - db[d2.argmin(dim=1)]
-            out[a:a + self.block] = 1.0 - torch.sqrt((diff * diff).sum(dim=1) / q.shape[1])
-        return out
+        if self._h is None:
+            h = ctypes.c_void_p()
+            _lib.check(_lib.lib().isy_memory_create(_lib.ptr(self.database), self.database.shape[0],
+                                                    self.database.shape[1], self.device, ctypes.byref(h)))
+            self._h = h
+        return self._h
+
+    def _release(self):
+        if self._h is not None:
+            try:
+                _lib.lib().isy_memory_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+    def __del__(self):
+        self._release()
+
+    def familiarity(self, queries, nearest=False, out=None):
+        """queries (Q, K) -> familiarity (Q,) float32 [, nearest stored index (Q,) int32]; CUDA in, CUDA out."""
+        h = self._handle()
+        L = _lib.lib()
+        K = self.database.shape[1]
+        if torch.is_tensor(queries) and queries.is_cuda:
+            q = queries.reshape(-1, queries.shape[-1])
+            if q.shape[1] != K:
+                raise ValueError("queries have %d values, the stored vectors %d" % (q.shape[1], K))
+            if q.dtype != torch.float32 or q.stride(1) != 1 or q.stride(0) % 4 or q.data_ptr() % 16 or \
+                    q.device.index != self.device:
+                ld = (K + 3) // 4 * 4
+                buf = torch.zeros((q.shape[0], ld), dtype=torch.float32, device="cuda:%d" % self.device)
+                buf[:, :K] = q
+                q = buf[:, :K]
+            Q = q.shape[0]
+            dev = q.device
+            fam = out if out is not None else torch.empty(Q, dtype=torch.float32, device=dev)
+            idx = torch.empty(Q, dtype=torch.int32, device=dev) if nearest else None
+            need = int(L.isy_familiarity_workspace_bytes(h, Q))
+            if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(L.isy_familiarity(h, q.data_ptr(), Q, q.stride(0), fam.data_ptr(),
+                                         None if idx is None else idx.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                         ctypes.c_void_p(stream)))
+            self._inflight = q
+            return (fam, idx) if nearest else fam
+        q = np.ascontiguousarray(torch.as_tensor(queries).detach().cpu().numpy(), dtype=np.float32).reshape(-1, K)
+        fam = np.empty(q.shape[0], dtype=np.float32)
+        idx = np.empty(q.shape[0], dtype=np.int32)
+        _lib.check(L.isy_familiarity_host(h, _lib.ptr(q), q.shape[0], _lib.ptr(fam), _lib.ptr(idx)))
+        fam, idx = torch.from_numpy(fam), torch.from_numpy(idx)
+        return (fam, idx) if nearest else fam
 
 
-def evaluate(views, route_views, whitening=None, memory=None):
+def evaluate(views, route_views, whitening=None, memory=None, device=0):
     """
     views (V, N[, C]) and route_views (L, N[, C]): ommatidia responses (or PN vectors when 2-D) of the second phase and
     of the training route, e.g. `stats["ommatidia"]` / `stats["ommatidia_out"]` of `datasets.collect_familiarity_dataset`.
@@ -108,7 +174,7 @@ def evaluate(views, route_views, whitening=None, memory=None):
     pr = pn_responses(route_views) if torch.as_tensor(route_views).ndim == 3 else torch.as_tensor(route_views)
     if whitening is not None:
         pv, pr = whitening(pv), whitening(pr)
-    memory = PerfectMemory() if memory is None else memory
+    memory = PerfectMemory(device=pv.device.index if pv.is_cuda else device) if memory is None else memory
     memory.store(pr)
     return memory.familiarity(pv)
 
@@ -127,11 +193,12 @@ def familiarity_map(fam, nb_rows, nb_cols, nb_orientations):
     return torch.as_tensor(fam).detach().cpu().numpy().reshape(nb_rows, nb_cols, nb_orientations)
 
 
-def evaluate_sharded(local_views, route_views, nb_positions, views_per_position, whitening=None, dst=None, group=None):
+def evaluate_sharded(local_views, route_views, nb_positions, views_per_position, whitening=None, dst=None, group=None,
+                     memory=None):
     """
     Multi-GPU: every rank passes the views of ITS block of positions (`distributed.shard`) and the whole training
     route; the familiarities are gathered in position order (all ranks, or rank `dst` only).
     """
     from . import distributed
-    fam = evaluate(local_views, route_views, whitening=whitening)
+    fam = evaluate(local_views, route_views, whitening=whitening, memory=memory)
     return distributed.gather_views({"familiarity": fam}, nb_positions, views_per_position, dst=dst, group=group)["familiarity"]

@@ -24,6 +24,17 @@ def _data(V=60, L=25, N=40, C=5, seed=0):
     return views, route
 
 
+class _NumpyMemory:
+    """stands in for the CUDA perfect memory in the CPU tests of the host logic (the definition, in NumPy float64)"""
+
+    def store(self, v):
+        self.db = torch.as_tensor(v).double().numpy()
+        return self
+
+    def familiarity(self, q):
+        return torch.from_numpy(fam.reference_familiarity(torch.as_tensor(q).double().numpy(), self.db)[0])
+
+
 def test_pn_responses_is_the_reference_expression():
     views, _ = _data()
     ref = np.clip(views.mean(axis=2), 0, 1)        # agent.py:742-744 applied to every view
@@ -41,15 +52,22 @@ def test_whitening_and_perfect_memory_match_their_definitions():
     yv, yr = (pv - m) @ w, (pr - m) @ w
     ref = 1 - np.sqrt(((yv[:, None, :] - yr[None, :, :]) ** 2).mean(2)).min(1)
     wh = fam.Whitening(nb_output=10, dtype=torch.float64).fit(pr)
-    got = fam.evaluate(views.astype(np.float64), route.astype(np.float64), whitening=wh).numpy()
+    got = fam.evaluate(views.astype(np.float64), route.astype(np.float64), whitening=wh, memory=_NumpyMemory()).numpy()
     # eigenvectors are defined up to a sign: distances are not affected
     assert np.allclose(got, ref, atol=1e-6)
     assert np.allclose(got[:25:3], 1.0, atol=1e-5)              # views on the route are fully familiar
     white = wh(pr).numpy()
     assert np.allclose(white.T @ white / pr.shape[0], np.eye(10), atol=1e-3)   # whitened: unit covariance
-    # blocks of queries give what one block gives
-    mem = fam.PerfectMemory(block=7).store(torch.as_tensor(yr))
-    assert np.allclose(mem.familiarity(torch.as_tensor(yv)).numpy(), ref, atol=1e-9)
+    f2, idx = fam.reference_familiarity(yv, yr)
+    assert np.allclose(f2, ref, atol=1e-12) and np.array_equal(idx[:25:3], np.arange(0, 25, 3))
+
+
+def test_the_cuda_memory_has_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    mem = fam.PerfectMemory().store(np.zeros((3, 8), dtype=np.float32))
+    with pytest.raises(Exception):
+        mem.familiarity(np.zeros((2, 8), dtype=np.float32))
 
 
 def test_familiarity_par_uses_the_reference_indexing():
@@ -79,9 +97,9 @@ def _worker(rank, world, port, q):
         from invertsy_b200.views import shard_positions
         P, H = 7, 4
         views, route = _data(V=P * H, L=9)
-        full = fam.evaluate(views, route)
+        full = fam.evaluate(views, route, memory=_NumpyMemory())
         a, b = shard_positions(P, rank, world)
-        got = fam.evaluate_sharded(views[a * H:b * H], route, P, H)
+        got = fam.evaluate_sharded(views[a * H:b * H], route, P, H, memory=_NumpyMemory())
         q.put((rank, bool(torch.allclose(got, full))))
     finally:
         dist.destroy_process_group()

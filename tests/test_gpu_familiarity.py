@@ -1,0 +1,98 @@
+"""
+GPU: the perfect-memory familiarity kernels (csrc/isy_fam.cuh: TF32 tcgen05 filter + exact fp32 re-check) through the
+C ABI, against the NumPy float64 statement of the definition (`familiarity.reference_familiarity`):
+familiarity(q) = 1 - min_m sqrt(mean_k (q_k - m_k)^2).  Tolerance: 2e-6 absolute on the familiarity (fp32 sums of up to
+a few thousand squared differences + one sqrt); the nearest index must be the true one wherever the runner-up is further
+than 1e-6 in mean squared difference.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-6
+
+
+@pytest.fixture(scope="module")
+def fam():
+    from invertsy_b200 import familiarity
+    assert torch.cuda.is_available()
+    return familiarity
+
+
+def _check(fam, q, m, via="cuda"):
+    ref, ref_i = fam.reference_familiarity(q, m)
+    mem = fam.PerfectMemory().store(m)
+    if via == "cuda":
+        f, i = mem.familiarity(torch.as_tensor(q, dtype=torch.float32).cuda(), nearest=True)
+        torch.cuda.synchronize()
+    else:
+        f, i = mem.familiarity(q, nearest=True)
+    f, i = f.cpu().numpy(), i.cpu().numpy()
+    assert np.abs(f - ref).max() < TOL, np.abs(f - ref).max()
+    bad = np.nonzero(i != ref_i)[0]
+    if bad.size:   # only genuine near-ties may differ
+        d = ((q[bad].astype(np.float64) - m[i[bad]].astype(np.float64)) ** 2).mean(1)
+        d0 = ((q[bad].astype(np.float64) - m[ref_i[bad]].astype(np.float64)) ** 2).mean(1)
+        assert np.abs(d - d0).max() < 1e-6
+    return f, i
+
+
+@pytest.mark.parametrize("Q,M,K", [(1000, 812, 1000), (128, 256, 32), (1, 1, 4), (129, 257, 36), (300, 3, 1000),
+                                    (5000, 1500, 600), (77, 812, 1001)])
+def test_random_vectors_match_the_definition(fam, Q, M, K):
+    rng = np.random.RandomState(Q + M + K)
+    m = rng.uniform(0, 1, (M, K)).astype(np.float32)
+    q = rng.uniform(0, 1, (Q, K)).astype(np.float32)
+    n = min(Q, M)
+    q[:n:5] = m[:n:5]                                   # some queries are stored vectors: familiarity exactly 1
+    f, i = _check(fam, q, m)
+    assert np.all(f[:n:5] == 1.0) and np.array_equal(i[:n:5], np.arange(0, n, 5))
+
+
+def test_route_like_memory_with_near_ties(fam):
+    """stored vectors that differ little from their neighbours (consecutive route views) and queries between them"""
+    rng = np.random.RandomState(3)
+    M, K, Q = 812, 1000, 4096
+    base = rng.uniform(0, 1, K)
+    walk = np.cumsum(rng.normal(0, 0.01, (M, K)), axis=0)
+    m = np.clip(base + walk, 0, 1).astype(np.float32)
+    j = rng.randint(0, M - 1, Q)
+    t = rng.uniform(0, 1, (Q, 1))
+    q = np.clip((1 - t) * m[j] + t * m[j + 1] + rng.normal(0, 0.02, (Q, K)), 0, 1).astype(np.float32)
+    _check(fam, q, m)
+
+
+def test_host_buffers_and_strided_device_queries(fam):
+    rng = np.random.RandomState(4)
+    m = rng.uniform(0, 1, (100, 250)).astype(np.float32)
+    q = rng.uniform(0, 1, (333, 250)).astype(np.float32)
+    a, _ = _check(fam, q, m, via="host")
+    mem = fam.PerfectMemory().store(m)
+    wide = torch.zeros((333, 256), dtype=torch.float32, device="cuda")     # row stride 256 floats, 250 used
+    wide[:, :250] = torch.as_tensor(q)
+    b = mem.familiarity(wide[:, :250]).cpu().numpy()
+    c = mem.familiarity(torch.as_tensor(q, dtype=torch.float64).cuda()).cpu().numpy()   # converted copy
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_rendered_views_end_to_end(fam):
+    """N2 -> N3 on the device: PN inputs written by the render kernel (one-channel `resp`) straight into the memory"""
+    import invertsy_b200 as ib
+    world = ib.Seville2009()
+    eye = ib.CompoundEye(nb_input=1000, omm_res=5., c_sensitive=[0, 0., 1., 0., 0.])
+    route = ib.Seville2009.load_routes(degrees=True)["path"][0][::4]
+    r = ib.Renderer(world, eye._eye_layout(), sky=ib.UniformSky(10.))
+    s1 = eye.sensor_params(1)
+    stored = r.render(route[:, :3], np.deg2rad(route[:, 3:4]), outputs=("resp",), sensor=s1)["resp"]
+    pos, yaw = ib.views.grid_views(6, 6, 8)
+    views = r.render(pos, np.deg2rad(yaw), outputs=("resp",), sensor=s1)["resp"]
+    mem = fam.PerfectMemory().store(stored)
+    f, i = mem.familiarity(views, nearest=True)
+    torch.cuda.synchronize()
+    ref, ref_i = fam.reference_familiarity(views.cpu().numpy(), stored.cpu().numpy())
+    assert np.abs(f.cpu().numpy() - ref).max() < TOL
+    assert (i.cpu().numpy() != ref_i).mean() < 0.01
+    assert np.allclose(mem.familiarity(stored).cpu().numpy(), 1.0, atol=1e-6)
+    assert fam.familiarity_map(f, 6, 6, 8).shape == (6, 6, 8)
