@@ -204,6 +204,10 @@ size_t isy_familiarity_workspace_bytes(const isy_memory* m, int64_t Q);
 int isy_familiarity(const isy_memory* m, const float* queries_dev, int64_t Q, int64_t row_stride,
                     float* familiarity_dev, int32_t* nearest_dev, void* workspace_dev, size_t workspace_bytes,
                     void* stream);
+/* Synchronises `stream` and returns in *count how many queries of the LAST isy_familiarity call on this workspace had
+ * all four candidates inside the filter's error margin (the exact re-check then cannot rule out a fifth; csrc/isy_fam.cuh).
+ * 0 on every workload measured so far; exposed so that a caller can see it.                                     */
+int isy_familiarity_unresolved(const isy_memory* m, int64_t Q, void* workspace_dev, void* stream, int64_t* count);
 /* the same with host buffers ([Q][K] contiguous); blocking */
 int isy_familiarity_host(const isy_memory* m, const float* queries_host, int64_t Q, float* familiarity_host,
                          int32_t* nearest_host);

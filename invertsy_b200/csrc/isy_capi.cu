@@ -927,6 +927,7 @@ struct isy_memory {
     float* d_stored;    // [Mpad][ldm] the vectors as given (exact re-check)
     float* d_centred;   // [Mpad][ldm] vectors minus their mean (operand of the TF32 filter)
     float* d_cn;        // [Mpad] |m|^2
+    float mc_max;       // max over the stored vectors of |m - mean|_2 (error bound of the TF32 filter)
     CUtensorMap map_b;  // d_centred, box 32 x 256, 128-byte swizzle
 };
 
@@ -981,6 +982,9 @@ int memory_fill(isy_memory* m, const float* v) {
             s += x * x;
         }
         cn[i] = (float)s;
+        double sc = 0.0;
+        for (int64_t k = 0; k < K; ++k) sc += (double)centred[(size_t)i * ld + k] * centred[(size_t)i * ld + k];
+        m->mc_max = std::max(m->mc_max, (float)(std::sqrt(sc) * (1.0 + 1e-6)));
     }
     CUDA_TRY(cudaMalloc(&m->d_stored, stored.size() * sizeof(float)));
     CUDA_TRY(cudaMalloc(&m->d_centred, centred.size() * sizeof(float)));
@@ -1028,7 +1032,8 @@ int64_t isy_memory_size(const isy_memory* m) { return m ? m->M : -1; }
 
 size_t isy_familiarity_workspace_bytes(const isy_memory* m, int64_t Q) {
     if (!m || Q < 0) return 0;
-    return align_up((size_t)std::max<int64_t>(Q, 1) * sizeof(int4));
+    // candidates (int4) and their filter scores (float4) per query, then the counter of unresolved queries
+    return align_up((size_t)std::max<int64_t>(Q, 1) * (sizeof(int4) + sizeof(float4))) + 256;
 }
 
 int isy_familiarity(const isy_memory* m, const float* queries_dev, int64_t Q, int64_t row_stride, float* familiarity_dev,
@@ -1049,18 +1054,32 @@ int isy_familiarity(const isy_memory* m, const float* queries_dev, int64_t Q, in
     int rc = make_map(&map_a, queries_dev, Q, m->K, row_stride, fam::kBM);
     if (rc != ISY_OK) return rc;
     int4* cand = reinterpret_cast<int4*>(workspace_dev);
+    float4* score = reinterpret_cast<float4*>(cand + Q);
+    unsigned int* unresolved = reinterpret_cast<unsigned int*>((unsigned char*)workspace_dev + align_up((size_t)Q * (sizeof(int4) + sizeof(float4))));
+    CUDA_TRY(cudaMemsetAsync(unresolved, 0, sizeof(unsigned int), st));
     const int ntiles = (int)((Q + fam::kBM - 1) / fam::kBM);
     const int grid = std::min(ntiles, device_sms(m->device));
     CUDA_TRY(cudaFuncSetAttribute(fam::fam_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fam::kSmemBytes));
-    fam::fam_filter_kernel<<<grid, fam::kThreads, fam::kSmemBytes, st>>>(map_a, m->map_b, m->d_cn, (int)Q, (int)m->M, (int)m->K, cand);
+    fam::fam_filter_kernel<<<grid, fam::kThreads, fam::kSmemBytes, st>>>(map_a, m->map_b, m->d_cn, (int)Q, (int)m->M, (int)m->K, cand, score);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     const int wpb = 8;
     fam::fam_recheck_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, st>>>(queries_dev, (long long)row_stride, m->d_stored, (long long)m->ldm,
-                                                                                   (int)Q, (int)m->K, cand, familiarity_dev,
-                                                                                   nearest_dev);
+                                                                                   (int)Q, (int)m->K, cand, score, m->mc_max,
+                                                                                   familiarity_dev, nearest_dev, unresolved);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
+    return ISY_OK;
+}
+
+int isy_familiarity_unresolved(const isy_memory* m, int64_t Q, void* workspace_dev, void* stream, int64_t* count) {
+    if (!m || !workspace_dev || !count || Q < 0) return fail(ISY_ERR_INVALID, "isy_familiarity_unresolved: bad argument");
+    DeviceGuard g(m->device);
+    unsigned int n = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n, (unsigned char*)workspace_dev + align_up((size_t)std::max<int64_t>(Q, 1) * (sizeof(int4) + sizeof(float4))),
+                             sizeof n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    *count = n;
     return ISY_OK;
 }
 

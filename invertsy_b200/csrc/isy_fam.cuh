@@ -137,11 +137,12 @@ struct Top4 {
 // ---------------------------------------------------------------------------------------------------
 // tmA: queries  [Q][K] floats, box 32 x 128;  tmB: centred stored vectors [M][K] floats, box 32 x 256; both with
 // the 128-byte swizzle and zero fill outside the tensors (ragged Q, M, K cost nothing and contribute zeros).
-// cn[m] = |m|^2 of the UNcentred stored vectors.  cand[q] = indices of the four smallest scores (-1 = none).
+// cn[m] = |m|^2 of the UNcentred stored vectors.  cand[q] / score[q] = the four smallest scores, ascending, and their
+// stored vectors (-1 = none).
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1)
 fam_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const float* __restrict__ cn, int Q, int M, int K, int4* __restrict__ cand) {
+                  const float* __restrict__ cn, int Q, int M, int K, int4* __restrict__ cand, float4* __restrict__ score) {
     extern __shared__ uint8_t fam_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fam_smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sA = smem_u32(smem);                                   // [kStages][128 x 32] floats
@@ -233,7 +234,10 @@ fam_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 mbar_arrive(acc_empty(ab));
             }
             const int q = tile * kBM + (warp & 3) * 32 + lane;
-            if (q < Q) cand[q] = make_int4(top.i[0], top.i[1], top.i[2], top.i[3]);
+            if (q < Q) {
+                cand[q] = make_int4(top.i[0], top.i[1], top.i[2], top.i[3]);
+                score[q] = make_float4(top.v[0], top.v[1], top.v[2], top.v[3]);
+            }
         }
     }
     tc_fence_before();
@@ -247,25 +251,36 @@ fam_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ---------------------------------------------------------------------------------------------------
 // exact re-check: one warp per query; fp32 sum of squared differences with each candidate (lanes stride the
 // vector 16 bytes at a time), the smallest wins (ties: lower index).  familiarity = 1 - sqrt(d2 / K).
+//
+// Which candidates need it: the filter's score of a stored vector is off by at most
+//     2 * (2^-10 |q|_2 |m - mean|_2  +  K 2^-24 sum_k |q_k (m - mean)_k|)  <=  2.2 * 2^-10 |q|_2 mc_max     (K < 2^12)
+// (TF32 operands rounded to nearest: 2^-11 relative each; Cauchy-Schwarz; fp32 accumulation), so a candidate whose
+// score exceeds the best by more than twice that cannot be the nearest and is not loaded.  |q|_2 is formed here from
+// the query the warp reads anyway; mc_max = max_m |m - mean|_2 comes from isy_memory_create.  If even the fourth
+// candidate is inside the margin a fifth might be too: such queries are counted in *unresolved (none on the heat-map
+// grid; the count is part of the result so that a caller can see it).
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 fam_recheck_kernel(const float* __restrict__ queries, long long ldq, const float* __restrict__ stored, long long lds, int Q, int K,
-                   const int4* __restrict__ cand, float* __restrict__ fam_out, int* __restrict__ nearest_out) {
+                   const int4* __restrict__ cand, const float4* __restrict__ score, float mc_max, float* __restrict__ fam_out,
+                   int* __restrict__ nearest_out, unsigned int* __restrict__ unresolved) {
     const int lane = threadIdx.x & 31;
     const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= Q) return;
     const int4 c4 = cand[q];
+    const float4 v4 = score[q];
     const int c[kTopK] = {c4.x, c4.y, c4.z, c4.w};
+    const float v[kTopK] = {v4.x, v4.y, v4.z, v4.w};
     const float* x = queries + q * ldq;
     const bool vec = (K & 3) == 0 && (ldq & 3) == 0 && (lds & 3) == 0 && ((uintptr_t)queries & 15) == 0 && ((uintptr_t)stored & 15) == 0;
-    float best = __int_as_float(0x7f800000);
+    float best = __int_as_float(0x7f800000), xx = 0.f, margin = __int_as_float(0x7f800000);
     int best_i = -1;
 #pragma unroll
     for (int t = 0; t < kTopK; ++t) {
         const int m = c[t];
-        if (m < 0) continue;                                   // (warp-uniform: the candidates are the query's)
+        if (m < 0 || v[t] > v[0] + margin) continue;           // (warp-uniform: the candidates are the query's)
         const float* y = stored + (size_t)m * lds;
-        float s0 = 0.f, s1 = 0.f;
+        float s0 = 0.f, s1 = 0.f, n0 = 0.f;
         if (vec) {
             const float4* x4 = reinterpret_cast<const float4*>(x);
             const float4* y4 = reinterpret_cast<const float4*>(y);
@@ -273,21 +288,30 @@ fam_recheck_kernel(const float* __restrict__ queries, long long ldq, const float
                 const float4 a = __ldg(x4 + k), b = __ldg(y4 + k);
                 const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
                 s0 = fmaf(d0, d0, s0), s1 = fmaf(d1, d1, s1), s0 = fmaf(d2, d2, s0), s1 = fmaf(d3, d3, s1);
+                if (t == 0) n0 = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, n0))));
             }
         } else {
             for (int k = lane; k < K; k += 32) {
-                const float d = __ldg(x + k) - __ldg(y + k);
+                const float a = __ldg(x + k), d = a - __ldg(y + k);
                 s0 = fmaf(d, d, s0);
+                if (t == 0) n0 = fmaf(a, a, n0);
             }
         }
         float s = s0 + s1;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (t == 0) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) n0 += __shfl_xor_sync(0xffffffffu, n0, o);
+            xx = n0;
+            margin = 2.0f * 2.2f * 9.765625e-4f * sqrtf(xx) * mc_max;
+        }
         if (s < best || (s == best && m < best_i)) best = s, best_i = m;
     }
     if (lane == 0) {
         if (fam_out) fam_out[q] = 1.0f - sqrtf(best / (float)K);
         if (nearest_out) nearest_out[q] = best_i;
+        if (unresolved && c[kTopK - 1] >= 0 && v[kTopK - 1] <= v[0] + margin) atomicAdd(unresolved, 1u);
     }
 }
 

@@ -128,6 +128,15 @@ class PerfectMemory:
     def __del__(self):
         self._release()
 
+    def unresolved(self):
+        """queries of the last device call whose four candidates all lay inside the filter's error margin (csrc/isy_fam.cuh)"""
+        q, Q = self._inflight
+        n = ctypes.c_int64(0)
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        _lib.check(_lib.lib().isy_familiarity_unresolved(self._handle(), Q, self._ws.data_ptr(), ctypes.c_void_p(stream),
+                                                         ctypes.byref(n)))
+        return int(n.value)
+
     def familiarity(self, queries, nearest=False, out=None):
         """queries (Q, K) -> familiarity (Q,) float32 [, nearest stored index (Q,) int32]; CUDA in, CUDA out."""
         h = self._handle()
@@ -154,7 +163,7 @@ class PerfectMemory:
             _lib.check(L.isy_familiarity(h, q.data_ptr(), Q, q.stride(0), fam.data_ptr(),
                                          None if idx is None else idx.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
                                          ctypes.c_void_p(stream)))
-            self._inflight = q
+            self._inflight = (q, Q)
             return (fam, idx) if nearest else fam
         q = np.ascontiguousarray(torch.as_tensor(queries).detach().cpu().numpy(), dtype=np.float32).reshape(-1, K)
         fam = np.empty(q.shape[0], dtype=np.float32)

@@ -27,6 +27,7 @@ def _check(fam, q, m, via="cuda"):
     if via == "cuda":
         f, i = mem.familiarity(torch.as_tensor(q, dtype=torch.float32).cuda(), nearest=True)
         torch.cuda.synchronize()
+        assert 0 <= mem.unresolved() <= q.shape[0]        # (diagnostic count: four candidates inside the error margin)
     else:
         f, i = mem.familiarity(q, nearest=True)
     f, i = f.cpu().numpy(), i.cpu().numpy()
