@@ -208,6 +208,11 @@ int isy_familiarity(const isy_memory* m, const float* queries_dev, int64_t Q, in
  * all four candidates inside the filter's error margin (the exact re-check then cannot rule out a fifth; csrc/isy_fam.cuh).
  * 0 on every workload measured so far; exposed so that a caller can see it.                                     */
 int isy_familiarity_unresolved(const isy_memory* m, int64_t Q, void* workspace_dev, void* stream, int64_t* count);
+/* Diagnostics: the four candidates of every query of the LAST isy_familiarity call on this workspace and their filter
+ * scores v = |m|^2 - 2 q.(m - mean) as the tensor cores produced them (cand_host[Q][4], score_host[Q][4], ascending;
+ * either may be NULL).  Synchronises `stream`.  Tests use it to check the filter's error model.                    */
+int isy_familiarity_candidates(const isy_memory* m, int64_t Q, void* workspace_dev, void* stream, int32_t* cand_host,
+                               float* score_host);
 /* the same with host buffers ([Q][K] contiguous); blocking */
 int isy_familiarity_host(const isy_memory* m, const float* queries_host, int64_t Q, float* familiarity_host,
                          int32_t* nearest_host);

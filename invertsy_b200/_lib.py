@@ -24,7 +24,8 @@ EXPORTS = (
     "isy_render_host",
     "isy_world_call_host", "isy_sky_call_host", "isy_spectrum_influence_host",
     "isy_memory_create", "isy_memory_destroy", "isy_memory_size",
-    "isy_familiarity_workspace_bytes", "isy_familiarity", "isy_familiarity_unresolved", "isy_familiarity_host",
+    "isy_familiarity_workspace_bytes", "isy_familiarity", "isy_familiarity_unresolved", "isy_familiarity_candidates",
+    "isy_familiarity_host",
 )
 
 
@@ -103,6 +104,8 @@ def lib():
     L.isy_familiarity.argtypes = [vp, vp, i64, i64, vp, vp, vp, ctypes.c_size_t, vp]
     L.isy_familiarity_host.argtypes = [vp, vp, i64, vp, vp]
     L.isy_familiarity_unresolved.argtypes = [vp, i64, vp, vp, ctypes.POINTER(i64)]
+    L.isy_familiarity_candidates.argtypes = [vp, i64, vp, vp, vp, vp]
+    L.isy_familiarity_candidates.restype = ctypes.c_int
     for name in ("isy_memory_create", "isy_memory_destroy", "isy_familiarity", "isy_familiarity_host",
                  "isy_familiarity_unresolved"):
         getattr(L, name).restype = ctypes.c_int

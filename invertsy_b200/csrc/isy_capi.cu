@@ -923,10 +923,12 @@ struct isy_memory {
     int device;
     int64_t M, K;
     int64_t ldm;        // row stride of the device copies in floats (K rounded up to 4: TMA strides are multiples of 16 B)
-    int64_t Mpad;       // rows of the device copies (M rounded up to the 256-row TMA box, zero rows)
+    int64_t U;          // unique stored vectors (bit-identical copies are kept once)
+    int64_t Mpad;       // rows of the device copies (U rounded up to the 256-row TMA box, zero rows)
     float* d_stored;    // [Mpad][ldm] the vectors as given (exact re-check)
     float* d_centred;   // [Mpad][ldm] vectors minus their mean (operand of the TF32 filter)
     float* d_cn;        // [Mpad] |m|^2
+    int32_t* d_orig;    // [Mpad] index (as given to isy_memory_create) of each unique vector: the lowest of its copies
     float mc_max;       // max over the stored vectors of |m - mean|_2 (error bound of the TF32 filter)
     CUtensorMap map_b;  // d_centred, box 32 x 256, 128-byte swizzle
 };
@@ -967,31 +969,53 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64
 }
 
 int memory_fill(isy_memory* m, const float* v) {
-    const int64_t M = m->M, K = m->K, ld = m->ldm, Mp = m->Mpad;
+    const int64_t M = m->M, K = m->K, ld = m->ldm;
+    // Bit-identical stored vectors (an eye that saturates sees the same thing from neighbouring route steps) are kept
+    // once: the filter multiplies the unique ones only, and exact ties between copies cannot crowd the four candidate
+    // slots.  orig[u] = lowest index among the copies of unique vector u, which is what an arg-min over all M returns.
+    std::vector<int32_t> orig;
+    {
+        std::vector<int64_t> order((size_t)M);
+        for (int64_t i = 0; i < M; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+            return memcmp(v + a * K, v + b * K, (size_t)K * sizeof(float)) < 0;
+        });
+        std::vector<char> dup((size_t)M, 0);
+        for (int64_t j = 1; j < M; ++j)      // stable sort: the first of a run of equals has the lowest index
+            if (memcmp(v + order[j - 1] * K, v + order[j] * K, (size_t)K * sizeof(float)) == 0) dup[order[j]] = 1;
+        for (int64_t i = 0; i < M; ++i)
+            if (!dup[i]) orig.push_back((int32_t)i);
+    }
+    const int64_t U = (int64_t)orig.size();
+    m->U = U;
+    m->Mpad = (U + fam::kNB - 1) / fam::kNB * fam::kNB;
+    const int64_t Mp = m->Mpad;
     std::vector<double> mean((size_t)K, 0.0);
-    for (int64_t i = 0; i < M; ++i)
-        for (int64_t k = 0; k < K; ++k) mean[k] += v[i * K + k];
-    for (int64_t k = 0; k < K; ++k) mean[k] /= (double)M;
+    for (int64_t u = 0; u < U; ++u)
+        for (int64_t k = 0; k < K; ++k) mean[k] += v[(int64_t)orig[u] * K + k];
+    for (int64_t k = 0; k < K; ++k) mean[k] /= (double)U;
     std::vector<float> stored((size_t)Mp * ld, 0.f), centred((size_t)Mp * ld, 0.f), cn((size_t)Mp, 0.f);
-    for (int64_t i = 0; i < M; ++i) {
-        double s = 0.0;
+    for (int64_t u = 0; u < U; ++u) {
+        double s = 0.0, sc = 0.0;
         for (int64_t k = 0; k < K; ++k) {
-            const double x = v[i * K + k];
-            stored[(size_t)i * ld + k] = (float)x;
-            centred[(size_t)i * ld + k] = (float)(x - mean[k]);
+            const double x = v[(int64_t)orig[u] * K + k];
+            stored[(size_t)u * ld + k] = (float)x;
+            centred[(size_t)u * ld + k] = (float)(x - mean[k]);
             s += x * x;
+            sc += (double)centred[(size_t)u * ld + k] * centred[(size_t)u * ld + k];
         }
-        cn[i] = (float)s;
-        double sc = 0.0;
-        for (int64_t k = 0; k < K; ++k) sc += (double)centred[(size_t)i * ld + k] * centred[(size_t)i * ld + k];
+        cn[u] = (float)s;
         m->mc_max = std::max(m->mc_max, (float)(std::sqrt(sc) * (1.0 + 1e-6)));
     }
+    orig.resize((size_t)Mp, -1);
     CUDA_TRY(cudaMalloc(&m->d_stored, stored.size() * sizeof(float)));
     CUDA_TRY(cudaMalloc(&m->d_centred, centred.size() * sizeof(float)));
     CUDA_TRY(cudaMalloc(&m->d_cn, cn.size() * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&m->d_orig, orig.size() * sizeof(int32_t)));
     CUDA_TRY(cudaMemcpy(m->d_stored, stored.data(), stored.size() * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(m->d_centred, centred.data(), centred.size() * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(m->d_cn, cn.data(), cn.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(m->d_orig, orig.data(), orig.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     return make_map(&m->map_b, m->d_centred, Mp, K, ld, fam::kNB);
 }
 
@@ -1006,7 +1030,7 @@ int isy_memory_create(const float* vectors_host, int64_t M, int64_t K, int devic
     if (!g.ok) return fail(ISY_ERR_CUDA, "isy_memory_create: cannot select CUDA device %d (no CPU fallback)", device);
     isy_memory* m = new isy_memory;
     memset(m, 0, sizeof *m);
-    m->device = device, m->M = M, m->K = K, m->ldm = (K + 3) / 4 * 4, m->Mpad = (M + fam::kNB - 1) / fam::kNB * fam::kNB;
+    m->device = device, m->M = M, m->K = K, m->ldm = (K + 3) / 4 * 4;
     const int rc = memory_fill(m, vectors_host);
     if (rc != ISY_OK) {
         const std::string msg = g_err;
@@ -1024,6 +1048,7 @@ int isy_memory_destroy(isy_memory* m) {
     cudaFree(m->d_stored);
     cudaFree(m->d_centred);
     cudaFree(m->d_cn);
+    cudaFree(m->d_orig);
     delete m;
     return ISY_OK;
 }
@@ -1060,13 +1085,13 @@ int isy_familiarity(const isy_memory* m, const float* queries_dev, int64_t Q, in
     const int ntiles = (int)((Q + fam::kBM - 1) / fam::kBM);
     const int grid = std::min(ntiles, device_sms(m->device));
     CUDA_TRY(cudaFuncSetAttribute(fam::fam_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fam::kSmemBytes));
-    fam::fam_filter_kernel<<<grid, fam::kThreads, fam::kSmemBytes, st>>>(map_a, m->map_b, m->d_cn, (int)Q, (int)m->M, (int)m->K, cand, score);
+    fam::fam_filter_kernel<<<grid, fam::kThreads, fam::kSmemBytes, st>>>(map_a, m->map_b, m->d_cn, (int)Q, (int)m->U, (int)m->K, cand, score);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     const int wpb = 8;
     fam::fam_recheck_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, st>>>(queries_dev, (long long)row_stride, m->d_stored, (long long)m->ldm,
                                                                                    (int)Q, (int)m->K, cand, score, m->mc_max,
-                                                                                   familiarity_dev, nearest_dev, unresolved);
+                                                                                   familiarity_dev, nearest_dev, m->d_orig, unresolved);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return ISY_OK;
@@ -1080,6 +1105,18 @@ int isy_familiarity_unresolved(const isy_memory* m, int64_t Q, void* workspace_d
                              sizeof n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     *count = n;
+    return ISY_OK;
+}
+
+int isy_familiarity_candidates(const isy_memory* m, int64_t Q, void* workspace_dev, void* stream, int32_t* cand_host,
+                               float* score_host) {
+    if (!m || !workspace_dev || Q < 0 || (!cand_host && !score_host))
+        return fail(ISY_ERR_INVALID, "isy_familiarity_candidates: bad argument");
+    DeviceGuard g(m->device);
+    const int4* cand = reinterpret_cast<const int4*>(workspace_dev);
+    if (cand_host) CUDA_TRY(cudaMemcpyAsync(cand_host, cand, (size_t)Q * sizeof(int4), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    if (score_host) CUDA_TRY(cudaMemcpyAsync(score_host, cand + Q, (size_t)Q * sizeof(float4), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     return ISY_OK;
 }
 

@@ -263,7 +263,7 @@ fam_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 __global__ void __launch_bounds__(256)
 fam_recheck_kernel(const float* __restrict__ queries, long long ldq, const float* __restrict__ stored, long long lds, int Q, int K,
                    const int4* __restrict__ cand, const float4* __restrict__ score, float mc_max, float* __restrict__ fam_out,
-                   int* __restrict__ nearest_out, unsigned int* __restrict__ unresolved) {
+                   int* __restrict__ nearest_out, const int* __restrict__ orig, unsigned int* __restrict__ unresolved) {
     const int lane = threadIdx.x & 31;
     const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= Q) return;
@@ -310,7 +310,7 @@ fam_recheck_kernel(const float* __restrict__ queries, long long ldq, const float
     }
     if (lane == 0) {
         if (fam_out) fam_out[q] = 1.0f - sqrtf(best / (float)K);
-        if (nearest_out) nearest_out[q] = best_i;
+        if (nearest_out) nearest_out[q] = best_i >= 0 ? __ldg(orig + best_i) : -1;   // index as the caller stored it
         if (unresolved && c[kTopK - 1] >= 0 && v[kTopK - 1] <= v[0] + margin) atomicAdd(unresolved, 1u);
     }
 }

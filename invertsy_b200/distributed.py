@@ -17,6 +17,34 @@ import torch.distributed as dist
 from .views import shard_positions
 
 
+def bind_to_gpu_numa(device_index):
+    """
+    Pins this process to the CPUs of the NUMA node its GPU hangs off (sysfs: the PCI device's `numa_node` and the node's
+    `cpulist`), so that pinned host buffers allocated afterwards are first-touched on that node and the D2H copies of
+    a rank do not cross the socket interconnect.  Returns the node, or None when the topology is not exposed.
+    """
+    import os
+    try:
+        import torch.cuda
+        bus = torch.cuda.get_device_properties(device_index)
+        pci = "%04x:%02x:%02x.0" % (bus.pci_domain_id, bus.pci_bus_id, bus.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % pci) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def rank_and_world(group=None):
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)

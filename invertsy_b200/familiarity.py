@@ -137,6 +137,21 @@ class PerfectMemory:
                                                          ctypes.byref(n)))
         return int(n.value)
 
+    def unique_rows(self):
+        """indices of the stored vectors the device keeps (bit-identical copies are stored once, lowest index first)"""
+        _, first = np.unique(self.database, axis=0, return_index=True)
+        return np.sort(first)
+
+    def candidates(self):
+        """diagnostics: (candidates (Q, 4) int32 -- indices into the UNIQUE stored vectors, `unique_rows()` --, filter
+        scores (Q, 4) float32) of the last device call"""
+        q, Q = self._inflight
+        cand, score = np.empty((Q, 4), dtype=np.int32), np.empty((Q, 4), dtype=np.float32)
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        _lib.check(_lib.lib().isy_familiarity_candidates(self._handle(), Q, self._ws.data_ptr(), ctypes.c_void_p(stream),
+                                                         _lib.ptr(cand), _lib.ptr(score)))
+        return cand, score
+
     def familiarity(self, queries, nearest=False, out=None):
         """queries (Q, K) -> familiarity (Q,) float32 [, nearest stored index (Q,) int32]; CUDA in, CUDA out."""
         h = self._handle()

@@ -97,3 +97,18 @@ def test_rendered_views_end_to_end(fam):
     assert (i.cpu().numpy() != ref_i).mean() < 0.01
     assert np.allclose(mem.familiarity(stored).cpu().numpy(), 1.0, atol=1e-6)
     assert fam.familiarity_map(f, 6, 6, 8).shape == (6, 6, 8)
+
+
+def test_duplicate_stored_vectors_are_kept_once_and_ties_go_to_the_lowest_index(fam):
+    rng = np.random.RandomState(9)
+    base = rng.uniform(0, 1, (40, 64)).astype(np.float32)
+    m = base[rng.randint(0, 40, 500)]                       # 500 stored vectors, at most 40 different ones
+    q = np.clip(base[rng.randint(0, 40, 300)] + rng.normal(0, 0.01, (300, 64)), 0, 1).astype(np.float32)
+    f, i = _check(fam, q, m)
+    ref, ref_i = fam.reference_familiarity(q, m)
+    assert np.array_equal(i, ref_i)                          # np.argmin: the first of the copies
+    mem = fam.PerfectMemory().store(m)
+    assert mem.unique_rows().size == np.unique(m, axis=0).shape[0] <= 40
+    mem.familiarity(torch.as_tensor(q).cuda())
+    torch.cuda.synchronize()
+    assert mem.unresolved() == 0
