@@ -33,8 +33,12 @@ __device__ __forceinline__ int smem_atomic_add(int* p, int v) {
 constexpr int kRU = ISY_RU;           // rays per lane and iteration in the rasteriser
 
 // is copy e (distance d, triangle tri) nearer than copy c? (ties: lower triangle index, then lower slot)
+// The upper word of the fp64 distance decides almost always (positive doubles order like their bit patterns): one
+// shared-memory word and an integer compare; equal upper words take the full comparison.
 __device__ __forceinline__ bool nearer(const Entry* tile, double d, int tri, unsigned int e, unsigned int c) {
     const Entry& o = tile[c];
+    const int dh = __double2hiint(d);
+    if (dh != o.dist_hi) return dh < o.dist_hi;
     const double dc = __hiloint2double(o.dist_hi, o.dist_lo);
     return d < dc || (d == dc && (tri < o.tri || (tri == o.tri && e < c)));
 }

@@ -218,6 +218,11 @@ __device__ __forceinline__ float4 zero_of<float4>() { return make_float4(0.f, 0.
 // Sky rows are never touched again: streaming stores.  The hit / depth / rgb rows will be patched by final_pass_patch a
 // few tens of microseconds later: normal stores, and written as late in the rasterisation as there is time for, so
 // that the patches meet them in L2 (kTemplates picks the part: the render kernel calls it twice).
+#ifndef ISY_RESP_EARLY
+#define ISY_RESP_EARLY 1
+#endif
+constexpr bool kRespEarly = ISY_RESP_EARLY;   // the per-heading response rows go out with the sky rows (1) or with the templates (0)
+
 template <typename T, bool kSky, bool kTemplates>
 __device__ void copy_rows(const RenderParams& rp, int p, int grp, int Hcur, int w0, int nw) {
     constexpr int kPer = sizeof(T) / sizeof(float);
@@ -251,7 +256,8 @@ __device__ void copy_rows(const RenderParams& rp, int p, int grp, int Hcur, int 
     }
     // A': the per-heading rows of the photoreceptor responses (plane 3 of the table).  They are patched like the
     // template rows, so they go out with them, late, as normal stores.
-    if (kTemplates && rp.sky_rows_h > 1 && rp.out.resp) {
+    if (kRespEarly ? kSky : kTemplates)
+    if (rp.sky_rows_h > 1 && rp.out.resp) {
         const size_t plane = (size_t)rp.sky_rows_h * (size_t)nR;
         T* const dk = reinterpret_cast<T*>(rp.out.resp);
         for (int hh = warp; hh < Hcur; hh += nw) {
