@@ -616,6 +616,14 @@ int isy_workspace_phase_cycles(void* workspace_dev, void* stream, uint64_t* out4
 
 namespace {
 
+struct CallCtx;
+int call_ctx(int device, size_t dev_need, size_t pin_need, CallCtx** out);
+std::mutex& call_mutex(int device);
+int render_host_small(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, const double* pos_host,
+                      const double* yaw_host, const double* view_quat_host, const double* sun_host,
+                      const isy_sky_params* sky, const isy_sensor_params* sensor, uint32_t flags,
+                      const isy_outputs* out_host, const size_t* per_view, int n_out);
+
 // Persistent staging of the host-buffer path: two compute/copy slots (device arenas that only
 // grow), two streams and their events, one per device.  Calls on one device are serialised.
 struct HostCtx {
@@ -677,6 +685,9 @@ int isy_render_host(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, 
                                    out_host->resp ? (size_t)N * sensor->channels * esz : 0};
     size_t bytes_per_pos = 0;
     for (size_t b : per_view) bytes_per_pos += (size_t)H * b;
+    // a few views (the closed-loop step of a simulation: one view per call): one packed transfer each way
+    if ((size_t)P * bytes_per_pos <= (2u << 20) && P * H <= 256)
+        return render_host_small(w, e, P, H, pos_host, yaw_host, view_quat_host, sun_host, sky, sensor, flags, out_host, per_view, kOut);
     int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(P, (int64_t)((96ull << 20) / std::max<size_t>(bytes_per_pos, 1))));
     if (chunk < P) chunk = std::max<int64_t>(chunk, std::min<int64_t>(P, 2 * device_sms(w->device)));
     const int nslots = chunk < P ? 2 : 1;
@@ -759,6 +770,7 @@ struct CallCtx {
     size_t pin_bytes = 0;
 };
 CallCtx g_call_ctx[16];
+std::mutex& call_mutex(int device) { return g_call_ctx[std::min(std::max(device, 0), 15)].mu; }
 
 cudaError_t grow_pinned(void** p, size_t* have, size_t need) {
     if (*have >= need) return cudaSuccess;
@@ -767,6 +779,56 @@ cudaError_t grow_pinned(void** p, size_t* have, size_t need) {
     cudaError_t e = cudaMallocHost(p, need);
     if (e == cudaSuccess) *have = need;
     return e;
+}
+
+// Few views with host buffers: inputs packed into the pinned mirror -> one H2D; the kernels; outputs and the head of the
+// workspace (its status word) in one contiguous device block -> one D2H; one synchronisation.  No allocation after
+// warm-up.  This is what `eye(sky=, scene=)` costs per step of a closed-loop simulation (simulation.py:836-838).
+int render_host_small(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, const double* pos_host,
+                      const double* yaw_host, const double* view_quat_host, const double* sun_host,
+                      const isy_sky_params* sky, const isy_sensor_params* sensor, uint32_t flags,
+                      const isy_outputs* out_host, const size_t* per_view, int n_out) {
+    std::lock_guard<std::mutex> lk(call_mutex(w->device));
+    const size_t B = (size_t)P * H;
+    const bool sun_pv = flags & ISY_FLAG_SUN_PER_VIEW;
+    const size_t n_pos = (size_t)P * 3, n_yaw = yaw_host ? B : 0, n_vq = view_quat_host ? B * 4 : 0;
+    const size_t n_sun = sun_host ? (sun_pv ? B * 2 : 2) : 0;
+    const size_t in_bytes = (n_pos + n_yaw + n_vq + n_sun) * sizeof(double);
+    size_t off[8], out_bytes = 0;
+    for (int k = 0; k < n_out; ++k) off[k] = out_bytes, out_bytes += align_up(B * per_view[k], 16);
+    const size_t ws_bytes = align_up(isy_render_workspace_bytes(w, e, P, H));
+    const size_t off_out = align_up(in_bytes), off_ws = off_out + align_up(out_bytes);
+    CallCtx* cx = nullptr;
+    int rc = call_ctx(w->device, off_ws + ws_bytes, std::max(in_bytes, align_up(out_bytes) + 512), &cx);
+    if (rc != ISY_OK) return rc;
+    unsigned char* dev = (unsigned char*)cx->dev;
+    double* pin = (double*)cx->pin;
+    memcpy(pin, pos_host, n_pos * 8);
+    if (n_yaw) memcpy(pin + n_pos, yaw_host, n_yaw * 8);
+    if (n_vq) memcpy(pin + n_pos + n_yaw, view_quat_host, n_vq * 8);
+    if (n_sun) memcpy(pin + n_pos + n_yaw + n_vq, sun_host, n_sun * 8);
+    CUDA_TRY(cudaMemcpyAsync(dev, pin, in_bytes, cudaMemcpyHostToDevice, cx->st));
+    double* d_in = (double*)dev;
+    unsigned char* d_out = dev + off_out;
+    isy_outputs o;
+    void** op[7] = {&o.rgb, (void**)&o.hit, &o.depth, &o.Y, &o.dop, &o.aop, &o.resp};
+    void* const hp[7] = {out_host->rgb, out_host->hit, out_host->depth, out_host->Y, out_host->dop, out_host->aop, out_host->resp};
+    for (int k = 0; k < n_out; ++k) *op[k] = per_view[k] ? d_out + off[k] : nullptr;
+    // the status word of this private workspace starts clean in every call (it is read below, with the outputs)
+    CUDA_TRY(cudaMemsetAsync(dev + off_ws + 256, 0, sizeof(int), cx->st));
+    rc = launch_render(w, e, P, H, d_in, n_yaw ? d_in + n_pos : nullptr, n_vq ? d_in + n_pos + n_yaw : nullptr,
+                       n_sun ? d_in + n_pos + n_yaw + n_vq : nullptr, nullptr, sky, sensor, flags, &o, dev + off_ws, ws_bytes, cx->st);
+    if (rc != ISY_OK) return rc;
+    // outputs and the first 512 bytes of the workspace are contiguous on the device
+    CUDA_TRY(cudaMemcpyAsync(pin, d_out, align_up(out_bytes) + 512, cudaMemcpyDeviceToHost, cx->st));
+    CUDA_TRY(cudaStreamSynchronize(cx->st));
+    const int status = *(const int*)((const unsigned char*)pin + align_up(out_bytes) + 256);
+    if (status == ISY_ERR_OVERFLOW)
+        return fail(ISY_ERR_OVERFLOW, "isy_render: a position sees more triangle copies than the workspace slab holds");
+    if (status) return fail(status, "isy_render: device-side error %d", status);
+    for (int k = 0; k < n_out; ++k)
+        if (per_view[k]) memcpy(hp[k], (const unsigned char*)pin + off[k], B * per_view[k]);
+    return ISY_OK;
 }
 
 int call_ctx(int device, size_t dev_need, size_t pin_need, CallCtx** out) {

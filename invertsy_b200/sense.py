@@ -96,6 +96,8 @@ class CompoundEye(object):
         self.responses = np.zeros((self.nb_ommatidia, 3), dtype=dtype)
         self._layout = None
         self._renderers = {}
+        self._host_out = {}          # the call's host result buffer, re-used from step to step
+        self._sensor3 = None
 
     # ---- geometry ----
     @property
@@ -162,12 +164,14 @@ class CompoundEye(object):
             raise ValueError("CompoundEye needs a scene (a WorldBase) to look at")
         r = self._renderer(scene, sky)
         yaw = yaw_only(self._ori)
+        if self._sensor3 is None:
+            self._sensor3 = self.sensor_params(3)
         if yaw is not None:     # the pose of every simulation step of the reference: rasteriser for yaw-only views
             out = r.render_host(self._xyz.reshape(1, 3), yaw=np.array([[yaw]]), outputs=("resp",),
-                                sensor=self.sensor_params(3))
+                                sensor=self._sensor3, out=self._host_out)
         else:
             out = r.render_host(self._xyz.reshape(1, 3), quat=self._ori.as_quat().reshape(1, 1, 4), outputs=("resp",),
-                                sensor=self.sensor_params(3))
+                                sensor=self._sensor3, out=self._host_out)
         resp = out["resp"].numpy()[0].astype(self.dtype, copy=True)
         if self.noise:
             resp[add_noise(noise=self.noise, shape=resp.shape, rng=self.rng)] = 0.      # world.py:125-127

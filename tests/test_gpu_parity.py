@@ -335,3 +335,37 @@ def test_dense_synthetic_world_overflows_the_tile_and_stays_exact(ib):
     ref = _oracle_views(tri, pos, yaw_rad, pitch, yaw)
     assert (out["hit"] != ref).sum() == 0
     assert (ref[:2] >= 0).mean() > 0.2 and np.all(ref[4:] == -1)
+
+
+@pytest.mark.parametrize("world", ["seville", "sparse"])
+def test_queries_composed_by_scipy_like_the_reference(ib, world, request):
+    """
+    ~600 k rays per world whose query angles come from SciPy exactly as the reference forms them --
+    `yaw, pitch, _ = (eye.ori * omm_ori).as_euler('ZYX')` with `eye.ori = R.from_euler('Z', yaw_deg, degrees=True)`
+    (world.py:84, examples/test_sky.py:25, simulation.py:2706) -- instead of the `yaw + heading` shortcut of the
+    other large cases: the batched yaw-only path and the explicit-quaternion path must both give the oracle's
+    winners on those queries.
+    """
+    from scipy.spatial.transform import Rotation as R
+    w = request.getfixturevalue(world)
+    rng = np.random.RandomState(12)
+    P, H, N = 20, 30, 1000
+    pitch, yaw = o.fibonacci_eye(N)
+    omm = o.eye_rotations(pitch, yaw)
+    pos = np.c_[rng.uniform(0.5, 9.5, P), rng.uniform(0.5, 9.5, P), np.full(P, 0.01)]
+    yaw_deg = rng.uniform(-180, 180, (P, H))
+    yaw_deg[0, :4] = (180., -180., 0., 179.99999)
+    ref = np.empty((P * H, N), dtype=np.int32)
+    quats = np.empty((P, H, 4))
+    for p in range(P):
+        for h in range(H):
+            view = R.from_euler('Z', yaw_deg[p, h], degrees=True)
+            quats[p, h] = view.as_quat()
+            gy, gp, _ = (view * omm).as_euler('ZYX').T                      # the reference's query angles
+            ref[p * H + h] = c_oracle.world_hits(w.polygons, 2.0, pos[p], gp, gy)[0]
+    r = ib.Renderer(w, ib.EyeLayout.from_rotation(omm))
+    a = _render_np(r, pos=pos, yaw=np.deg2rad(yaw_deg), outputs=("hit",))["hit"]       # yaw-only rasteriser
+    b = _render_np(r, pos=pos, quat=quats, outputs=("hit",))["hit"]                    # general orientations (bins)
+    assert ref.size >= 500000
+    assert int((a != ref).sum()) == 0, "%d of %d rays differ (yaw-only path)" % (int((a != ref).sum()), ref.size)
+    assert int((b != ref).sum()) == 0, "%d of %d rays differ (quaternion path)" % (int((b != ref).sum()), ref.size)

@@ -43,4 +43,16 @@ t0 = time.perf_counter()
 for k in range(n):
     h = r.render_host(route[k:k + 1, :3], np.deg2rad(route[k:k + 1, 3:4]), outputs=("rgb", "Y", "dop", "aop"))
 res["render_host_single_view"] = {"ms": (time.perf_counter() - t0) / n * 1e3}
+# the drop-in eye of a closed-loop simulation step (simulation.py:836-838): eye.xyz / eye.ori set, eye(sky=, scene=) called
+ce = ib.CompoundEye(nb_input=1000, omm_res=5., c_sensitive=[0, 0., 1., 0., 0.])
+for label, make in (("eye_call_yaw_only", lambda k: R.from_euler('Z', route[k, 3], degrees=True)),
+                    ("eye_call_general_orientation", lambda k: R.from_euler('ZYX', [route[k, 3], 4., -2.], degrees=True))):
+    for k in range(5):
+        ce.xyz, ce.ori = route[k, :3], make(k)
+        ce(sky=sky, scene=world)
+    t0 = time.perf_counter()
+    for k in range(n):
+        ce.xyz, ce.ori = route[k, :3], make(k)
+        resp = ce(sky=sky, scene=world)
+    res[label] = {"ms": (time.perf_counter() - t0) / n * 1e3, "what": "CompoundEye.__call__ -> isy_render_host(resp), host to host"}
 print(json.dumps(res))
