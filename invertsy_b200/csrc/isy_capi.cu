@@ -493,6 +493,19 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
             CUDA_TRY(cudaGetLastError());
         }
     }
+    // sky-only call: nothing to render but the element-wise sky (isy_setup.cuh, sky_views_kernel)
+    if (w->T == 0 && !vquat && e->S == 1 && sp.kind != ISY_SKY_NONE && !(flags & ISY_FLAG_OUT_F64) && !out->rgb && !out->hit &&
+        !out->depth && !out->resp && (out->Y || out->dop || out->aop)) {
+        const long long B = (long long)P * H;
+        const int grid = (int)std::min<long long>(B, 8ll * device_sms(w->device));
+        sky_views_kernel<<<grid, 256, 0, st>>>(yaw, B, (int)e->R, e->d_py, e->d_trig, (const double*)(base + pl.off_ftheta), sp,
+                                                (const SunConst*)(base + pl.off_sun), rp.sun_per_view,
+                                                (const double2*)(base + pl.off_gtab), (float*)out->Y, (float*)out->dop,
+                                                (float*)out->aop);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        return ISY_OK;
+    }
     const int eye_kind0 = (vquat || !e->d_sorted) ? kEyeAny : (pl.global_best ? kEyeLarge : kEyeSmall);
     if (pl.rows && eye_kind0 == kEyeSmall && !init_c && e->S == 1 && !(sp.kind == ISY_SKY_PEREZ && rp.sun_per_view) &&
         !(flags & (ISY_FLAG_OUT_F64 | ISY_FLAG_INIT_FROM_SKY | ISY_FLAG_BRUTE_FORCE | ISY_FLAG_PER_VIEW_SKY)) &&

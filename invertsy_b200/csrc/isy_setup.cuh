@@ -130,6 +130,45 @@ __global__ void sky_shared_kernel(const double* __restrict__ yaw, int H, int R, 
     }
 }
 
+// Sky-only calls (an empty world, only Y / DoP / AoP asked for: sun sweeps over a dorsal-rim eye, examples/test_sky.py):
+// no position has anything to cull or rasterise, so the views are a pure element-wise map (view, ray) -> sky.  One CTA
+// takes a view at a time; consecutive threads take consecutive rays, so every store instruction covers 128 bytes of
+// one output row.  The arithmetic is sky_eval's, the same as in the render kernel's final pass.
+__global__ void __launch_bounds__(256) sky_views_kernel(const double* __restrict__ yaw, long long B, int R,
+                                                        const double* __restrict__ eye_py, const double* __restrict__ eye_trig,
+                                                        const double* __restrict__ f_theta, isy_sky_params sp,
+                                                        const SunConst* __restrict__ sun, int sun_per_view,
+                                                        const double2* __restrict__ gtab_g, float* __restrict__ oY,
+                                                        float* __restrict__ oP, float* __restrict__ oA) {
+    __shared__ double2 gtab[2 * (kGTab + 1)];
+    const bool perez = sp.kind == ISY_SKY_PEREZ;
+    if (perez)
+        for (int i = threadIdx.x; i < 2 * (kGTab + 1); i += blockDim.x) gtab[i] = gtab_g[i];
+    __syncthreads();
+    const float nanf_ = __int_as_float(0x7fc00000);
+    for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+        double hsn = 0, hcs = 1;
+        SunConst sc;
+        if (perez) {
+            sincos(wrap_yaw(yaw ? yaw[b] : 0.0), &hsn, &hcs);
+            sc = sun[sun_per_view ? b : 0];
+        }
+        const size_t row = (size_t)b * (size_t)R;
+        for (int r = threadIdx.x; r < R; r += blockDim.x) {
+            double Y = sp.luminance, P = 0, A = CUDART_NAN;                      // UniformSky: sky.py:77-79
+            if (perez) {
+                const double4 t4v = *reinterpret_cast<const double4*>(eye_trig + 4 * (size_t)r);
+                const double sy = t4v.z * hcs + t4v.w * hsn, cy = t4v.w * hcs - t4v.z * hsn;   // yaw_e + heading
+                sky_eval<false>(sp, sc, t4v.y * cy, t4v.y * sy, -t4v.x, eye_py[2 * (size_t)r] + kHalfPi, f_theta[r], Y, P, A,
+                                false, gtab);
+            }
+            if (oY) __stcs(oY + row + r, (float)Y);
+            if (oP) __stcs(oP + row + r, (float)P);
+            if (oA) __stcs(oA + row + r, perez ? (float)A : nanf_);
+        }
+    }
+}
+
 // Template rows of a launch in rows mode (isy_shade.cuh): what a ray that hits nothing gets -- hit = -1, depth = NaN,
 // the ground colour or NaN by its own pitch (world.py:80, :90) -- and, under a uniform sky, the three constant sky
 // rows (sky.py:77-79: y = luminance, p = 0, a = NaN).

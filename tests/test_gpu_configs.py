@@ -48,6 +48,23 @@ def test_config2_sky_sweep_sun_per_view(ib):
         assert np.abs(out["Y"][k] - y).max() < 1e-5 and np.abs(out["dop"][k] - p).max() < 1e-5
         assert circ_diff(out["aop"][k], a).max() < 1e-5
     assert np.all(np.isnan(out["rgb"]))          # dorsal rays, empty world: nothing seen (world.py:80)
+    # sky outputs only: the element-wise sky kernel (sky_views_kernel) instead of the render kernel; headings too
+    yw = np.linspace(-3.1, 3.1, K).reshape(K, 1)
+    sky_only = _np(r, pos=np.zeros((K, 3)), yaw=yw, sun=suns, outputs=("Y", "dop", "aop"))
+    general = _np(r, pos=np.zeros((K, 3)), yaw=yw, sun=suns, outputs=("Y", "dop", "aop", "rgb"))
+    for name in ("Y", "dop", "aop"):
+        assert np.array_equal(sky_only[name], general[name], equal_nan=True), name
+    for k in range(1, K, 7):
+        y, p, a = o.sky_render(suns[k, 0], suns[k, 1], o.view_rotations(np.rad2deg(yw[k, 0]), omm))
+        assert np.abs(sky_only["Y"][k] - y).max() < 1e-5 and np.abs(sky_only["dop"][k] - p).max() < 1e-5
+        assert circ_diff(sky_only["aop"][k], a).max() < 1e-5
+    # one sun for all views, and a uniform sky
+    one = _np(r, pos=np.zeros((6, 3)), yaw=yw[:6], outputs=("Y", "aop"))
+    y, p, a = o.sky_render(1.0, 0.0, o.view_rotations(np.rad2deg(yw[3, 0]), omm))
+    assert np.abs(one["Y"][3] - y).max() < 1e-5 and circ_diff(one["aop"][3], a).max() < 1e-5
+    ru = ib.Renderer(empty, ib.EyeLayout.from_angles(pitch, yaw), sky=ib.UniformSky(7.))
+    uni = _np(ru, pos=np.zeros((4, 3)), yaw=yw[:4], outputs=("Y", "dop", "aop"))
+    assert np.all(uni["Y"] == 7.) and np.all(uni["dop"] == 0.) and np.all(np.isnan(uni["aop"]))
 
 
 def test_config4_parallel_lines_slice(ib):
