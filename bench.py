@@ -11,19 +11,22 @@ the analytic sky (sun at zenith distance 60 deg, azimuth 180 deg as in examples/
 
 One *step* is the whole job the reference's heat-map scripts do with those views (sim/simulation.py:2675-2722,
 :3061-3092), on N GPUs (STRONG scaling: the one grid is split by position):
-  1. render  : rank r renders its block of positions (views.shard_positions); every view writes rgb + hit + depth +
+  1. render  : rank r renders every N-th position (views.shard_positions_interleaved: all ranks see the same mix of
+               dense and sparse vegetation); every view writes rgb + hit + depth +
                Y + DoP + AoP + the eye's PN response (36 B per ommatidium) to HBM once;
   2. evaluate: the PN responses of the block go through the perfect memory of the 812 route views
                (tcgen05 TF32 filter + exact fp32 re-check, csrc/isy_fam.cuh) -> one familiarity per view;
-  3. gather  : NCCL all_gather of the familiarity rows (1.44 M floats in total) so that every rank holds the map.
+  3. gather  : NCCL all_gather of the familiarity rows (1.44 M floats in total) + an on-device transpose into view
+               order, so that every rank holds the map.
 All three are inside the timed region; time = max over ranks (CUDA events + barriers).
 
   value : whole-job views/s (poses resident in HBM, results left in HBM).
-  e2e   : views/s through the reference-facing host API `Renderer.render_host` (C ABI isy_render_host) with pinned
-          HOST buffers on the WHOLE grid: H2D of the poses, D2H of the PN responses (4 KB per view, what the
-          data-collection simulations keep: simulation.py:2721 + agent.py:744) inside the timed region.
-          `e2e_familiarity` (poses in, familiarity out) and `e2e_full_views` (rgb, Y, DoP, AoP out: 24 KB per view,
-          bounded slice) are reported next to it.
+  e2e   : views/s with
+          HOST buffers: the same step through the package's public call `familiarity.HeatMap.__call__` on the WHOLE
+          grid -- H2D of the poses from pinned memory, the step, D2H of its result (the familiarity map) into pinned
+          memory, all inside the timed region.  `e2e_responses` (poses in, the PN responses of every view out through
+          isy_render_host: 4 KB per view, what the data-collection simulations log, simulation.py:2721 + agent.py:744)
+          and `e2e_full_views` (rgb, Y, DoP, AoP out: 24 KB per view, bounded slice) are reported next to it.
   roofline : dominant kernel = the render kernel; bound = HBM (the only traffic the algorithm requires is writing
           each view once); `roofline_familiarity` gives the tensor-core figure of the filter kernel.
   cpu_baseline : the UNMODIFIED reference (oracle/_ref, shipped by build()) -- or its bit-identical NumPy port when
@@ -79,8 +82,8 @@ def base_config(args):
             "views_per_step": args.rows * args.cols * args.oris,
             "outputs": "rgb,hit,depth,Y,dop,aop,PN response float32/int32 (36 B per ommatidium) + familiarity per view",
             "l2": "outputs per step far exceed L2 (126 MB); nothing is re-read between steps",
-            "parallelism": "strong scaling: positions of the ONE grid sharded over the ranks, familiarity rows "
-                           "all-gathered (NCCL) inside the timed region"}
+            "parallelism": "strong scaling: positions of the ONE grid dealt round-robin over the ranks, familiarity rows "
+                           "all-gathered (NCCL) and put into view order inside the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -278,16 +281,15 @@ def main():
     pos, yaw = grid_workload(args.rows, args.cols, args.oris)
     P, H = yaw.shape
     B = P * H
-    a, b = views.shard_positions(P, rank, world_size)
-    shard_max = max(views.shard_positions(P, k, world_size)[1] - views.shard_positions(P, k, world_size)[0]
-                    for k in range(world_size))
-    Pl, Bl = b - a, (b - a) * H
-    pos_d = torch.as_tensor(pos[a:b], device=dev)
-    yaw_d = torch.as_tensor(yaw[a:b], device=dev)
     names = ("rgb", "hit", "depth", "Y", "dop", "aop", "resp")
-    out = {}
-    fam_pad = torch.zeros(shard_max * H, dtype=torch.float32, device=dev)      # this rank's rows (padded to the largest shard)
-    fam_all = torch.empty(world_size * shard_max * H, dtype=torch.float32, device=dev)
+    # the job as the package's public API runs it: positions dealt round-robin over the ranks (every rank sees the same mix
+    # of dense and sparse vegetation), render -> familiarity -> all_gather + transpose into view order
+    hm = fam.HeatMap(r, memory, sensor, P, H, outputs=names)
+    mine = hm.positions()
+    Pl, Bl = len(mine), len(mine) * H
+    pos_d = torch.as_tensor(pos[mine], device=dev)
+    yaw_d = torch.as_tensor(yaw[mine], device=dev)
+    out = hm.views
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
@@ -298,11 +300,10 @@ def main():
         r.render(pos_d, yaw_d, outputs=names, out=out, sensor=sensor)
         if marks:
             marks[1].record()
-        memory.familiarity(out["resp"], out=fam_pad[:Bl])
+        memory.familiarity(out["resp"], out=hm.local[:Bl])
         if marks:
             marks[2].record()
-        if world_size > 1:
-            dist.all_gather_into_tensor(fam_all, fam_pad)
+        isy_dist.all_gather_interleaved(hm.local, P, H, out=hm.full, scratch=hm.scratch)
         if marks:
             marks[3].record()
 
@@ -349,13 +350,13 @@ def main():
              "cycles_per_position": pc[:3].sum() / max(pc[3], 1)}
     # sanity on the last step's result (cheap, outside the timed region)
     hit_frac = float((out["hit"][: 36 * 64] >= 0).float().mean().item())
-    fam_local = fam_pad[:Bl]
+    fam_local = hm.local[:Bl]
     unresolved = memory.unresolved()
     check = {"hit_fraction_first_rows": hit_frac, "familiarity_min": float(fam_local.min().item()),
              "familiarity_max": float(fam_local.max().item()), "familiarity_unresolved_queries": unresolved}
     if world_size > 1:      # every rank holds the whole map after the gather: this rank's rows are where they belong
-        mine = fam_all.view(world_size, shard_max * H)[rank, :Bl]
-        check["gathered_rows_match"] = bool(torch.equal(mine, fam_local))
+        got = hm.full[:B].view(P, H)[torch.as_tensor(mine, device=dev)].reshape(-1)
+        check["gathered_rows_match"] = bool(torch.equal(got, fam_local))
 
     # ---------------- extras: render kernel alone on the whole grid per rank (weak), sky per view ------------
     extras = {}
@@ -393,58 +394,53 @@ def main():
         del wout, pos_wd, yaw_wd
         torch.cuda.empty_cache()
 
-    # ---------------- e2e: host buffers through the C-ABI host entry point, whole grid ----------------
-    pos_h = torch.as_tensor(pos[a:b]).pin_memory()
-    yaw_h = torch.as_tensor(yaw[a:b]).pin_memory()
-    host_out = {"resp": torch.empty((Bl, N_OMM), dtype=torch.float32, pin_memory=True)}
-
-    def e2e_step():
-        r.render_host(pos_h.numpy(), yaw_h.numpy(), outputs=("resp",), out=host_out, sensor=sensor)
-
-    e2e_step()
+    # ---------------- e2e: the same step through the public API with HOST buffers ----------------
+    # poses of this rank's positions in pinned host memory -> H2D; render (all 7 outputs) + familiarity + all_gather +
+    # transpose; the familiarity map (the step's result) -> D2H into pinned host memory, on every rank
+    pos_h = torch.as_tensor(pos[mine]).pin_memory()
+    yaw_h = torch.as_tensor(yaw[mine]).pin_memory()
+    hm(pos_h, yaw_h)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
+        fam_host = hm(pos_h, yaw_h)
     e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = B * args.e2e_steps / e_s
-    h2d = int(P * 24 + B * 8 + 16 * world_size)
-    d2h = int(B * N_OMM * 4)
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "views_per_step": int(B), "api": "Renderer.render_host(outputs=('resp',)) -> isy_render_host: poses in, PN "
-           "responses out (pinned host buffers, NUMA node %s)" % numa, "pcie_GBps_per_gpu": Bl * N_OMM * 4 * args.e2e_steps / e_s / 1e9}
-    # host check: the e2e path returned what the device path computed
-    check["e2e_matches_device"] = bool(torch.equal(host_out["resp"][:1000], out["resp"][:1000].cpu()))
-    del host_out
+    h2d = int(P * 24 + B * 8)
+    d2h = int(B * 4 * world_size)
+    e2e = {"value": B * args.e2e_steps / e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "views_per_step": int(B), "api": "familiarity.HeatMap.__call__: host poses in -> Renderer.render (7 outputs) -> "
+           "PerfectMemory.familiarity -> all_gather -> familiarity map out (pinned host, every rank)"}
+    check["e2e_matches_device"] = bool(torch.equal(fam_host[:B], (hm.full if world_size > 1 else hm.local)[:B].cpu()))
 
     if not args.no_extras:
-        fam_h = torch.empty(Bl, dtype=torch.float32, pin_memory=True)
+        # the data-collection path: PN responses (4 KB per view) to the host through isy_render_host, whole grid
+        host_out = {"resp": torch.empty((Bl, N_OMM), dtype=torch.float32, pin_memory=True)}
 
-        def fam_step():       # poses in (host), familiarity out (host)
-            p_d, y_d = pos_h.to(dev, non_blocking=True), yaw_h.to(dev, non_blocking=True)
-            r.render(p_d, y_d, outputs=("resp",), out=out, sensor=sensor)
-            memory.familiarity(out["resp"], out=fam_pad[:Bl])
-            fam_h.copy_(fam_pad[:Bl], non_blocking=True)
-            torch.cuda.synchronize()
+        def resp_step():
+            r.render_host(pos_h.numpy(), yaw_h.numpy(), outputs=("resp",), out=host_out, sensor=sensor)
 
-        fam_step()
+        resp_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            fam_step()
-        e_f = max_over_ranks(time.perf_counter() - t0)
-        extras["e2e_familiarity"] = {"value": B * args.e2e_steps / e_f, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                                     "d2h_bytes_per_step": int(B * 4), "what": "poses in (pinned host), one familiarity "
-                                     "per view out (pinned host); views stay on the device"}
+            resp_step()
+        torch.cuda.synchronize()
+        e_r = max_over_ranks(time.perf_counter() - t0)
+        extras["e2e_responses"] = {"value": B * args.e2e_steps / e_r, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                                   "d2h_bytes_per_step": int(B * N_OMM * 4), "pcie_GBps_per_gpu": Bl * N_OMM * 4 * args.e2e_steps / e_r / 1e9,
+                                   "what": "Renderer.render_host(outputs=('resp',)) -> isy_render_host: poses in, the PN responses of every "
+                                           "view out (4 KB per view, what the data-collection simulations log); the box exposes one NUMA "
+                                           "node (%s), the ranks share its host-memory path" % numa}
+        check["e2e_responses_match_device"] = bool(torch.equal(host_out["resp"][:1000], out["resp"][:1000].cpu()))
+        del host_out
         Pe = min(2048, Pl)
         full_names = ("rgb", "Y", "dop", "aop")
         full_out = {}
-        r.render_host(pos[a:a + Pe], yaw[a:a + Pe], outputs=full_names, out=full_out)
+        r.render_host(pos[mine[:Pe]], yaw[mine[:Pe]], outputs=full_names, out=full_out)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            r.render_host(pos[a:a + Pe], yaw[a:a + Pe], outputs=full_names, out=full_out)
+            r.render_host(pos[mine[:Pe]], yaw[mine[:Pe]], outputs=full_names, out=full_out)
         e_v = max_over_ranks(time.perf_counter() - t0)
         extras["e2e_full_views"] = {"value": world_size * Pe * H * args.e2e_steps / e_v, "unit": UNIT,
                                     "d2h_bytes_per_step": int(world_size * Pe * H * N_OMM * 24),

@@ -14,7 +14,7 @@ the gloo backend.
 import torch
 import torch.distributed as dist
 
-from .views import shard_positions
+from .views import shard_positions, shard_positions_interleaved
 
 
 def bind_to_gpu_numa(device_index):
@@ -102,3 +102,26 @@ def render_sharded(render_fn, pos, yaw, reduce_fn=None, dst=None, group=None):
     small = reduce_fn(local) if reduce_fn is not None else local
     views_per_position = yaw.shape[1] if getattr(yaw, "ndim", 1) > 1 else 1
     return gather_views(small, len(pos), views_per_position, dst=dst, group=group), local, block
+
+
+def all_gather_interleaved(local, nb_positions, views_per_position, out=None, scratch=None, group=None):
+    """
+    For positions dealt round-robin (`views.shard_positions_interleaved`): `local` holds this rank's views in its own
+    order, [ceil(P / world) * H] values (padded to the largest shard; the padding is ignored).  One NCCL all_gather, then
+    one on-device transpose puts every view at its global index p * H + h.  Returns the [P * H] tensor (every rank).
+    """
+    rank, world = rank_and_world(group)
+    H = views_per_position
+    per = (nb_positions + world - 1) // world
+    if local.numel() != per * H:
+        raise ValueError("local must hold ceil(P / world) * H = %d values (pad the short shards)" % (per * H))
+    if world == 1:
+        return local[:nb_positions * H]
+    if scratch is None:
+        scratch = torch.empty(world * per * H, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(scratch, local, group=group)
+    full = scratch.view(world, per, H).permute(1, 0, 2)          # [local index][rank][heading] = global position order
+    if out is None:
+        out = torch.empty(per * world * H, dtype=local.dtype, device=local.device)
+    out.view(per, world, H).copy_(full)
+    return out[:nb_positions * H]

@@ -226,3 +226,54 @@ def evaluate_sharded(local_views, route_views, nb_positions, views_per_position,
     from . import distributed
     fam = evaluate(local_views, route_views, whitening=whitening, memory=memory)
     return distributed.gather_views({"familiarity": fam}, nb_positions, views_per_position, dst=dst, group=group)["familiarity"]
+
+
+class HeatMap(object):
+    """
+    The whole job of the reference's familiarity heat-map / parallel-lines scripts for one set of views, on however many
+    GPUs the process group has (sim/simulation.py:2675-2722 renders the views, :3061-3092 evaluates them):
+
+        hm = HeatMap(renderer, memory, sensor, nb_positions=P, nb_headings=H)
+        fam = hm(pos, yaw)            # host poses of THIS rank's positions in, the whole map out (pinned host tensor)
+
+    Positions are dealt round-robin over the ranks (`views.shard_positions_interleaved`); each rank renders its share,
+    turns the PN responses the render kernel writes into familiarities with the perfect memory, one NCCL all_gather +
+    an on-device transpose give every rank the map in view order p * H + h.  All buffers are allocated once.
+    """
+
+    def __init__(self, renderer, memory, sensor, nb_positions, nb_headings, outputs=("resp",), group=None):
+        from . import distributed
+        self.r, self.memory, self.sensor, self.group = renderer, memory, sensor, group
+        self.P, self.H = int(nb_positions), int(nb_headings)
+        self.rank, self.world = distributed.rank_and_world(group)
+        self.per = (self.P + self.world - 1) // self.world          # positions of the largest shard
+        self.outputs = tuple(outputs) if "resp" in outputs else tuple(outputs) + ("resp",)
+        dev = "cuda:%d" % renderer.device
+        self.views = {}                                             # the rank's rendered outputs (device, re-used)
+        self.local = torch.zeros(self.per * self.H, dtype=torch.float32, device=dev)
+        self.scratch = torch.empty(self.world * self.per * self.H, dtype=torch.float32, device=dev) if self.world > 1 else None
+        self.full = torch.empty(self.world * self.per * self.H, dtype=torch.float32, device=dev) if self.world > 1 else None
+        self.host = torch.empty(self.P * self.H, dtype=torch.float32, pin_memory=True)
+
+    def positions(self):
+        """indices of the positions this rank takes"""
+        from .views import shard_positions_interleaved
+        return shard_positions_interleaved(self.P, self.rank, self.world)
+
+    def on_device(self, pos_dev, yaw_dev):
+        """this rank's poses (device tensors) -> the whole map (device), asynchronous on the current stream"""
+        from . import distributed
+        n = pos_dev.shape[0] * self.H
+        self.r.render(pos_dev, yaw_dev, outputs=self.outputs, out=self.views, sensor=self.sensor)
+        self.memory.familiarity(self.views["resp"], out=self.local[:n])
+        return distributed.all_gather_interleaved(self.local, self.P, self.H, out=self.full, scratch=self.scratch,
+                                                  group=self.group)
+
+    def __call__(self, pos_host, yaw_host):
+        dev = self.local.device
+        pos_d = torch.as_tensor(pos_host).to(dev, non_blocking=True)
+        yaw_d = torch.as_tensor(yaw_host).to(dev, non_blocking=True)
+        fam = self.on_device(pos_d, yaw_d)
+        self.host.copy_(fam, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return self.host

@@ -84,3 +84,12 @@ def shard_positions(nb_positions, rank, world_size):
     base, extra = divmod(nb_positions, world_size)
     start = rank * base + min(rank, extra)
     return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_positions_interleaved(nb_positions, rank, world_size):
+    """
+    Every world_size-th position from `rank`: the positions of one rank are spread over the whole arena, so that all
+    ranks see the same mix of dense and sparse vegetation (contiguous blocks of the heat-map grid differ by +-30 % in
+    work, which is what limits strong scaling).  Returns the index array; `unshard_interleaved` undoes it.
+    """
+    return np.arange(rank, nb_positions, world_size)

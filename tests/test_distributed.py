@@ -75,3 +75,36 @@ def test_single_process_is_a_passthrough():
     yaw = np.zeros((3, 2))
     got, local, blk = render_sharded(_fake_render, pos, yaw)
     assert blk == (0, 3) and torch.equal(got["Y"], local["Y"])
+
+
+def _worker_interleaved(rank, world, port, P, H, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from invertsy_b200.distributed import all_gather_interleaved
+        from invertsy_b200.views import shard_positions_interleaved
+        full = torch.arange(P * H, dtype=torch.float32) * 0.5 + 1.0          # value of view p * H + h
+        idx = shard_positions_interleaved(P, rank, world)
+        per = (P + world - 1) // world
+        local = torch.zeros(per * H)
+        local[:len(idx) * H] = full.view(P, H)[torch.as_tensor(idx)].reshape(-1)
+        got = all_gather_interleaved(local, P, H)
+        q.put((rank, bool(torch.equal(got, full)), len(idx)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("P,H", [(7, 3), (8, 2), (1, 4)])
+def test_interleaved_shards_gather_back_into_view_order(P, H):
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_interleaved, args=(r, world, port, P, H, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res) and sum(n for _, _, n in res) == P
