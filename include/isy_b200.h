@@ -86,7 +86,7 @@ typedef struct {
     void* Y;        /* [B][N]     sky luminance      (sky.py:313, :334), cone-averaged               */
     void* dop;      /* [B][N]     degree of polarisation (sky.py:317)                                */
     void* aop;      /* [B][N]     angle of polarisation  (sky.py:320-324), circular cone average     */
-    void* resp;     /* [B][N][C]  photoreceptor responses of the eye (needs isy_sensor_params), C = 3 or 1:
+    void* resp;     /* [B][N][C]  photoreceptor responses of the eye (needs isy_sensor_params), C = 3 or 1 (or 0 -> 1 value):
                                   what `eye(sky=, scene=)` leaves in eye.responses (simulation.py:2707, :2721),
                                   or, with C = 1, the PN input clip(responses.mean(axis=1), 0, 1) (agent.py:744)  */
 } isy_outputs;      /* element type: float, or double with ISY_FLAG_OUT_F64                           */
@@ -98,12 +98,18 @@ typedef struct {
  *     else luminance2skycolour(Y) / 255 under a sky (world.py:465-479), else 0;
  * the samples of an ommatidium are averaged with the cone weights; then, per channel c in (R, G, B),
  *     resp_c = clip(mean_c * w_rgb[c] * gain, 0, 1)                (c_sensitive, omm_res of the eye's constructor)
- * and with channels == 1 the output is clip((resp_R + resp_G + resp_B) / 3, 0, 1).                            */
+ * and with channels == 1 the output is clip((resp_R + resp_G + resp_B) / 3, 0, 1).
+ * Polarisation (omm_pol_op = rho in [0, 1]): a sample that sees the sky is multiplied by
+ *     rho * (sin^2(A - phi) + cos^2(A - phi) * (1 - P)^2) + (1 - rho)
+ * with P, A the degree and angle of polarisation of the sky in its direction (sky.py:317-324) and phi the azimuth of
+ * the sample's own viewing direction (the microvilli of a dorsal-rim ommatidium lie along it); 1 for rho = 0.
+ * channels == 0 is the polarisation photoreceptor of a PolarisationSensor (agent.py:835, :879): one value per
+ * ommatidium, resp = gain * sqrt(cone average of Y * that term over the samples that see the sky, 0 for the others). */
 typedef struct {
     float w_rgb[3];    /* spectral sensitivity to R, G, B: c_sensitive[1:4] of the IRGBU vector (agent.py:590)  */
     float gain;        /* omm_res / saturation (agent.py:589)                                                    */
-    int32_t channels;  /* 3 or 1                                                                                 */
-    int32_t reserved;
+    int32_t channels;  /* 3, 1 or 0 (see above)                                                                  */
+    float pol_op;      /* omm_pol_op: polarisation sensitivity of the photoreceptors, 0 = none                   */
 } isy_sensor_params;
 
 typedef struct isy_world isy_world;

@@ -11,7 +11,7 @@ from . import env  # noqa: F401
 from .env.world import WorldBase, Seville2009, SimpleWorld  # noqa: F401
 from .env.sky import Sky, UniformSky  # noqa: F401
 from .render import EyeLayout, Renderer, fibonacci_lattice  # noqa: F401
-from .sense import CompoundEye  # noqa: F401
+from .sense import CompoundEye, PolarisationSensor  # noqa: F401
 from . import datasets, distributed, familiarity, views  # noqa: F401
 
 __version__ = "0.1.0"

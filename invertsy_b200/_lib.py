@@ -43,13 +43,14 @@ class Outputs(ctypes.Structure):
 class SensorParams(ctypes.Structure):
     """isy_sensor_params: the photoreceptor transform behind the `resp` output (include/isy_b200.h)."""
     _fields_ = [("w_rgb", ctypes.c_float * 3), ("gain", ctypes.c_float), ("channels", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("pol_op", ctypes.c_float)]
 
     @staticmethod
-    def make(w_rgb=(1., 1., 1.), gain=1., channels=3):
+    def make(w_rgb=(1., 1., 1.), gain=1., channels=3, pol_op=0.):
+        """channels: 3 = (N, 3) responses, 1 = PN inputs (N,), 0 = polarisation photoreceptors (N,)"""
         sp = SensorParams()
         sp.w_rgb[0], sp.w_rgb[1], sp.w_rgb[2] = (float(v) for v in w_rgb)
-        sp.gain, sp.channels, sp.reserved = float(gain), int(channels), 0
+        sp.gain, sp.channels, sp.pol_op = float(gain), int(channels), float(pol_op)
         return sp
 
 

@@ -410,8 +410,8 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
     if (sp.kind == ISY_SKY_PEREZ && !sun) return fail(ISY_ERR_INVALID, "isy_render: Perez sky needs a sun position");
     if ((out->Y || out->dop || out->aop) && sp.kind == ISY_SKY_NONE)
         return fail(ISY_ERR_INVALID, "isy_render: sky outputs requested without a sky");
-    if (out->resp && (!sensor || (sensor->channels != 1 && sensor->channels != 3)))
-        return fail(ISY_ERR_INVALID, "isy_render: photoreceptor responses need isy_sensor_params with 1 or 3 channels");
+    if (out->resp && (!sensor || (sensor->channels != 0 && sensor->channels != 1 && sensor->channels != 3)))
+        return fail(ISY_ERR_INVALID, "isy_render: photoreceptor responses need isy_sensor_params with 3, 1 or 0 channels");
     Plan pl = make_plan(w, e, P, H);
     if (!ws || ws_bytes < pl.total)
         return fail(ISY_ERR_WORKSPACE, "isy_render: workspace %zu B < required %zu B", ws_bytes, pl.total);
@@ -668,8 +668,8 @@ int isy_render_host(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, 
                     const double* yaw_host, const double* view_quat_host, const double* sun_host,
                     const isy_sky_params* sky, const isy_sensor_params* sensor, uint32_t flags,
                     const isy_outputs* out_host) {
-    if (out_host && out_host->resp && (!sensor || (sensor->channels != 1 && sensor->channels != 3)))
-        return fail(ISY_ERR_INVALID, "isy_render_host: photoreceptor responses need isy_sensor_params with 1 or 3 channels");
+    if (out_host && out_host->resp && (!sensor || (sensor->channels != 0 && sensor->channels != 1 && sensor->channels != 3)))
+        return fail(ISY_ERR_INVALID, "isy_render_host: photoreceptor responses need isy_sensor_params with 3, 1 or 0 channels");
     if (!w || !e || !pos_host || !out_host || P < 0 || H <= 0) return fail(ISY_ERR_INVALID, "isy_render_host: bad argument");
     if (w->device < 0 || w->device >= 16) return fail(ISY_ERR_INVALID, "isy_render_host: device index out of range");
     DeviceGuard g(w->device);
@@ -695,7 +695,7 @@ int isy_render_host(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, 
     const size_t per_view[kOut] = {out_host->rgb ? 3 * (size_t)N * esz : 0, out_host->hit ? (size_t)R * 4 : 0,
                                    out_host->depth ? (size_t)R * esz : 0, out_host->Y ? (size_t)N * esz : 0,
                                    out_host->dop ? (size_t)N * esz : 0, out_host->aop ? (size_t)N * esz : 0,
-                                   out_host->resp ? (size_t)N * sensor->channels * esz : 0};
+                                   out_host->resp ? (size_t)N * std::max(sensor->channels, 1) * esz : 0};
     size_t bytes_per_pos = 0;
     for (size_t b : per_view) bytes_per_pos += (size_t)H * b;
     // a few views (the closed-loop step of a simulation: one view per call): one packed transfer each way

@@ -131,18 +131,35 @@ struct RenderParams {
 };
 
 // ---- photoreceptor transform behind out.resp (isy_sensor_params in isy_b200.h) ----
+// polarisation term of a photoreceptor of sensitivity rho whose microvilli lie along the azimuth (cphi, sphi) of its
+// viewing direction:  rho (sin^2(A - phi) + cos^2(A - phi) (1 - P)^2) + (1 - rho).  (X, Yd) = view direction minus sun
+// direction in the xy plane gives the angle of polarisation without any trigonometry: A = atan2(Yd, X) + pi/2 (sky.py:323)
+// => (sin A, cos A) = (X, -Yd) / |(X, Yd)|.
+__device__ __forceinline__ float sensor_pol_term(float rho, float P, float X, float Yd, float cphi, float sphi) {
+    const float h2 = X * X + Yd * Yd;
+    if (!(rho > 0.f) || !(h2 > 1e-36f)) return 1.f;
+    float ih;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ih) : "f"(h2));
+    const float sA = X * ih, cA = -Yd * ih;
+    const float cd = cA * cphi + sA * sphi, c2 = cd * cd, q = 1.f - P;
+    return rho * ((1.f - c2) + c2 * q * q) + (1.f - rho);
+}
 // colour of one cone sample on the 0..1 scale: triangle colour, else ground, else the sky colour of its luminance
-// (luminance2skycolour / 255, world.py:465-479), else nothing
-__device__ __forceinline__ void sensor_colour(bool hit, float tr, float tg, float tb, bool ground, bool has_sky, double Y,
-                                              float& r, float& g, float& b) {
-    if (hit) {
+// (luminance2skycolour / 255, world.py:465-479) times the polarisation term `pol`, else nothing.  channels == 0
+// (polarisation photoreceptor): the sky's luminance times the term where the sample sees the sky, else 0.
+__device__ __forceinline__ void sensor_colour(const isy_sensor_params& sp, bool hit, float tr, float tg, float tb, bool ground,
+                                              bool has_sky, double Y, float pol, float& r, float& g, float& b) {
+    const bool sees_sky = !hit && !ground && has_sky;
+    if (sp.channels == 0) {
+        r = g = b = sees_sky ? (float)Y * pol : 0.f;
+    } else if (hit) {
         r = tr, g = tg, b = tb;
     } else if (ground) {
         r = (float)(229.0 / 255.0), g = (float)(183.0 / 255.0), b = (float)(90.0 / 255.0);
     } else if (has_sky) {
-        r = (float)(fmin(fmax(19.0 * Y + 13.0, 0.0), 255.0) / 255.0);
-        g = (float)(fmin(fmax(19.0 * Y + 135.0, 0.0), 255.0) / 255.0);
-        b = (float)(fmin(fmax(19.0 * Y + 201.0, 0.0), 255.0) / 255.0);
+        r = (float)(fmin(fmax(19.0 * Y + 13.0, 0.0), 255.0) / 255.0) * pol;
+        g = (float)(fmin(fmax(19.0 * Y + 135.0, 0.0), 255.0) / 255.0) * pol;
+        b = (float)(fmin(fmax(19.0 * Y + 201.0, 0.0), 255.0) / 255.0) * pol;
     } else {
         r = 0.f, g = 0.f, b = 0.f;
     }
@@ -160,8 +177,12 @@ __device__ __forceinline__ float sensor_pn(float r, float g, float b) {
 // stores the response(s) of ommatidium `oi` (element index b*N + n) from its cone-averaged 0..1 colour
 template <typename T>
 __device__ __forceinline__ void sensor_store(const isy_sensor_params& sp, void* resp, size_t oi, float r, float g, float b) {
-    sensor_finish(sp, r, g, b);
     T* q = reinterpret_cast<T*>(resp);
+    if (sp.channels == 0) {      // polarisation photoreceptor: gain * sqrt(averaged polarised luminance)
+        __stcs(q + oi, (T)(sp.gain * sqrtf(fmaxf(r, 0.f))));
+        return;
+    }
+    sensor_finish(sp, r, g, b);
     if (sp.channels == 1) {
         __stcs(q + oi, (T)sensor_pn(r, g, b));
     } else {

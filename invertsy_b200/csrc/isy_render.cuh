@@ -350,8 +350,17 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                         o.r = __ldg(col + 0), o.g = __ldg(col + 1), o.b = __ldg(col + 2);
                     }
                     o.sr = 0.f, o.sg = 0.f, o.sb = 0.f;
-                    if (rp.out.resp)
-                        sensor_colour(ray.hit >= 0, (float)o.r, (float)o.g, (float)o.b, ray.pitch >= 0, want_sky, o.Y, o.sr, o.sg, o.sb);
+                    if (rp.out.resp) {
+                        float pol = 1.f;
+                        if (perez && rp.sensor.pol_op > 0.f) {
+                            const SunConst& sc = rp.sun[rp.sun_per_view ? b : 0];
+                            const double hxy = sqrt(dx * dx + dy * dy);
+                            pol = sensor_pol_term(rp.sensor.pol_op, (float)o.P, (float)(dx - sc.sx), (float)(dy - sc.sy),
+                                                  hxy > 0 ? (float)(dx / hxy) : 1.f, hxy > 0 ? (float)(dy / hxy) : 0.f);
+                        }
+                        sensor_colour(rp.sensor, ray.hit >= 0, (float)o.r, (float)o.g, (float)o.b, ray.pitch >= 0, want_sky, o.Y, pol,
+                                      o.sr, o.sg, o.sb);
+                    }
                     write_view<kF64>(rp, b, rr, valid, ray.hit, ray.best, o);
                 }
             }

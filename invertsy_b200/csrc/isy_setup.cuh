@@ -124,7 +124,9 @@ __global__ void sky_shared_kernel(const double* __restrict__ yaw, int H, int R, 
     tab[i] = (float)Y, tab[plane + i] = (float)P, tab[2 * plane + i] = (float)A;
     if (want_resp) {   // plane 3: the PN response of this (heading, ray) when the ray hits nothing
         float sr, sg, sb;
-        sensor_colour(false, 0.f, 0.f, 0.f, eye_py[2 * (size_t)r] >= 0, true, Y, sr, sg, sb);
+        const float pol = sensor_pol_term(sensor.pol_op, (float)P, (float)(t4v.y * cy - sun[0].sx), (float)(t4v.y * sy - sun[0].sy),
+                                          (float)cy, (float)sy);
+        sensor_colour(sensor, false, 0.f, 0.f, 0.f, eye_py[2 * (size_t)r] >= 0, true, Y, pol, sr, sg, sb);
         sensor_finish(sensor, sr, sg, sb);
         tab[3 * plane + i] = sensor_pn(sr, sg, sb);
     }
@@ -187,7 +189,7 @@ __global__ void row_templates_kernel(const double* __restrict__ eye_py, int R, i
     if (uniform_sky) sky_rows[r] = (float)luminance, sky_rows[R + r] = 0.f, sky_rows[2 * (size_t)R + r] = nanf_;
     if (want_resp) {   // PN response of a ray that hits nothing under no sky / a uniform sky (constant luminance)
         float sr, sg, sb;
-        sensor_colour(false, 0.f, 0.f, 0.f, ground, has_sky != 0, luminance, sr, sg, sb);
+        sensor_colour(sensor, false, 0.f, 0.f, 0.f, ground, has_sky != 0, luminance, 1.f, sr, sg, sb);   // (uniform sky: DoP = 0)
         sensor_finish(sensor, sr, sg, sb);
         bg[5 * (size_t)R + r] = sensor_pn(sr, sg, sb);
     }

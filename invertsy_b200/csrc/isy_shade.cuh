@@ -71,11 +71,12 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
         for (int hh0 = hc * hper; hh0 < hend; hh0 += kSU, off0 += kSU * ostride, offn0 += kSU * nstride) {
             double Y[kSU], P[kSU], A[kSU];
             float sA[kSU], cA[kSU];      // (cone-sampled eyes) sin / cos of the polarisation angle
+            float pol[kSU];              // polarisation term of the photoreceptor (out.resp)
             size_t view[kSU];
             unsigned int id[kSU];
 #pragma unroll
             for (int q = 0; q < kSU; ++q) {
-                Y[q] = 0, P[q] = 0, A[q] = CUDART_NAN;
+                Y[q] = 0, P[q] = 0, A[q] = CUDART_NAN, pol[q] = 1.f;
                 const int hh = min(hh0 + q, hend - 1);
                 view[q] = (size_t)p * rp.H + grp + (size_t)hh * rp.ngroups;   // group = every ngroups-th heading
                 const int hs = sm.ras.hinv[hh];
@@ -86,6 +87,9 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
                     const SunConst& sc = kOneSun ? sm.sun0 : rp.sun[rp.sun_per_view ? view[q] : 0];
                     sky_eval<false>(rp.sky, sc, t4v.y * cy, t4v.y * sy, -t4v.x, e_pitch + kHalfPi, f_theta, Y[q], P[q], A[q],
                                     false, sm.gtab);
+                    if (rp.out.resp && rp.sensor.pol_op > 0.f)
+                        pol[q] = sensor_pol_term(rp.sensor.pol_op, (float)P[q], (float)(t4v.y * cy - sc.sx), (float)(t4v.y * sy - sc.sy),
+                                                 (float)cy, (float)sy);
                     if (kCone) {
                         // A = atan2(dy - sy, dx - sx) + pi/2 (sky.py:323)  =>  (sin A, cos A) = (X, -Y) / |(X, Y)|
                         const float X = (float)(t4v.y * cy - sc.sx), Yd = (float)(t4v.y * sy - sc.sy), h2 = X * X + Yd * Yd;
@@ -117,7 +121,7 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
                     cr = __ldg(col + 0), cg = __ldg(col + 1), cb = __ldg(col + 2);
                 }
                 float sr = 0.f, sg = 0.f, sb = 0.f;      // the sample on the 0..1 scale of the photoreceptor transform
-                if (rp.out.resp) sensor_colour(id[q] != kNoCopy, cr, cg, cb, ground, perez || uniform, Y[q], sr, sg, sb);
+                if (rp.out.resp) sensor_colour(rp.sensor, id[q] != kNoCopy, cr, cg, cb, ground, perez || uniform, Y[q], pol[q], sr, sg, sb);
                 if (kCone) {
                     if (valid) {
                         const size_t i = off0 + q * ostride;

@@ -20,6 +20,12 @@ unpinned parts explicitly:
     `luminance2skycolour(Y) / 255` under a sky, else 0; the samples are averaged with the cone weights;
     responses (N, 3) = clip(mean colour * c_sensitive[R, G, B] * omm_res, 0, 1).  `transform_reference` states
     the same in NumPy (float64) for tests and documentation;
+  * `omm_pol_op` = rho > 0: a sample that sees the sky is multiplied by rho (sin^2(A - phi) + cos^2(A - phi)(1 - P)^2)
+    + (1 - rho), P / A the sky's degree / angle of polarisation in its direction and phi the azimuth of the sample's
+    viewing direction (the microvilli of the photoreceptor lie along it); `PolarisationSensor` (the dorsal-rim sensor
+    of the path-integration agents, agent.py:835, :879) returns one such photoreceptor per ommatidium:
+    omm_res * sqrt(cone average of Y * that term), the sky's luminance seen through a polarisation filter;
+  * `eye(sky=sky)` without a scene (examples/test_sky.py:22) renders against an empty world: the sky alone;
   * `noise` > 0: a fraction of the ommatidia is blanked per call exactly as the reference's environment does for
     its own outputs (`env/_helpers.py:10-36` add_noise -> `c[eta] = 0`, world.py:125-127), with the eye's `rng`.
 
@@ -70,6 +76,31 @@ def yaw_only(rot, tol=0.0):
     if abs(x) > tol or abs(y) > tol:
         return None
     return 2.0 * np.arctan2(z, w) if w >= 0 else 2.0 * np.arctan2(-z, -w)
+
+
+_EMPTY = {}
+
+
+def _empty_world(device):
+    """a world without triangles (sky-only calls)"""
+    from .env.world import WorldBase
+    if device not in _EMPTY:
+        _EMPTY[device] = WorldBase(np.zeros((0, 3, 3), dtype=np.float32), np.zeros((0, 3), dtype=np.float32), device=device)
+    return _EMPTY[device]
+
+
+def dorsal_rim_layout(nb_input=60, field_of_view=56., degrees=True):
+    """
+    Ommatidia of a dorsal-rim polarisation sensor: `nb_input` viewing directions on a Fibonacci lattice over the cap of
+    full opening angle `field_of_view` around the zenith (InvertPy's own layout is not vendored: this is the library's,
+    documented here).  Returns the orientations as a SciPy Rotation (direction = ori.apply([1, 0, 0])).
+    """
+    fov = np.deg2rad(field_of_view) if degrees else float(field_of_view)
+    i = np.arange(nb_input, dtype=np.float64)
+    yaw = (np.pi * (1. + np.sqrt(5.)) * (i + .5)) % (2 * np.pi) - np.pi
+    z = 1. - (1. - np.cos(fov / 2.)) * (i + .5) / nb_input          # uniform in solid angle over the cap
+    pitch = np.arccos(z) - np.pi / 2                                   # negative pitch looks up (world.py:84-90)
+    return R.from_euler('ZY', np.c_[yaw, pitch])
 
 
 class CompoundEye(object):
@@ -127,7 +158,9 @@ class CompoundEye(object):
 
     def sensor_params(self, channels=3):
         """the eye's photoreceptor transform as the C ABI takes it (isy_sensor_params)"""
-        return _lib.SensorParams.make(self.w_rgb, float(np.max(self.omm_res)), channels)
+        return _lib.SensorParams.make(self.w_rgb, float(np.max(self.omm_res)), channels, float(np.max(self.omm_pol_op)))
+
+    nb_channels = 3      # values per ommatidium in `responses`
 
     # ---- pose (reference: eye.xyz = ..., eye.ori = R.from_euler('Z', yaw, degrees=True)) ----
     @property
@@ -161,18 +194,20 @@ class CompoundEye(object):
     # ---- sensing ----
     def __call__(self, sky=None, scene=None, callback=None):
         if scene is None:
-            raise ValueError("CompoundEye needs a scene (a WorldBase) to look at")
+            if sky is None:
+                raise ValueError("the eye needs a sky and / or a scene to look at")
+            scene = _empty_world(self.device)          # eye(sky=sky): the sky alone (examples/test_sky.py:22)
         r = self._renderer(scene, sky)
         yaw = yaw_only(self._ori)
         if self._sensor3 is None:
-            self._sensor3 = self.sensor_params(3)
+            self._sensor3 = self.sensor_params(3 if self.nb_channels == 3 else 0)
         if yaw is not None:     # the pose of every simulation step of the reference: rasteriser for yaw-only views
             out = r.render_host(self._xyz.reshape(1, 3), yaw=np.array([[yaw]]), outputs=("resp",),
                                 sensor=self._sensor3, out=self._host_out)
         else:
             out = r.render_host(self._xyz.reshape(1, 3), quat=self._ori.as_quat().reshape(1, 1, 4), outputs=("resp",),
                                 sensor=self._sensor3, out=self._host_out)
-        resp = out["resp"].numpy()[0].astype(self.dtype, copy=True)
+        resp = out["resp"].numpy()[0].astype(self.dtype, copy=True).reshape(self.nb_ommatidia, -1)
         if self.noise:
             resp[add_noise(noise=self.noise, shape=resp.shape, rng=self.rng)] = 0.      # world.py:125-127
         self.responses = resp
@@ -190,3 +225,24 @@ class CompoundEye(object):
         res = {} if out is None else {"resp": out}
         res = r.render_host(pos, np.deg2rad(yaw_deg), outputs=("resp",), sensor=self.sensor_params(channels), out=res)
         return res["resp"].numpy()
+
+
+class PolarisationSensor(CompoundEye):
+    """
+    The dorsal-rim polarisation sensor of the reference's path-integration agents (`PolarisationSensor(nb_input=60,
+    field_of_view=56, degrees=True, noise=, rng=)`, agent/agent.py:835, :1385; called as `pol_sensor(sky=, scene=)`,
+    :879).  One polarisation-sensitive photoreceptor per ommatidium (`omm_pol_op` = 1 by default):
+        responses (N, 1) = omm_res * sqrt(Y * (rho (sin^2(A - phi) + cos^2(A - phi)(1 - P)^2) + 1 - rho))
+    evaluated on the device from the sky model's Y / DoP / AoP in each viewing direction (include/isy_b200.h,
+    isy_sensor_params, channels = 0); a sample that a triangle or the ground hides contributes nothing.
+    """
+    nb_channels = 1
+
+    def __init__(self, nb_input=60, field_of_view=56., degrees=True, omm_ori=None, omm_pol_op=1., omm_rho=np.deg2rad(5.4),
+                 omm_res=1., c_sensitive=(0., 0., 0., 0., 1.), **kwargs):
+        if omm_ori is None:
+            omm_ori = dorsal_rim_layout(nb_input, field_of_view, degrees)
+        self.field_of_view = np.deg2rad(field_of_view) if degrees else float(field_of_view)
+        CompoundEye.__init__(self, nb_input=nb_input, omm_ori=omm_ori, omm_rho=omm_rho, omm_res=omm_res,
+                             omm_pol_op=omm_pol_op, c_sensitive=c_sensitive, **kwargs)
+        self.responses = np.zeros((self.nb_ommatidia, 1), dtype=self.dtype)

@@ -148,3 +148,52 @@ def test_familiarity_of_a_small_grid_on_the_gpu(ib):
     # a route view is fully familiar with itself
     assert np.allclose(fam.evaluate(rviews, rviews, whitening=wh).cpu().numpy(), 1.0, atol=1e-3)
     assert fam.familiarity_map(f, 5, 5, 4).shape == (5, 5, 4)
+
+
+def _pol_term(rho, p, a, phi):
+    return rho * (np.sin(a - phi) ** 2 + np.cos(a - phi) ** 2 * (1. - p) ** 2) + (1. - rho)
+
+
+@pytest.mark.parametrize("yaw_only", [True, False])
+def test_polarisation_sensor_and_sky_only_eye_calls(ib, yaw_only):
+    """`pol_sensor(sky=, scene=)` (agent.py:879) and `eye(sky=sky)` (examples/test_sky.py:22): the device's responses
+    against the NumPy statement of the documented photoreceptor model on the oracle's sky (Y, DoP, AoP)"""
+    ths, phs = np.deg2rad(40.), 0.7
+    sky = ib.Sky(ths, phs)
+    ori = R.from_euler('Z', 33., degrees=True) if yaw_only else R.from_euler('ZYX', [33., 6., -4.], degrees=True)
+    # --- dorsal-rim polarisation sensor, sky alone and under a world (Seville: nothing reaches that high)
+    pol = ib.PolarisationSensor(nb_input=60, field_of_view=56, degrees=True, omm_res=0.8)
+    pol.ori = ori
+    pol.xyz = [5., 5., 0.01]
+    r = pol(sky=sky)
+    assert r.shape == (60, 1) and r.dtype == np.float32
+    glob = ori * pol.omm_ori
+    y, p, a = o.sky_render(ths, phs, glob)
+    d = glob.apply([1, 0, 0])
+    phi = np.arctan2(d[:, 1], d[:, 0])
+    want = 0.8 * np.sqrt(y * _pol_term(1.0, p, a, phi))
+    assert np.abs(r[:, 0] - want).max() < 1e-5
+    assert np.abs(pol(sky=sky, scene=ib.Seville2009())[:, 0] - want).max() < 1e-5
+    assert r.std() > 0.01                                      # the filter does modulate the responses
+    # --- a polarisation-sensitive compound eye looking at the sky alone: colour responses times the term
+    eye = ib.CompoundEye(nb_input=400, omm_pol_op=0.6, omm_res=1.2, c_sensitive=[0, 0.3, 1., 0.5, 0])
+    eye.ori = ori
+    r = eye(sky=sky)
+    glob = ori * eye.omm_ori
+    y, p, a = o.sky_render(ths, phs, glob)
+    d = glob.apply([1, 0, 0])
+    phi = np.arctan2(d[:, 1], d[:, 0])
+    yaw_g, pitch_g, _ = glob.as_euler('ZYX').T
+    col = o.luminance2skycolour(y) / 255. * _pol_term(0.6, p, a, phi)[:, None]
+    col[pitch_g >= 0] = np.array(o.GROUND_COLOUR) / 255.      # looking down: the ground colour (world.py:90), no sky light
+    want = np.clip(col * eye.c_sensitive[1:4] * 1.2, 0, 1)
+    assert r.shape == (400, 3) and np.abs(r - want).max() < 1e-5
+    # batches (rows mode under shared headings) give what the single calls give
+    if yaw_only:
+        pos = np.tile([[5., 5., 0.01]], (130, 1))
+        yw = np.tile(np.arange(36) * 10. - 180., (130, 1))
+        pn = eye.render_batch(ib.sense._empty_world(0), sky, pos, yw, channels=1)
+        eye.ori = R.from_euler('Z', yw[0, 7], degrees=True)
+        single = eye(sky=sky)
+        assert np.abs(pn[7] - np.clip(single.mean(axis=1), 0, 1)).max() < 1e-6
+        assert np.abs(pn[36 * 129 + 7] - pn[7]).max() == 0
