@@ -191,6 +191,13 @@ int isy_sky_call_host(const isy_sky_params* sky, double theta_s, double phi_s, c
 int isy_spectrum_influence_host(const double* v_host, int64_t n, const double* irgbu_host, int64_t rows,
                                 int device, double* sum_host, double* channels_host);
 
+/* The same applied to a batch of luminance rows on the device, in place and per view -- what `Sky.__call__(ori, irgbu=...)`
+ * does to the luminance of each call (sky.py:342-344: y = spectrum_influence(y, irgbu).sum(axis=1)) for every view of a
+ * batched render: Y_dev[B][n] (float, or double with ISY_FLAG_OUT_F64), irgbu_dev rows*5 doubles on the device.
+ * One CTA per view: the call-wide nansum / nanmax reductions of sky.py:692-695 become per-view reductions.  Asynchronous. */
+int isy_spectrum_influence_views(void* Y_dev, int64_t B, int64_t n, const double* irgbu_dev, int64_t rows, uint32_t flags,
+                                 int device, void* stream);
+
 /* ---- familiarity of rendered views: the consumer of every view in the reference's heat-map and
  * parallel-lines runs (agent/agent.py:741-744 -> memory -> sim/simulation.py:3085-3092) ------------------------
  * A perfect memory stores M vectors of K values (the PN inputs of the route views, i.e. `resp` with one channel):

@@ -22,7 +22,7 @@ EXPORTS = (
     "isy_eye_create", "isy_eye_destroy", "isy_eye_rays",
     "isy_render_workspace_bytes", "isy_render", "isy_workspace_status", "isy_workspace_phase_cycles",
     "isy_render_host",
-    "isy_world_call_host", "isy_sky_call_host", "isy_spectrum_influence_host",
+    "isy_world_call_host", "isy_sky_call_host", "isy_spectrum_influence_host", "isy_spectrum_influence_views",
     "isy_memory_create", "isy_memory_destroy", "isy_memory_size",
     "isy_familiarity_workspace_bytes", "isy_familiarity", "isy_familiarity_unresolved", "isy_familiarity_candidates",
     "isy_familiarity_host",
@@ -96,6 +96,8 @@ def lib():
     L.isy_world_call_host.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
     L.isy_sky_call_host.argtypes = [ctypes.POINTER(SkyParams), dbl, dbl, vp, i64, vp, ctypes.c_int, vp, vp, vp, vp, vp]
     L.isy_spectrum_influence_host.argtypes = [vp, i64, vp, i64, ctypes.c_int, vp, vp]
+    L.isy_spectrum_influence_views.argtypes = [vp, i64, i64, vp, i64, ctypes.c_uint32, ctypes.c_int, vp]
+    L.isy_spectrum_influence_views.restype = ctypes.c_int
     L.isy_memory_create.argtypes = [vp, i64, i64, ctypes.c_int, ctypes.POINTER(vp)]
     L.isy_memory_destroy.argtypes = [vp]
     L.isy_memory_size.argtypes = [vp]

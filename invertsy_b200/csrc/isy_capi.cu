@@ -980,7 +980,7 @@ int isy_spectrum_influence_host(const double* v_host, int64_t n, const double* i
     CUDA_TRY(d_w.alloc((size_t)rows * 5));
     CUDA_TRY(cudaMemcpy(d_v.p, v_host, (size_t)n * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_w.p, irgbu_host, (size_t)rows * 40, cudaMemcpyHostToDevice));
-    spectrum_kernel<<<1, 1024>>>(d_v.p, n, d_w.p, rows, d_o.p, d_c.p);
+    spectrum_kernel<double><<<1, 1024>>>(d_v.p, n, d_w.p, rows, d_o.p, d_c.p);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     if (sum_host) CUDA_TRY(cudaMemcpy(sum_host, d_o.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
@@ -1180,6 +1180,25 @@ int isy_familiarity_unresolved(const isy_memory* m, int64_t Q, void* workspace_d
                              sizeof n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     *count = n;
+    return ISY_OK;
+}
+
+int isy_spectrum_influence_views(void* Y_dev, int64_t B, int64_t n, const double* irgbu_dev, int64_t rows, uint32_t flags,
+                                 int device, void* stream) {
+    if (!Y_dev || !irgbu_dev || B < 0 || n <= 0 || rows <= 0) return fail(ISY_ERR_INVALID, "isy_spectrum_influence_views: bad argument");
+    if (n % rows) return fail(ISY_ERR_INVALID, "isy_spectrum_influence_views: %lld values cannot be tiled by %lld irgbu rows",
+                              (long long)n, (long long)rows);
+    if (B == 0) return ISY_OK;
+    if (B > 0x7fffffff) return fail(ISY_ERR_INVALID, "isy_spectrum_influence_views: too many views for one call");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(ISY_ERR_CUDA, "isy_spectrum_influence_views: cannot select CUDA device %d (no CPU fallback)", device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (flags & ISY_FLAG_OUT_F64)
+        spectrum_kernel<double><<<(unsigned)B, 256, 0, st>>>((const double*)Y_dev, n, irgbu_dev, rows, (double*)Y_dev, (double*)nullptr);
+    else
+        spectrum_kernel<float><<<(unsigned)B, 256, 0, st>>>((const float*)Y_dev, n, irgbu_dev, rows, (float*)Y_dev, (float*)nullptr);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
     return ISY_OK;
 }
 

@@ -53,12 +53,16 @@ __device__ __forceinline__ double block_reduce(double v, bool is_max, double* sc
     return r;
 }
 
-__global__ void spectrum_kernel(const double* __restrict__ v_all, int64_t n, const double* __restrict__ irgbu,
-                                int64_t rows, double* __restrict__ sum_all, double* __restrict__ chan_all) {
+// T = double: the drop-in call; T = float: the luminance rows of a batched render, one CTA per view, in place
+// (sum_all may alias v_all: every value is read into registers before the view's results are written ... per element,
+// after the three reductions that need all of them).
+template <typename T>
+__global__ void spectrum_kernel(const T* v_all, int64_t n, const double* __restrict__ irgbu,
+                                int64_t rows, T* sum_all, T* chan_all) {
     __shared__ double scratch[32];
-    const double* v = v_all + (size_t)blockIdx.x * n;
-    double* out = sum_all ? sum_all + (size_t)blockIdx.x * n : nullptr;
-    double* chan = chan_all ? chan_all + (size_t)blockIdx.x * n * 5 : nullptr;
+    const T* v = v_all + (size_t)blockIdx.x * n;
+    T* out = sum_all ? sum_all + (size_t)blockIdx.x * n : nullptr;
+    T* chan = chan_all ? chan_all + (size_t)blockIdx.x * n * 5 : nullptr;
     double ssq = 0.0, vmax = CUDART_NAN;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
         double x = v[i];
@@ -91,10 +95,10 @@ __global__ void spectrum_kernel(const double* __restrict__ v_all, int64_t n, con
             double l2 = 0.001 * w[c] * kWl2[c] * ssq / size;
             double val = vm * (x + l1 + l2) / wmax;   // :696
             if (w[c] < 0) val = x;                    // :700
-            if (chan) chan[5 * i + c] = val;
+            if (chan) chan[5 * i + c] = (T)val;
             acc += val;                               // .sum(axis=1)  sky.py:344
         }
-        if (out) out[i] = acc;
+        if (out) out[i] = (T)acc;
     }
 }
 

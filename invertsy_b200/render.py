@@ -141,8 +141,10 @@ class Renderer(object):
         return self._workspace
 
     def render(self, pos, yaw=None, quat=None, sun=None, outputs=("rgb", "Y", "dop", "aop"), init_from_sky=False,
-               brute_force=False, f64=False, out=None, sky=None, per_view_sky=False, sensor=None):
+               brute_force=False, f64=False, out=None, sky=None, per_view_sky=False, sensor=None, irgbu=None):
         """
+        irgbu: (rows, 5) spectral weights: the luminance of every view goes through spectrum_influence(y, irgbu).sum(axis=1)
+        as `Sky.__call__(ori, irgbu=...)` does per call (sky.py:342-344); rows = 1 or a divisor of the ommatidia count.
         per_view_sky: evaluate the sky for every view even when all positions share their headings (cross-check).
         sensor: _lib.SensorParams for the "resp" output -- (B,N,3) photoreceptor responses, or (B,N) PN inputs with
         channels=1 (include/isy_b200.h, isy_sensor_params).
@@ -213,6 +215,12 @@ class Renderer(object):
                                          None if sun_t is None else sun_t.data_ptr(),
                                          ctypes.byref(sp), None if sensor is None else ctypes.byref(sensor), flags,
                                          ctypes.byref(o), ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream)))
+        if irgbu is not None and "Y" in res and "Y" in outputs:
+            w = torch.as_tensor(np.ascontiguousarray(irgbu, dtype=np.float64).reshape(-1, 5), device=dev)
+            _lib.check(_lib.lib().isy_spectrum_influence_views(res["Y"].data_ptr(), B, N, w.data_ptr(), w.shape[0],
+                                                               _lib.FLAG_OUT_F64 if f64 else 0, self.device,
+                                                               ctypes.c_void_p(stream)))
+            sun_t = (sun_t, w)
         # keep the input tensors alive until the stream has consumed them
         self._inflight = (pos, yaw, quat, sun_t)
         return res

@@ -116,3 +116,24 @@ def test_config5_synthetic_stress_slice(ib):
             ref = c_oracle.world_hits(tri, 2.0, pos[p], rp, gy)[0]
             assert (out["hit"][p * 2 + h] != ref).sum() == 0
     assert (out["hit"] >= 0).mean() > 0.05
+
+
+def test_spectrum_influence_per_view_in_batches(ib):
+    """`sky(ori, irgbu=...)` weights the luminance of each call (sky.py:342-344, :671-703); a batched render does the same
+    per view on the device (isy_spectrum_influence_views), float and double outputs, one irgbu row or one per ommatidium"""
+    world = ib.Seville2009()
+    pitch, yaw = o.fibonacci_eye(1000)
+    ths, phs = np.deg2rad(55.), -1.0
+    r = ib.Renderer(world, ib.EyeLayout.from_angles(pitch, yaw), sky=ib.Sky(ths, phs))
+    omm = o.eye_rotations(pitch, yaw)
+    rng = np.random.RandomState(8)
+    pos = np.c_[rng.uniform(2, 8, 5), rng.uniform(2, 8, 5), np.full(5, 0.01)]
+    yw = rng.uniform(-180, 180, (5, 3))
+    for irgbu in (np.array([[0., 0., 1., 0., 0.]]), np.array([[.2, .1, .8, .3, 1.]]), rng.uniform(0, 1, (1000, 5))):
+        a = _np(r, pos=pos, yaw=np.deg2rad(yw), outputs=("Y", "dop"), irgbu=irgbu)
+        b = _np(r, pos=pos, yaw=np.deg2rad(yw), outputs=("Y",), irgbu=irgbu, f64=True)
+        for v in (0, 7, 14):
+            y, p, _ = o.sky_render(ths, phs, o.view_rotations(yw[v // 3, v % 3], omm), irgbu=irgbu)
+            assert np.abs(b["Y"][v] - y).max() < 1e-9 * max(1., np.abs(y).max())
+            assert np.abs(a["Y"][v] - y).max() < 2e-5 * max(1., np.abs(y).max())
+            assert np.abs(a["dop"][v] - p).max() < 1e-5
