@@ -230,6 +230,22 @@ int isy_familiarity_candidates(const isy_memory* m, int64_t Q, void* workspace_d
 int isy_familiarity_host(const isy_memory* m, const float* queries_host, int64_t Q, float* familiarity_host,
                          int32_t* nearest_host);
 
+/* ---- Willshaw-type mushroom-body memory: the default memory of the reference's visual-navigation agent
+ * (agent/agent.py:560-575: #KC = 40 x #PN, sparseness 1 %; the model is InvertPy's WillshawNetwork, not vendored --
+ * this library's definition is stated in csrc/isy_willshaw.cuh and invertsy_b200/familiarity.py) -------------------
+ * nb_kc Kenyon cells each sum fan_in pseudo-randomly chosen PNs; the round(sparseness * nb_kc) cells with the largest
+ * input fire; storing a view clears the output synapses of its firing cells; familiarity = 1 - fraction of the firing
+ * cells whose synapse is still set.  Vectors are device pointers, [.][row_stride] floats, nb_pn used per row.        */
+typedef struct isy_willshaw isy_willshaw;
+int isy_willshaw_create(int64_t nb_pn, int64_t nb_kc, int32_t fan_in, double sparseness, uint32_t seed, int device,
+                        isy_willshaw** out);
+int isy_willshaw_destroy(isy_willshaw* m);
+int isy_willshaw_reset(isy_willshaw* m);                  /* forget everything (all synapses back to 1)             */
+int64_t isy_willshaw_active(const isy_willshaw* m);       /* number of cells that fire per view                     */
+int isy_willshaw_train(isy_willshaw* m, const float* vectors_dev, int64_t M, int64_t row_stride, void* stream);
+int isy_willshaw_familiarity(const isy_willshaw* m, const float* queries_dev, int64_t Q, int64_t row_stride,
+                             float* familiarity_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

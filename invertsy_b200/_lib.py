@@ -26,6 +26,8 @@ EXPORTS = (
     "isy_memory_create", "isy_memory_destroy", "isy_memory_size",
     "isy_familiarity_workspace_bytes", "isy_familiarity", "isy_familiarity_unresolved", "isy_familiarity_candidates",
     "isy_familiarity_host",
+    "isy_willshaw_create", "isy_willshaw_destroy", "isy_willshaw_reset", "isy_willshaw_active", "isy_willshaw_train",
+    "isy_willshaw_familiarity",
 )
 
 
@@ -109,6 +111,16 @@ def lib():
     L.isy_familiarity_unresolved.argtypes = [vp, i64, vp, vp, ctypes.POINTER(i64)]
     L.isy_familiarity_candidates.argtypes = [vp, i64, vp, vp, vp, vp]
     L.isy_familiarity_candidates.restype = ctypes.c_int
+    L.isy_willshaw_create.argtypes = [i64, i64, i32, dbl, ctypes.c_uint32, ctypes.c_int, ctypes.POINTER(vp)]
+    L.isy_willshaw_destroy.argtypes = [vp]
+    L.isy_willshaw_reset.argtypes = [vp]
+    L.isy_willshaw_active.argtypes = [vp]
+    L.isy_willshaw_active.restype = i64
+    L.isy_willshaw_train.argtypes = [vp, vp, i64, i64, vp]
+    L.isy_willshaw_familiarity.argtypes = [vp, vp, i64, i64, vp, vp]
+    for name in ("isy_willshaw_create", "isy_willshaw_destroy", "isy_willshaw_reset", "isy_willshaw_train",
+                 "isy_willshaw_familiarity"):
+        getattr(L, name).restype = ctypes.c_int
     for name in ("isy_memory_create", "isy_memory_destroy", "isy_familiarity", "isy_familiarity_host",
                  "isy_familiarity_unresolved"):
         getattr(L, name).restype = ctypes.c_int

@@ -14,6 +14,7 @@
 
 #include "isy_kernels.cuh"
 #include "isy_fam.cuh"
+#include "isy_willshaw.cuh"
 
 using namespace isy;
 
@@ -1239,6 +1240,96 @@ int isy_familiarity_host(const isy_memory* m, const float* queries_host, int64_t
     if (familiarity_host) CUDA_TRY(cudaMemcpy(familiarity_host, d_f.p, (size_t)Q * sizeof(float), cudaMemcpyDeviceToHost));
     if (nearest_host) CUDA_TRY(cudaMemcpy(nearest_host, d_n.p, (size_t)Q * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return ISY_OK;
+}
+
+}  // extern "C"
+
+
+// ================================================================================================
+// Willshaw memory (isy_willshaw.cuh)
+// ================================================================================================
+struct isy_willshaw {
+    int device;
+    int64_t nb_pn, nb_kc;
+    int32_t fan_in, k;
+    uint32_t seed;
+    unsigned int* d_mask;   // bit j: the KC -> MBON synapse of cell j is still 1
+    size_t smem;
+};
+
+namespace {
+size_t willshaw_smem(int64_t nb_pn, int64_t nb_kc) { return (size_t)((nb_pn + 3) & ~3ll) * 4 + (size_t)nb_kc * 4 + mb::kBins * 4; }
+}  // namespace
+
+extern "C" {
+
+int isy_willshaw_create(int64_t nb_pn, int64_t nb_kc, int32_t fan_in, double sparseness, uint32_t seed, int device,
+                        isy_willshaw** out) {
+    if (!out || nb_pn <= 0 || nb_kc <= 0 || fan_in <= 0 || !(sparseness > 0) || sparseness > 1)
+        return fail(ISY_ERR_INVALID, "isy_willshaw_create: bad argument");
+    if (willshaw_smem(nb_pn, nb_kc) > 220 * 1024)
+        return fail(ISY_ERR_INVALID, "isy_willshaw_create: %lld PNs + %lld KCs do not fit the shared memory of one SM (4 bytes each, 220 KB)",
+                    (long long)nb_pn, (long long)nb_kc);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(ISY_ERR_CUDA, "isy_willshaw_create: cannot select CUDA device %d (no CPU fallback)", device);
+    isy_willshaw* m = new isy_willshaw{device, nb_pn, nb_kc, fan_in, 0, seed, nullptr, willshaw_smem(nb_pn, nb_kc)};
+    m->k = (int32_t)std::max<int64_t>(1, std::min<int64_t>(nb_kc, (int64_t)std::llround(sparseness * (double)nb_kc)));
+    if (cudaMalloc(&m->d_mask, (size_t)((nb_kc + 31) / 32) * 4) != cudaSuccess) {
+        delete m;
+        return fail(ISY_ERR_CUDA, "isy_willshaw_create: out of device memory");
+    }
+    *out = m;
+    return isy_willshaw_reset(m);
+}
+
+int isy_willshaw_destroy(isy_willshaw* m) {
+    if (!m) return ISY_OK;
+    DeviceGuard g(m->device);
+    cudaFree(m->d_mask);
+    delete m;
+    return ISY_OK;
+}
+
+int isy_willshaw_reset(isy_willshaw* m) {
+    if (!m) return fail(ISY_ERR_INVALID, "isy_willshaw_reset: null handle");
+    DeviceGuard g(m->device);
+    CUDA_TRY(cudaMemset(m->d_mask, 0xff, (size_t)((m->nb_kc + 31) / 32) * 4));
+    return ISY_OK;
+}
+
+int64_t isy_willshaw_active(const isy_willshaw* m) { return m ? m->k : -1; }
+
+static int willshaw_launch(const isy_willshaw* m, bool train, const float* views_dev, int64_t Q, int64_t row_stride, float* fam_dev,
+                           void* stream) {
+    if (!m || !views_dev || Q < 0 || row_stride < m->nb_pn || (!train && !fam_dev))
+        return fail(ISY_ERR_INVALID, "isy_willshaw: bad argument");
+    if (Q == 0) return ISY_OK;
+    if (Q > 0x7fffffff) return fail(ISY_ERR_INVALID, "isy_willshaw: too many views for one call");
+    DeviceGuard g(m->device);
+    if (!g.ok) return fail(ISY_ERR_CUDA, "isy_willshaw: cannot select CUDA device %d (no CPU fallback)", m->device);
+    const int grid = (int)std::min<int64_t>(Q, device_sms(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (train) {
+        CUDA_TRY(cudaFuncSetAttribute(mb::willshaw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
+        mb::willshaw_kernel<true><<<grid, mb::kThreads, m->smem, st>>>(views_dev, (long long)row_stride, (int)Q, (int)m->nb_pn, (int)m->nb_kc,
+                                                                       m->fan_in, m->k, m->seed, m->d_mask, nullptr);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(mb::willshaw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
+        mb::willshaw_kernel<false><<<grid, mb::kThreads, m->smem, st>>>(views_dev, (long long)row_stride, (int)Q, (int)m->nb_pn, (int)m->nb_kc,
+                                                                        m->fan_in, m->k, m->seed, m->d_mask, fam_dev);
+    }
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ISY_OK;
+}
+
+int isy_willshaw_train(isy_willshaw* m, const float* vectors_dev, int64_t M, int64_t row_stride, void* stream) {
+    return willshaw_launch(m, true, vectors_dev, M, row_stride, nullptr, stream);
+}
+
+int isy_willshaw_familiarity(const isy_willshaw* m, const float* queries_dev, int64_t Q, int64_t row_stride, float* familiarity_dev,
+                             void* stream) {
+    return willshaw_launch(m, false, queries_dev, Q, row_stride, familiarity_dev, stream);
 }
 
 }  // extern "C"

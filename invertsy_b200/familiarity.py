@@ -188,6 +188,115 @@ class PerfectMemory:
         return (fam, idx) if nearest else fam
 
 
+def _hash32(x):
+    """the "lowbias32" integer hash of csrc/isy_willshaw.cuh, vectorised (uint32 arithmetic)"""
+    x = np.asarray(x, dtype=np.uint32).copy()
+    x ^= x >> np.uint32(16)
+    x *= np.uint32(0x7feb352d)
+    x ^= x >> np.uint32(15)
+    x *= np.uint32(0x846ca68b)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+def willshaw_wiring(nb_pn, nb_kc, fan_in, seed):
+    """(nb_kc, fan_in) PN index of every KC input: umulhi(hash32(j * fan_in + i + seed), nb_pn)"""
+    j = np.arange(nb_kc, dtype=np.uint64)[:, None] * np.uint64(fan_in) + np.arange(fan_in, dtype=np.uint64)[None, :] + np.uint64(seed)
+    h = _hash32((j & np.uint64(0xffffffff)).astype(np.uint32)).astype(np.uint64)
+    return ((h * np.uint64(nb_pn)) >> np.uint64(32)).astype(np.int64)
+
+
+def reference_willshaw(stored, queries, nb_kc, fan_in=8, sparseness=0.01, seed=2021):
+    """
+    NumPy statement of the Willshaw memory (see `WillshawMemory`): returns the familiarity of every query after all
+    `stored` vectors have been learnt.  KC inputs are summed in float32 in input order; the k = round(sparseness * nb_kc)
+    largest fire, ties going to the lower cell index.
+    """
+    stored, queries = np.asarray(stored, dtype=np.float32), np.asarray(queries, dtype=np.float32)
+    wiring = willshaw_wiring(stored.shape[1], nb_kc, fan_in, seed)
+    k = int(max(1, min(nb_kc, round(sparseness * nb_kc))))
+
+    def firing(x):
+        s = np.zeros((x.shape[0], nb_kc), dtype=np.float32)
+        for i in range(fan_in):
+            s = s + x[:, wiring[:, i]]
+        order = np.argsort(-s, axis=1, kind="stable")[:, :k]          # stable: ties keep the lower index first
+        act = np.zeros((x.shape[0], nb_kc), dtype=bool)
+        np.put_along_axis(act, order, True, axis=1)
+        return act
+
+    synapse = ~firing(stored).any(axis=0)                             # cleared by every stored view's firing cells
+    out = np.empty(queries.shape[0])
+    for a in range(0, queries.shape[0], 64):
+        out[a:a + 64] = 1.0 - (firing(queries[a:a + 64]) & synapse[None, :]).sum(axis=1) / k
+    return out
+
+
+class WillshawMemory:
+    """
+    Willshaw-type mushroom body (the default memory of the reference's `VisualNavigationAgent`, agent.py:560-575:
+    "#KC equal to 40 x #PN, sparseness is 1 %"; InvertPy's `WillshawNetwork` is not vendored: **parity unpinned**).
+    Definition (csrc/isy_willshaw.cuh, `reference_willshaw`):
+      * every Kenyon cell sums `fan_in` projection neurons chosen by a fixed integer hash of (cell, input, seed);
+      * the k = round(sparseness * nb_kc) cells with the largest input fire (ties: the lower cell index);
+      * KC -> MBON synapses start at 1; `store` sets the synapses of the firing cells of every stored view to 0;
+      * familiarity(view) = 1 - (firing cells whose synapse is still 1) / k  -- 1 for a stored view, ~0 for a novel one.
+    Runs on the device behind the C ABI (`isy_willshaw_*`); vectors are float32 CUDA tensors.  No CPU fallback.
+    """
+
+    def __init__(self, nb_pn, nb_kc=None, fan_in=8, sparseness=0.01, seed=2021, device=0):
+        self.nb_pn, self.nb_kc = int(nb_pn), int(40 * nb_pn if nb_kc is None else nb_kc)
+        self.fan_in, self.sparseness, self.seed, self.device = int(fan_in), float(sparseness), int(seed), int(device)
+        self._h = None
+
+    def _handle(self):
+        if self._h is None:
+            h = ctypes.c_void_p()
+            _lib.check(_lib.lib().isy_willshaw_create(self.nb_pn, self.nb_kc, self.fan_in, self.sparseness, self.seed,
+                                                      self.device, ctypes.byref(h)))
+            self._h = h
+        return self._h
+
+    def __del__(self):
+        if self._h is not None:
+            try:
+                _lib.lib().isy_willshaw_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+    @property
+    def nb_active(self):
+        return int(_lib.lib().isy_willshaw_active(self._handle()))
+
+    def reset(self):
+        _lib.check(_lib.lib().isy_willshaw_reset(self._handle()))
+        return self
+
+    def _dev(self, v):
+        v = torch.as_tensor(v)
+        v = v.reshape(-1, v.shape[-1]).to(device="cuda:%d" % self.device, dtype=torch.float32).contiguous()
+        if v.shape[1] != self.nb_pn:
+            raise ValueError("vectors have %d values, the memory %d projection neurons" % (v.shape[1], self.nb_pn))
+        return v
+
+    def store(self, vectors):
+        v = self._dev(vectors)
+        stream = torch.cuda.current_stream(v.device).cuda_stream
+        _lib.check(_lib.lib().isy_willshaw_train(self._handle(), v.data_ptr(), v.shape[0], v.stride(0), ctypes.c_void_p(stream)))
+        self._inflight = v
+        return self
+
+    def familiarity(self, queries, out=None):
+        q = self._dev(queries)
+        fam = out if out is not None else torch.empty(q.shape[0], dtype=torch.float32, device=q.device)
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        _lib.check(_lib.lib().isy_willshaw_familiarity(self._handle(), q.data_ptr(), q.shape[0], q.stride(0), fam.data_ptr(),
+                                                       ctypes.c_void_p(stream)))
+        self._inflight = q
+        return fam
+
+
 def evaluate(views, route_views, whitening=None, memory=None, device=0):
     """
     views (V, N[, C]) and route_views (L, N[, C]): ommatidia responses (or PN vectors when 2-D) of the second phase and

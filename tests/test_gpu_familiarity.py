@@ -112,3 +112,23 @@ def test_duplicate_stored_vectors_are_kept_once_and_ties_go_to_the_lowest_index(
     mem.familiarity(torch.as_tensor(q).cuda())
     torch.cuda.synchronize()
     assert mem.unresolved() == 0
+
+
+@pytest.mark.parametrize("nb_pn,nb_kc,fan_in,sparse", [(1000, 40000, 8, 0.01), (64, 2000, 5, 0.05), (300, 4099, 3, 0.001)])
+def test_willshaw_memory_matches_its_numpy_statement(fam, nb_pn, nb_kc, fan_in, sparse):
+    rng = np.random.RandomState(nb_kc)
+    stored = rng.uniform(0, 1, (60, nb_pn)).astype(np.float32)
+    queries = rng.uniform(0, 1, (90, nb_pn)).astype(np.float32)
+    queries[:20] = stored[:20]                                        # learnt views: familiarity exactly 1
+    queries[20:40] = np.clip(stored[20:40] + rng.normal(0, 0.02, (20, nb_pn)), 0, 1)   # near a learnt view
+    queries[40:50] = np.round(queries[40:50] * 4) / 4                 # coarse values: many tied KC inputs
+    mem = fam.WillshawMemory(nb_pn, nb_kc, fan_in=fan_in, sparseness=sparse, seed=7).store(stored)
+    got = mem.familiarity(queries).cpu().numpy()
+    ref = fam.reference_willshaw(stored, queries, nb_kc, fan_in, sparse, seed=7)
+    assert mem.nb_active == max(1, round(sparse * nb_kc))
+    assert np.abs(got - ref).max() < 1e-6, np.abs(got - ref).max()
+    assert np.all(got[:20] == 1.0) and got[50:].mean() < got[20:40].mean() < 1.0
+    # storing in two calls is the same as in one; reset forgets
+    two = fam.WillshawMemory(nb_pn, nb_kc, fan_in=fan_in, sparseness=sparse, seed=7).store(stored[:25]).store(stored[25:])
+    assert np.array_equal(two.familiarity(queries).cpu().numpy(), got)
+    assert np.all(mem.reset().familiarity(queries[:5]).cpu().numpy() == 0.0)

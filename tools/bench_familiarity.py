@@ -34,3 +34,15 @@ ms = float(np.median([s.elapsed_time(e) for s, e in ev]))
 flop = 2.0 * a.Q * a.M * a.K
 print(json.dumps({"Q": a.Q, "M": a.M, "K": a.K, "ms": ms, "tflops_tf32": flop / ms / 1e9,
                   "queries_per_s": a.Q / ms * 1e3, "query_bytes_GBps": a.Q * a.K * 4 * 2 / ms / 1e6}))
+wm = fam.WillshawMemory(a.K, 40 * a.K).store(m)
+Qw = min(a.Q, 148 * 64)
+for _ in range(2):
+    wm.familiarity(q[:Qw], out=out[:Qw])
+torch.cuda.synchronize()
+s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+s.record()
+wm.familiarity(q[:Qw], out=out[:Qw])
+e.record()
+torch.cuda.synchronize()
+print(json.dumps({"willshaw": {"views": Qw, "nb_pn": a.K, "nb_kc": 40 * a.K, "ms": s.elapsed_time(e),
+                               "views_per_s": Qw / s.elapsed_time(e) * 1e3}}))
