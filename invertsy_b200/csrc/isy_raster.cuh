@@ -348,7 +348,10 @@ __device__ __forceinline__ void raster_row(const RenderParams& rp, SmemLayout& s
 template <bool kSmem>
 __device__ __forceinline__ void raster_rows_flat(const RenderParams& rp, SmemLayout& sm, unsigned int* gbest,
                                                  const Exact* exacts, int r0, int nrows, int c0, int ncols, int ub0, int ustep,
-                                                 const Entry& ent, double dist, int e, int hh, int hs, float hf) {
+                                                 const Entry& ent, double dist, int e, int hh, int hs, float hf, int seg = 0,
+                                                 int nseg = 1) {
+    // seg / nseg: this caller takes the seg-th of nseg equal parts of every unit's list range (a pair shared by the
+    // whole CTA: every warp gets a slice of every row, whatever the number of rows)
     const int lane = threadIdx.x & 31, Gy = rp.cells_cols;
     const int n1 = min(ncols, Gy - c0);            // columns before the wrap
     const bool wraps = n1 < ncols;
@@ -362,6 +365,11 @@ __device__ __forceinline__ void raster_rows_flat(const RenderParams& rp, SmemLay
             const int cell = row * Gy + (second ? 0 : c0), n = second ? ncols - n1 : n1;
             a0 = kSmem ? sm.ras.cell_start[cell] : __ldg(rp.cells_start + cell);
             a1 = kSmem ? sm.ras.cell_start[cell + n] : __ldg(rp.cells_start + cell + n);
+            if (nseg > 1) {
+                const unsigned full = a1 - a0;
+                a1 = a0 + (unsigned)(((unsigned long long)full * (unsigned)(seg + 1)) / (unsigned)nseg);
+                a0 = a0 + (unsigned)(((unsigned long long)full * (unsigned)seg) / (unsigned)nseg);
+            }
         }
         const unsigned len = a1 - a0;
         unsigned inc = len;
@@ -420,9 +428,15 @@ __device__ void raster_cells(const RenderParams& rp, SmemLayout& sm, unsigned in
     const int items = E * Hcur;
     constexpr int kBigItem = 12;      // cells: above this the warp shares the pair
     constexpr int kGiantItem = 1024;  // cells: above this the CTA shares the pair
+    // Large eyes (tables in global memory, hundreds of rays under an ordinary copy): nearly every pair is "large", and a
+    // warp that walked the 32 it classified one after the other would leave the others idle.  They are queued instead
+    // (sm.jrange is free outside the band walk) and pulled one at a time by whichever warp is free.
+    constexpr bool kQueue = !kSmem;
     unsigned short* giants = sm.giants;
     int* n_giant = &sm.n_giants;
-    if (threadIdx.x == 0) *n_giant = 0;
+    int* n_queued = &sm.order_n[1];
+    unsigned int* queue = sm.jrange;
+    if (threadIdx.x == 0) *n_giant = 0, *n_queued = 0;
     __syncthreads();
     for (;;) {
         int base = 0;
@@ -439,6 +453,10 @@ __device__ void raster_cells(const RenderParams& rp, SmemLayout& sm, unsigned in
         if (ncell > kGiantItem && item < 65536) {      // set aside (if the list is full the warp keeps it)
             const int slot = smem_atomic_add(n_giant, 1);
             if (slot < kMaxGiants) giants[slot] = (unsigned short)item, ncell = 0;
+        }
+        if (kQueue && ncell > kBigItem) {
+            const int slot = smem_atomic_add(n_queued, 1);
+            if (slot < kMaxE) queue[slot] = (unsigned int)item, ncell = 0;
         }
         // small pairs: one lane each
         if (ncell > 0 && ncell <= kBigItem) {
@@ -467,7 +485,27 @@ __device__ void raster_cells(const RenderParams& rp, SmemLayout& sm, unsigned in
         __syncwarp();
     }
     __syncthreads();
-    // giants: batches of 32 rows dealt to the warps
+    if (kQueue) {   // the queued pairs, one at a time per warp
+        if (threadIdx.x == 0) *s_next = 0;
+        __syncthreads();
+        const int nq = min(*n_queued, kMaxE);
+        for (;;) {
+            int i = 0;
+            if (lane == 0) i = smem_atomic_add(s_next, 1);
+            i = __shfl_sync(0xffffffffu, i, 0);
+            if (i >= nq) break;
+            const int item = (int)queue[i];
+            const int e = item / Hcur, hh = item - e * Hcur;
+            int r0, nrows, c0, ncols;
+            pair_window(rp, sm, e, hh, r0, nrows, c0, ncols);
+            const Entry ent = sm.tile[e];
+            const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
+            raster_rows_flat<kSmem>(rp, sm, gbest, exacts, r0, nrows, c0, ncols, 0, 32, ent, dist, e, hh, sm.ras.hinv[hh],
+                                    (float)sm.head_val[hh]);
+            __syncwarp();
+        }
+    }
+    // giants: every warp takes its slice of every row
     const int ng = min(*n_giant, kMaxGiants);
     for (int g = 0; g < ng; ++g) {
         const int item = giants[g];
@@ -478,7 +516,7 @@ __device__ void raster_cells(const RenderParams& rp, SmemLayout& sm, unsigned in
         const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
         const float hf = (float)sm.head_val[hh];
         const int hs = sm.ras.hinv[hh];
-        raster_rows_flat<kSmem>(rp, sm, gbest, exacts, r0, nrows, c0, ncols, 32 * warp, 32 * kWarps, ent, dist, e, hh, hs, hf);
+        raster_rows_flat<kSmem>(rp, sm, gbest, exacts, r0, nrows, c0, ncols, 0, 32, ent, dist, e, hh, hs, hf, warp, kWarps);
     }
 }
 
