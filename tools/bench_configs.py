@@ -137,6 +137,8 @@ def config5(nviews):
     out = {}
     ms = timed(lambda: r.render(pos, yw, outputs=("rgb", "Y", "dop", "aop"), out=out), 3)
     r.check()
+    pc = r.phase_cycles().astype(float)
+    print("config5 cycles per position: project %.0f accel %.0f final %.0f" % tuple(pc[:3] / max(pc[3], 1)), file=sys.stderr)
     return {"views_timed": B, "rays_per_view": N * S, "triangles": T, "ms": ms, "views_per_s": B / ms * 1e3,
             "rays_per_s": B * N * S / ms * 1e3, "seconds_for_1M_views_one_gpu": 1e6 / (B / ms * 1e3)}
 
