@@ -330,6 +330,7 @@ namespace {
 struct Plan {
     int grid;
     int splits;
+    int ray_splits;   // what a general-orientation call may use (the slabs are sized for it)
     int Hg, ngroups;
     int slab_cap;
     bool global_best;
@@ -375,6 +376,12 @@ Plan make_plan(const isy_world* w, const isy_eye* e, int64_t P, int64_t H) {
     pl.ngroups = (int)((H + pl.Hg - 1) / pl.Hg);
     pl.splits = (int)std::max<int64_t>(1, std::min<int64_t>(splits, pl.ngroups));
     int64_t items = P * pl.splits;
+    // explicit rays / general orientations, fewer work items than SMs, many rays: up to 16 CTAs share the rays of one
+    // item (at least 128 blocks of 32 rays each); every one of them needs its own slab
+    pl.ray_splits = 1;
+    if (items < max_ctas / 2 && e->R >= 8192)
+        pl.ray_splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, max_ctas / std::max<int64_t>(items, 1)), e->R / 4096));
+    items *= pl.ray_splits;
     pl.grid = (int)std::max<int64_t>(1, std::min<int64_t>(items, max_ctas));
     pl.slab_cap = (int)std::min<int64_t>(2 * std::max<int64_t>(w->T, 1), 1 << 17);
     size_t off = 0;
@@ -451,7 +458,9 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
     rp.slab_entry = (Entry*)(base + pl.off_entry);
     rp.slab_exact = (Exact*)(base + pl.off_exact);
     rp.slab_best = pl.global_best ? (unsigned int*)(base + pl.off_best) : nullptr;
-    rp.slab_cap = pl.slab_cap, rp.splits = pl.splits, rp.items = (int)(P * pl.splits);
+    const bool any_eye = vquat || !e->d_sorted;     // (the only kernel whose final pass can share a view's rays)
+    rp.ray_splits = any_eye ? pl.ray_splits : 1;
+    rp.slab_cap = pl.slab_cap, rp.splits = pl.splits, rp.items = (int)(P * pl.splits * rp.ray_splits);
     rp.Hg = pl.Hg, rp.ngroups = pl.ngroups;
     {   // The fast final pass deals (block of 32 rays) x (chunk of headings) units to the warps round-robin; it is
         // throughput-bound, so pick the chunking whose busiest warp has the least to do (ties: the coarsest, which
@@ -560,7 +569,7 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
 #define ISY_LAUNCH(F64, EYE)                                                                                              \
     do {                                                                                                                  \
         CUDA_TRY(cudaFuncSetAttribute(render_kernel<F64, EYE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        render_kernel<F64, EYE><<<pl.grid, kThreads, smem, st>>>(rp);                                                     \
+        render_kernel<F64, EYE><<<std::min(pl.grid, std::max(rp.items, 1)), kThreads, smem, st>>>(rp);                                                     \
     } while (0)
     if (f64) {
         if (eye_kind == kEyeAny) ISY_LAUNCH(true, kEyeAny);

@@ -127,7 +127,8 @@ struct RenderParams {
     int Hg, ngroups;         // headings per group, number of groups (H = sum of group sizes)
     int shade_nch;           // fast final pass: heading chunks per ray block (chosen by the host so that the warps finish together)
     int splits;              // CTAs sharing one position (each redoes the cull, takes every splits-th group)
-    int items;               // P * splits
+    int ray_splits;          // general-orientation eyes, few positions: CTAs sharing the rays of one (position, group)
+    int items;               // P * splits * ray_splits
 };
 
 // ---- photoreceptor transform behind out.resp (isy_sensor_params in isy_b200.h) ----

@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
         const unsigned item = s_item;
         if (item >= (unsigned)rp.items) break;
         if (tid == 0) pulled = atomicAdd(rp.queue, 1u);
-        const int p = item / rp.splits, split = item % rp.splits;
+        const int per_pos = rp.splits * rp.ray_splits;
+        const int p = item / per_pos, split = (item % per_pos) / rp.ray_splits, rsplit = item % rp.ray_splits;
         // was this item culled while the previous one was rasterised?
         const CullScratch* const ahead = (ahead_stage && s_ahead_item == item) ? &s_cull_ahead : nullptr;
         long long t0 = clock64();
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                         const unsigned int nxt = s_item_next;
                         if (nxt < (unsigned)rp.items) {
                             const int gt = tid - (kWarps - kCopyWarps) * 32;
-                            cull_position<kCopyWarps * 32, 1>(rp, (int)(nxt / rp.splits), gt, vis, ahead_stage, rp.stage_cap,
+                            cull_position<kCopyWarps * 32, 1>(rp, (int)(nxt / (rp.splits * rp.ray_splits)), gt, vis, ahead_stage, rp.stage_cap,
                                                               s_cull_ahead);
                             if (gt == 0) s_ahead_item = nxt;
                         }
@@ -238,12 +239,16 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
             }
             // ---- generic final pass: warp units = (block of 32 consecutive rays) x (chunk of headings);
             //      the eye data of a ray are loaded once per unit and reused for its headings
-            const int nb = (r_n + 31) >> 5;
-            int nch = min(Hcur, max(1, (2 * kWarps + nb - 1) / nb));
+            // (a single view of very many explicit rays -- world(pos, ori) with 1e5 directions -- is shared by ray_splits
+            // CTAs: each takes a contiguous share of the 32-ray blocks, whole ommatidia)
+            const int nb_all = (r_n + 31) >> 5;
+            const int rb0 = (int)(((long long)nb_all * rsplit) / rp.ray_splits), rb1 = (int)(((long long)nb_all * (rsplit + 1)) / rp.ray_splits);
+            const int nb = rb1 - rb0;
+            int nch = min(Hcur, max(1, (2 * kWarps + max(nb, 1) - 1) / max(nb, 1)));
             const int hper = (Hcur + nch - 1) / nch;
             nch = (Hcur + hper - 1) / hper;
             for (int u = warp; u < nb * nch; u += kWarps) {
-                const int rb = u / nch, hc = u - rb * nch;
+                const int rb = rb0 + u / nch, hc = u - (u / nch) * nch;
                 const int r = r_lo + rb * 32 + lane;
                 const bool valid = r < r_lo + r_n;
                 const int rr = valid ? r : r_lo + r_n - 1;
