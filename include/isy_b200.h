@@ -120,6 +120,9 @@ int isy_abi_version(void);
 const char* isy_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
 int64_t isy_launch_count(void);
+/* Bounds-checked builds (-DISY_DEBUG_BOUNDS, tools/debug_bounds.py): synchronises `device` and returns how many of the
+ * kernels' own index asserts have failed since load (*first_line = source line of the first); -1 in a release build. */
+int64_t isy_debug_bounds_violations(int device, int32_t* first_line);
 
 /* ---- world: WorldBase.__init__ / .polygons / .colours / .horizon  (world.py:48-53, 131-163) ---
  * tri_xyz: T*9 floats [t][vertex][x,y,z] (host) ; tri_rgb: T*3 floats (host) ; both copied.     */

@@ -17,7 +17,7 @@ FLAG_INIT_FROM_SKY, FLAG_BRUTE_FORCE, FLAG_SUN_PER_VIEW, FLAG_OUT_F64, FLAG_PER_
 
 # every symbol include/isy_b200.h declares (tests check that the library exports all of them)
 EXPORTS = (
-    "isy_abi_version", "isy_last_error", "isy_launch_count",
+    "isy_abi_version", "isy_last_error", "isy_launch_count", "isy_debug_bounds_violations",
     "isy_world_create", "isy_world_destroy", "isy_world_triangles",
     "isy_eye_create", "isy_eye_destroy", "isy_eye_rays",
     "isy_render_workspace_bytes", "isy_render", "isy_workspace_status", "isy_workspace_phase_cycles",
@@ -78,6 +78,8 @@ def lib():
     L.isy_abi_version.restype = ctypes.c_int
     L.isy_last_error.restype = ctypes.c_char_p
     L.isy_launch_count.restype = i64
+    L.isy_debug_bounds_violations.argtypes = [ctypes.c_int, ctypes.POINTER(i32)]
+    L.isy_debug_bounds_violations.restype = i64
     L.isy_world_create.argtypes = [vp, vp, i64, dbl, ctypes.c_int, ctypes.POINTER(vp)]
     L.isy_world_destroy.argtypes = [vp]
     L.isy_world_triangles.argtypes = [vp]

@@ -97,6 +97,22 @@ int isy_abi_version(void) { return ISY_ABI_VERSION; }
 const char* isy_last_error(void) { return g_err.c_str(); }
 int64_t isy_launch_count(void) { return g_launches.load(); }
 
+int64_t isy_debug_bounds_violations(int device, int32_t* first_line) {
+#ifdef ISY_DEBUG_BOUNDS
+    DeviceGuard g(device);
+    unsigned int n = 0, line = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+    if (cudaMemcpyFromSymbol(&n, g_isy_bounds_violations, sizeof n) != cudaSuccess) return -2;
+    cudaMemcpyFromSymbol(&line, g_isy_bounds_first_line, sizeof line);
+    if (first_line) *first_line = (int32_t)line;
+    return (int64_t)n;
+#else
+    (void)device;
+    if (first_line) *first_line = 0;
+    return -1;      // not a bounds-checked build
+#endif
+}
+
 static int world_fill(isy_world* w, const float* tri_xyz, const float* tri_rgb, int64_t T, double horizon);
 
 int isy_world_create(const float* tri_xyz, const float* tri_rgb, int64_t T, double horizon, int device,

@@ -7,6 +7,25 @@
 
 #include "../../include/isy_b200.h"
 
+// ------------------------------------------------------------------------------------------
+// Bounds-checked build (-DISY_DEBUG_BOUNDS; `python tools/debug_bounds.py` builds it next to the product library and
+// runs GPU tests through it): compute-sanitizer is not available on the B200 pool, so the indexed shared-memory and
+// output accesses of the kernels carry their own asserts.  A violated bound is counted (isy_debug_bounds_violations)
+// and the access is skipped by the caller where that is possible; the release build compiles the checks away.
+// ------------------------------------------------------------------------------------------
+#ifdef ISY_DEBUG_BOUNDS
+__device__ unsigned int g_isy_bounds_violations = 0;
+__device__ unsigned int g_isy_bounds_first_line = 0;
+#define ISY_BOUND(cond)                                                  \
+    do {                                                                 \
+        if (!(cond)) {                                                   \
+            if (atomicAdd(&g_isy_bounds_violations, 1u) == 0) g_isy_bounds_first_line = __LINE__; \
+        }                                                                \
+    } while (0)
+#else
+#define ISY_BOUND(cond) do { } while (0)
+#endif
+
 namespace isy {
 
 constexpr double kPi = 3.141592653589793238462643383279502884;

@@ -25,6 +25,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "isy_common.cuh"
+
 namespace isy {
 namespace fam {
 
@@ -235,6 +237,7 @@ fam_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             const int q = tile * kBM + (warp & 3) * 32 + lane;
             if (q < Q) {
+                ISY_BOUND(top.i[0] < M && top.i[1] < M && top.i[2] < M && top.i[3] < M && top.i[0] >= 0);
                 cand[q] = make_int4(top.i[0], top.i[1], top.i[2], top.i[3]);
                 score[q] = make_float4(top.v[0], top.v[1], top.v[2], top.v[3]);
             }

@@ -39,6 +39,7 @@ __device__ __forceinline__ void emit_copy(const double th[3], const double ph[3]
     Entry e;
     finish_copy(th, ph, dist, t, e, exacts[slot]);
     if (slot >= kMaxE) entries[slot] = e;   // the slab only takes what the shared-memory tile cannot hold
+    ISY_BOUND(slot >= 0);
     if (slot < kMaxE) {
         sm.tile[slot] = e;
         float tlo = (float)fmin(th[0], fmin(th[1], th[2])) - kBinMargin;

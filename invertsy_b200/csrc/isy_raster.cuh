@@ -48,6 +48,7 @@ __device__ __forceinline__ bool nearer(const Entry* tile, double d, int tri, uns
 // arithmetic to two instructions (a generic pointer makes the compiler rebuild the window base every time).
 __device__ __forceinline__ void post_copy_u16(unsigned int best_s, unsigned int idx, const Entry* tile, double d, int tri,
                                               unsigned int e) {
+    ISY_BOUND(idx < (unsigned)kBestCap && e < (unsigned)kMaxE);
     const unsigned int addr = best_s + ((idx >> 1) << 2);
     const bool hi = idx & 1u;
     unsigned int old;
@@ -131,6 +132,7 @@ __device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& s
     for (int u = 0; u < RU; ++u) {
         const unsigned j = jb + u * 32 + lane;
         py[u] = make_float2(4.f, 0.f);                  // pitch 4 rad: outside every band
+        ISY_BOUND(jend <= (unsigned)kGridRaysSmem);
         if (j < jend) py[u] = sm.ras.sorted[j];
     }
 #pragma unroll
@@ -242,7 +244,9 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, const Exac
         e = __shfl_sync(0xffffffffu, e, 0);
         if (e >= E) break;
         last = e >= stop_after;
+        ISY_BOUND(e < kMaxE && ntall <= E);
         e = sm.order[e < ntall ? e : kMaxE - 1 - (e - ntall)];   // tall copies first: no long straggler at the end
+        ISY_BOUND(e < E);
         // run of pitch-sorted rays that covers the copy's pitch range (a few extra rays at both ends),
         // worked out when the copy was projected (small eyes) or when the band was loaded
         const unsigned int jr = sm.jrange[e];
@@ -294,7 +298,9 @@ __device__ __forceinline__ void raster_list(const RenderParams& rp, SmemLayout& 
     const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
     const unsigned int best_s = (unsigned int)__cvta_generic_to_shared(sm.ras.best);
     for (unsigned i = i0 + first; i < i1; i += step) {
+        ISY_BOUND(i < (unsigned)R && (!kSmem || i < (unsigned)kGridRaysSmem));
         const unsigned j = kSmem ? (unsigned)sm.ras.cell_list[i] : __ldg(rp.cells_list + i);
+        ISY_BOUND(j < (unsigned)R);
         const float2 py = kSmem ? sm.ras.sorted[j] : __ldg(gsorted + j);
         float fy = py.y + hf;                                  // both in (-pi, pi]: one shift wraps
         fy = fy > pi_f ? fy - twopi_f : (fy <= -pi_f ? fy + twopi_f : fy);

@@ -80,7 +80,9 @@ __device__ void final_pass_fast(const RenderParams& rp, SmemLayout& sm, const un
                 const int hh = min(hh0 + q, hend - 1);
                 view[q] = (size_t)p * rp.H + grp + (size_t)hh * rp.ngroups;   // group = every ngroups-th heading
                 const int hs = sm.ras.hinv[hh];
+                ISY_BOUND(pos >= 0 && pos < Rrow && hs < Hcur && (!kSmem || hs * Rrow + pos < kBestCap));
                 id[q] = kSmem ? (unsigned)sm.ras.best[hs * Rrow + pos] : gbest[(size_t)hs * R + pos];
+                ISY_BOUND(id[q] == kNoCopy || id[q] < (unsigned)kMaxE);
                 if (perez) {
                     const double hsn = sm.head_sin[hh], hcs = sm.head_cos[hh];
                     const double sy = t4v.z * hcs + t4v.w * hsn, cy = t4v.w * hcs - t4v.z * hsn;   // yaw_e + heading
@@ -306,6 +308,7 @@ __device__ void copy_rows(const RenderParams& rp, int p, int grp, int Hcur, int 
         if (!dst || e >= len) continue;
         const T v = __ldg(src + e);
         T* d = dst + view0 * (size_t)len + e;
+        ISY_BOUND((view0 + (size_t)(Hcur - 1) * vstride) * (size_t)len + e < (size_t)rp.P * rp.H * (size_t)len);
         if (stream) {
             for (int hh = 0; hh < Hcur; ++hh, d += vstride * (size_t)len) __stcs(d, v);
         } else {
@@ -334,10 +337,12 @@ __device__ void final_pass_patch(const RenderParams& rp, SmemLayout& sm, int p, 
 #endif
         // row = idx / R: exact in float for idx < 2^16 ((idx + 0.5) / R is at least 0.5 / R from an integer)
         const int hs = (int)(((float)idx + 0.5f) * inv_R), pos = idx - hs * R;
+        ISY_BOUND(hs < Hcur && pos < R && id < (unsigned)kMaxE);
         const int hh = sm.ras.hperm[hs];
         const int ray = sm.sorted_ray16[pos];
         const Entry& e = sm.tile[id];
         const size_t i = (view0 + (size_t)hh * rp.ngroups) * (size_t)R + (size_t)ray;
+        ISY_BOUND(hh < Hcur && ray < R && i < (size_t)rp.P * rp.H * (size_t)R);
         if (rp.out.hit) __stcs(rp.out.hit + i, e.tri);
         if (o_depth) __stcs(o_depth + i, (float)__hiloint2double(e.dist_hi, e.dist_lo));
         if (o_rgb) {

@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "isy_common.cuh"
+
 namespace isy {
 namespace mb {
 
@@ -78,7 +80,10 @@ willshaw_kernel(const float* __restrict__ views, long long ld, int Q, int nb_pn,
         for (int j = tid; j < nb_kc; j += kThreads) {
             float s = 0.f;
             uint32_t h = (uint32_t)j * (uint32_t)fan_in + seed;
-            for (int i = 0; i < fan_in; ++i) s += pn[__umulhi(hash32(h + (uint32_t)i), (uint32_t)nb_pn)];
+            for (int i = 0; i < fan_in; ++i) {
+                ISY_BOUND(__umulhi(hash32(h + (uint32_t)i), (uint32_t)nb_pn) < (uint32_t)nb_pn);
+                s += pn[__umulhi(hash32(h + (uint32_t)i), (uint32_t)nb_pn)];
+            }
             key[j] = float_key(s);
         }
         // radix select of the k-th largest key: 11, 11, 10 bits from the top
@@ -111,6 +116,7 @@ willshaw_kernel(const float* __restrict__ views, long long ld, int Q, int nb_pn,
                     unsigned int run = before;
                     for (int i = 0; i < per; ++i) {
                         const int b = kBins - 1 - (tid * per + i);
+                        ISY_BOUND(b >= 0 && b < kBins);
                         if (run + hist[b] >= want) {
                             s_prefix = (uint32_t)b, s_want = want - run;
                             break;

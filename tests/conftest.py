@@ -47,3 +47,17 @@ def circ_diff(a, b):
     d = np.abs((np.asarray(a) - np.asarray(b) + np.pi) % (2 * np.pi) - np.pi)
     both_nan = np.isnan(a) & np.isnan(b)
     return np.where(both_nan, 0., d)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """bounds-checked builds (tools/debug_bounds.py): report the kernels' own assert count, fail the session if any fired"""
+    if os.environ.get("ISY_REPORT_BOUNDS") != "1":
+        return
+    import ctypes
+    from invertsy_b200 import _lib
+    line = ctypes.c_int32(0)
+    n = int(_lib.lib().isy_debug_bounds_violations(0, ctypes.byref(line)))
+    print("\n[isy bounds] violations: %d%s" % (n, (" (first at csrc line %d)" % line.value) if n > 0 else
+                                               (" -- NOT a bounds-checked build" if n == -1 else (" -- no CUDA device" if n < 0 else ""))))
+    if n != 0:
+        session.exitstatus = 3
