@@ -1164,9 +1164,9 @@ size_t isy_familiarity_workspace_bytes(const isy_memory* m, int64_t Q) {
 
 int isy_familiarity(const isy_memory* m, const float* queries_dev, int64_t Q, int64_t row_stride, float* familiarity_dev,
                     int32_t* nearest_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (m && Q == 0) return ISY_OK;      // empty input (the reference's loops simply do not run)
     if (!m || !queries_dev || Q < 0 || (!familiarity_dev && !nearest_dev))
         return fail(ISY_ERR_INVALID, "isy_familiarity: bad argument");
-    if (Q == 0) return ISY_OK;
     if (Q >= (1ll << 31) - fam::kBM) return fail(ISY_ERR_INVALID, "isy_familiarity: too many queries for one call");
     if (row_stride < m->K || (row_stride & 3) || ((uintptr_t)queries_dev & 15))
         return fail(ISY_ERR_INVALID, "isy_familiarity: queries must be 16-byte aligned with a row stride that is a multiple of 4 floats and at least K");
@@ -1326,9 +1326,9 @@ int64_t isy_willshaw_active(const isy_willshaw* m) { return m ? m->k : -1; }
 
 static int willshaw_launch(const isy_willshaw* m, bool train, const float* views_dev, int64_t Q, int64_t row_stride, float* fam_dev,
                            void* stream) {
+    if (m && Q == 0) return ISY_OK;
     if (!m || !views_dev || Q < 0 || row_stride < m->nb_pn || (!train && !fam_dev))
         return fail(ISY_ERR_INVALID, "isy_willshaw: bad argument");
-    if (Q == 0) return ISY_OK;
     if (Q > 0x7fffffff) return fail(ISY_ERR_INVALID, "isy_willshaw: too many views for one call");
     DeviceGuard g(m->device);
     if (!g.ok) return fail(ISY_ERR_CUDA, "isy_willshaw: cannot select CUDA device %d (no CPU fallback)", m->device);

@@ -132,3 +132,43 @@ def test_willshaw_memory_matches_its_numpy_statement(fam, nb_pn, nb_kc, fan_in, 
     two = fam.WillshawMemory(nb_pn, nb_kc, fan_in=fan_in, sparseness=sparse, seed=7).store(stored[:25]).store(stored[25:])
     assert np.array_equal(two.familiarity(queries).cpu().numpy(), got)
     assert np.all(mem.reset().familiarity(queries[:5]).cpu().numpy() == 0.0)
+
+
+def test_heat_map_call_single_gpu(fam):
+    """`familiarity.HeatMap` (the call bench.py times as e2e): host poses in -> render -> perfect memory -> map out, against
+    the float64 statement on the rendered responses; one process = the whole grid, no collective"""
+    import invertsy_b200 as ib
+    from invertsy_b200 import _lib
+    world = ib.Seville2009()
+    pitch, yaw = ib.fibonacci_lattice(1000)
+    r = ib.Renderer(world, ib.EyeLayout.from_angles(pitch, yaw), sky=ib.Sky(np.deg2rad(60.), np.pi))
+    sensor = _lib.SensorParams.make((0., 1., 0.), 1., 1)
+    route = ib.Seville2009.load_routes(degrees=True)["path"][0][::5]
+    stored = r.render(route[:, :3], np.deg2rad(route[:, 3:4]), outputs=("resp",), sensor=sensor)["resp"]
+    memory = fam.PerfectMemory().store(stored)
+    pos, yaw_deg = ib.views.grid_views(12, 11, 36)                 # 132 positions x 36 headings: rows mode
+    hm = fam.HeatMap(r, memory, sensor, nb_positions=len(pos), nb_headings=36)
+    mine = hm.positions()
+    assert np.array_equal(mine, np.arange(len(pos)))
+    out = hm(pos[mine], np.deg2rad(yaw_deg[mine]))
+    assert out.shape == (len(pos) * 36,) and out.is_pinned()
+    views = hm.views["resp"].cpu().numpy()
+    ref, _ = fam.reference_familiarity(views, stored.cpu().numpy())
+    assert np.abs(out.numpy() - ref).max() < TOL
+    # the views it rendered are the per-view renders
+    single = r.render(pos[5:6], np.deg2rad(yaw_deg[5:6]), outputs=("resp",), sensor=sensor, per_view_sky=True)["resp"].cpu().numpy()
+    assert np.abs(views[5 * 36:6 * 36] - single).max() < 1e-6
+    assert fam.familiarity_map(out, 12, 11, 36).shape == (12, 11, 36)
+
+
+def test_bad_arguments_are_refused(fam):
+    from invertsy_b200 import _lib
+    mem = fam.PerfectMemory().store(np.zeros((3, 8), dtype=np.float32))
+    with pytest.raises(ValueError):
+        mem.familiarity(torch.zeros((2, 7), device="cuda"))
+    with pytest.raises(_lib.IsyError):
+        fam.WillshawMemory(100000, 100000)._handle()              # does not fit one SM's shared memory
+    with pytest.raises(_lib.IsyError):
+        fam.WillshawMemory(10, 100, sparseness=0.)._handle()
+    empty = mem.familiarity(torch.zeros((0, 8), device="cuda"))
+    assert empty.shape == (0,)
