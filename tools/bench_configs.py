@@ -8,6 +8,11 @@ Device-resident timings of the five BASELINE.json configurations on one GPU (CUD
   5  synthetic stress: 500 k blades, 10 k ommatidia x 16 cone samples, a --views5 sample of the 1 M views
 
     python tools/bench_configs.py [--configs 1,2,3,4,5] > profiles/rNN_configs.json
+
+Under torchrun (one process per GPU) configs 4 and 5 are sharded over the ranks -- config 4 by contiguous blocks of route
+steps, config 5 by contiguous chunks of its 1 M views (--views5 is then the TOTAL) -- and timed as the
+max over ranks between two barriers; rank 0 prints:
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_configs.py --configs 4,5 --views5 1000000
 """
 import argparse
 import json
@@ -22,6 +27,25 @@ import invertsy_b200 as ib
 from invertsy_b200 import views
 
 ALL = ("rgb", "hit", "depth", "Y", "dop", "aop")
+RANK, WORLD = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def sync_all():
+    torch.cuda.synchronize()
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+def max_ms(ms):
+    if WORLD == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def timed(fn, reps, warm=2):
@@ -100,6 +124,11 @@ def config4(chunk):
     hd = np.rad2deg(np.unwrap(np.deg2rad(route[:, 3])))
     rt = np.c_[rt, (np.interp(idx, np.arange(route.shape[0]), hd) + 180) % 360 - 180]
     pos, yaw_deg = views.parallel_views(rt, nb_orientations=72, nb_parallel=100, disposition_step=0.02)
+    P_total = pos.shape[0]
+    if WORLD > 1:     # blocks of route steps: positions are ordered (line k, step m); every rank takes its steps of every line
+        a, b = views.shard_positions(1000, RANK, WORLD)
+        keep = np.concatenate([np.arange(k * 1000 + a, k * 1000 + b) for k in range(100)])
+        pos, yaw_deg = pos[keep], yaw_deg[keep]
     P = pos.shape[0]
     pos_t = torch.as_tensor(pos, device="cuda")
     yw = torch.as_tensor(np.deg2rad(yaw_deg), device="cuda")
@@ -109,10 +138,12 @@ def config4(chunk):
         for s in range(0, P, chunk):
             e = min(s + chunk, P)
             r.render(pos_t[s:e], yw[s:e], outputs=ALL, out=out if e - s == chunk else None)
-    ms = timed(run, 2, 1)
+    run()
+    sync_all()
+    ms = max_ms(timed(run, 2, 0))
     r.check()
-    B = P * 72
-    return {"views": B, "positions": P, "chunk_positions": chunk, "ms": ms, "views_per_s": B / ms * 1e3,
+    B = P_total * 72
+    return {"views": B, "positions": P_total, "ranks": WORLD, "chunk_positions": chunk, "ms": ms, "views_per_s": B / ms * 1e3,
             "out_GB_per_s": B * 1000 * 32 / ms / 1e6}
 
 
@@ -131,15 +162,30 @@ def config5(nviews):
     rp = np.clip(pitch[:, None] + rho / 2 * rng.randn(N, S), -1.5, 1.5).ravel()
     ry = ((yaw[:, None] + rho / 2 * rng.randn(N, S) + np.pi) % (2 * np.pi) - np.pi).ravel()
     r = ib.Renderer(world, ib.EyeLayout.from_angles(rp, ry, samples=S), sky=ib.Sky(np.deg2rad(60), np.pi))
-    B = nviews
-    pos = torch.as_tensor(np.c_[rng.uniform(2, side - 2, B), rng.uniform(2, side - 2, B), np.full(B, 0.01)], device="cuda")
-    yw = torch.as_tensor(rng.uniform(-np.pi, np.pi, (B, 1)), device="cuda")
+    B_total = nviews
+    all_pos = np.c_[rng.uniform(2, side - 2, B_total), rng.uniform(2, side - 2, B_total), np.full(B_total, 0.01)]
+    all_yaw = rng.uniform(-np.pi, np.pi, (B_total, 1))
+    a, b = views.shard_positions(B_total, RANK, WORLD)
+    chunk = 4096                                        # views per call: 4096 x 10 000 ommatidia x 24 B = 0.98 GB of outputs
     out = {}
-    ms = timed(lambda: r.render(pos, yw, outputs=("rgb", "Y", "dop", "aop"), out=out), 3)
+
+    def run():
+        for s0 in range(a, b, chunk):
+            e0 = min(b, s0 + chunk)
+            r.render(torch.as_tensor(all_pos[s0:e0], device="cuda"), torch.as_tensor(all_yaw[s0:e0], device="cuda"),
+                     outputs=("rgb", "Y", "dop", "aop"), out=out if e0 - s0 == chunk else None)
+    B = B_total
+    if b - a <= chunk:
+        pos = torch.as_tensor(all_pos[a:b], device="cuda")
+        yw = torch.as_tensor(all_yaw[a:b], device="cuda")
+        run = lambda: r.render(pos, yw, outputs=("rgb", "Y", "dop", "aop"), out=out)   # noqa: E731
+    run()
+    sync_all()
+    ms = max_ms(timed(run, 3 if B_total <= 65536 else 1, 0))
     r.check()
     pc = r.phase_cycles().astype(float)
     print("config5 cycles per position: project %.0f accel %.0f final %.0f" % tuple(pc[:3] / max(pc[3], 1)), file=sys.stderr)
-    return {"views_timed": B, "rays_per_view": N * S, "triangles": T, "ms": ms, "views_per_s": B / ms * 1e3,
+    return {"views_timed": B, "ranks": WORLD, "rays_per_view": N * S, "triangles": T, "ms": ms, "views_per_s": B / ms * 1e3,
             "rays_per_s": B * N * S / ms * 1e3, "seconds_for_1M_views_one_gpu": 1e6 / (B / ms * 1e3)}
 
 
@@ -150,7 +196,11 @@ if __name__ == "__main__":
     ap.add_argument("--views5", type=int, default=2048)
     a = ap.parse_args()
     want = set(a.configs.split(","))
-    res = {"device": torch.cuda.get_device_name(0)}
+    torch.cuda.set_device(LOCAL)
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
+    res = {"device": torch.cuda.get_device_name(0), "ranks": WORLD}
     if "1" in want:
         res["config1_route"] = config1()
     if "2" in want:
@@ -161,4 +211,7 @@ if __name__ == "__main__":
         res["config4_parallel_lines"] = config4(a.chunk)
     if "5" in want:
         res["config5_synthetic_stress"] = config5(a.views5)
-    print(json.dumps(res, indent=1))
+    if RANK == 0:
+        print(json.dumps(res, indent=1))
+    if WORLD > 1:
+        dist.destroy_process_group()
