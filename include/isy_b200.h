@@ -71,10 +71,12 @@ enum {
                                         same results, used as an on-device cross-check                */
     ISY_FLAG_SUN_PER_VIEW = 1 << 2,  /* `sun` holds one (theta_s, phi_s) per view instead of one pair  */
     ISY_FLAG_OUT_F64 = 1 << 3,       /* rgb / depth / Y / dop / aop buffers are double instead of float */
-    ISY_FLAG_PER_VIEW_SKY = 1 << 4   /* evaluate the sky for every view even when all positions share one row of
+    ISY_FLAG_PER_VIEW_SKY = 1 << 4,  /* evaluate the sky for every view even when all positions share one row of
                                         headings under one sun (by default such calls evaluate it once per
                                         (heading, ray) and copy it into each view); same results to rounding,
                                         used as a cross-check                                             */
+    ISY_FLAG_NO_TILES = 1 << 5       /* scans with evenly spaced headings are rasterised copy by copy (column walk)
+                                        instead of tile by tile; same results, used as a cross-check        */
 };
 
 /* Per-ray / per-ommatidium outputs. Any pointer may be NULL (not produced).

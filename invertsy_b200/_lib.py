@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("ISY_B200_LIB", os.path.join(HERE, "libisy_b200.so")) 
 ABI_VERSION = 2
 ISY_OK, ISY_ERR_INVALID, ISY_ERR_CUDA, ISY_ERR_WORKSPACE, ISY_ERR_OVERFLOW = 0, -1, -2, -3, -4
 SKY_NONE, SKY_UNIFORM, SKY_PEREZ = 0, 1, 2
-FLAG_INIT_FROM_SKY, FLAG_BRUTE_FORCE, FLAG_SUN_PER_VIEW, FLAG_OUT_F64, FLAG_PER_VIEW_SKY = 1, 2, 4, 8, 16
+FLAG_INIT_FROM_SKY, FLAG_BRUTE_FORCE, FLAG_SUN_PER_VIEW, FLAG_OUT_F64, FLAG_PER_VIEW_SKY, FLAG_NO_TILES = 1, 2, 4, 8, 16, 32
 
 # every symbol include/isy_b200.h declares (tests check that the library exports all of them)
 EXPORTS = (

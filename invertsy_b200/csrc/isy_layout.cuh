@@ -28,6 +28,25 @@ constexpr int kHeadLut = 1024;        // slots of the azimuth -> first sorted he
 constexpr int kCellsSmem = 2048;      // cells of the eye's (pitch, yaw) ray grid kept in shared memory
 constexpr int kMaxGiants = 254;       // (copy, heading) pairs the cell walk can set aside per group
 constexpr int kSmallH = 4;            // up to this many headings per group the rasteriser walks the ray grid
+constexpr int kMaxTiles = kBestCap / 32 + kMaxH;   // (ceil(R / 32) x H) tiles of a scan whose winner buffer holds H x R slots
+
+// The threads [0, n) of the CTA, synchronised on hardware barrier `id` (0: the whole CTA, __syncthreads).  In rows mode
+// the last kCopyWarps warps stream the position's rows from the moment it starts, and everything up to the
+// rasterisation is done by the team of the others.
+struct Team {
+    int n, id;
+    __device__ __forceinline__ void sync() const {
+        if (id == 0) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+    }
+    __device__ __forceinline__ bool sync_and(bool pred) const {
+        if (id == 0) return __syncthreads_and(pred) != 0;
+        int r;
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %3, 0;\n\tbar.red.and.pred q, %1, %2, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
+                     : "=r"(r) : "r"(id), "r"(n), "r"((int)pred) : "memory");
+        return r != 0;
+    }
+};
 
 struct SmemBins {
     unsigned int bin_off[kBins + 4];  // exclusive offsets into list (counts during the count pass)
@@ -38,24 +57,35 @@ struct SmemBins {
 struct SmemRaster {
     unsigned short best[kBestCap];    // nearest containing copy (slot in tile) per (sorted heading, sorted ray)
     float2 sorted[kGridRaysSmem];     // the eye's rays in pitch order: (pitch, yaw) as floats (copied once per CTA)
-    unsigned int plut[kPitchLut + 4]; // first sorted ray at or above each pitch slot
+    unsigned short plut[kPitchLut + 4]; // first sorted ray at or above each pitch slot
     float hsort[2 * kMaxH];           // wrapped headings of the group, ascending, then the same + 2 pi
     float hvalf[2 * kMaxH];           // the wrapped heading itself (no + 2 pi) of each sorted slot
     unsigned char hperm[2 * kMaxH];   // heading index of each sorted slot
     unsigned char hinv[kMaxH];        // sorted slot of each heading
     unsigned short hlut[kHeadLut];    // first sorted slot that can reach each azimuth slot
     float uni[4];                     // {h0, delta, 1/delta, flag}: sorted headings are h0 + k*delta over the full circle
-    unsigned int cell_start[kCellsSmem + 4];      // the eye's static (pitch, yaw) ray grid: first list entry of each cell
+    unsigned short cell_start[kCellsSmem + 4];    // the eye's static (pitch, yaw) ray grid: first list entry of each cell
     unsigned short cell_list[kGridRaysSmem];      // ... and the pitch-sorted positions of the rays in each cell
+    // column walk (evenly spaced headings h0 + k*delta): the query azimuth of (ray j, sorted heading k) is
+    // phase[j] + c*delta - pi in column c = (colb[j] + k) mod H -- every column holds every ray exactly once
+    float phase[kGridRaysSmem];       // yaw_j + h0 + pi folded into [0, delta)
+    unsigned char colb[kGridRaysSmem];// floor((yaw_j + h0 + pi) / delta) mod H
+    float coloff[kMaxH + 2];          // c*delta - pi for c = -1 .. H
+    double ph_h0;                     // what phase[] / colb[] / coloff[] were built for: first sorted heading,
+    int ph_H, ph_lo;                  // ... number of headings, first sorted ray of the band
+    // tile walk: a tile = 32 consecutive pitch-sorted rays x one column; tile_cnt[t] = end of tile t's copy list
+    unsigned int tile_cnt[kMaxTiles + 1];
+    unsigned short crange[kMaxE];     // columns of each copy: (first + 1) | (number << 8)
 };
 
 struct SmemLayout {
     Entry tile[kMaxE];
     float4 bbox[kMaxE];               // (theta_lo, theta_hi, phi_lo, phi_hi) of each copy, margin included
+    unsigned short order[kMaxE];      // rasterisation order: tall copies from the front, the rest from the back
+                                      // (the tile walk keeps its copy lists in bbox + order once the ranges are taken)
     double head_sin[kMaxH], head_cos[kMaxH], head_val[kMaxH];   // per heading of the current group
     double2 gtab[2 * (kGTab + 1)];    // exp(D acos c) table of this call's sky (copied once per CTA)
     SunConst sun0;                    // sun constants when all views share one sun (copied once per CTA)
-    unsigned short order[kMaxE];      // rasterisation order: tall copies from the front, the rest from the back
     int order_n[2];                   // ... and how many of each
     unsigned short giants[kMaxGiants]; // cell walk: (copy, heading) pairs set aside for the whole CTA
     int n_giants;
@@ -71,8 +101,11 @@ struct SmemLayout {
     float resp1[kMaxE];                           // PN response of a ray that hits each copy's triangle (out.resp, 1 channel)
 };
 constexpr size_t kSmemBase = offsetof(SmemLayout, rgb);
-static_assert(kSmemBase <= 192 * 1024, "leave some of the 228 KB for L1");
+static_assert(kSmemBase <= 200 * 1024, "leave some of the 228 KB for L1");
 static_assert(sizeof(SmemLayout) <= 224 * 1024, "rows mode: 227 KB per CTA is the limit");
+
+constexpr int kTileListCap = (int)((sizeof(float4) + sizeof(unsigned short)) * kMaxE / sizeof(unsigned short));   // 10 368 entries
+static_assert(offsetof(SmemLayout, order) == offsetof(SmemLayout, bbox) + sizeof(float4) * kMaxE, "the tile lists span bbox + order");
 
 struct RayOut {
     double r, g, b;

@@ -74,26 +74,20 @@ struct CullScratch {
     unsigned int rowbeg[16], rowoff[17];
 };
 
-// barrier among the kNT threads that run a cull: the CTA (kBar = 0) or a named barrier
-template <int kNT, int kBar>
-__device__ __forceinline__ void group_sync() {
-    if (kBar == 0) __syncthreads();
-    else asm volatile("bar.sync %0, %1;" ::"n"(kBar), "n"(kNT) : "memory");
-}
 
 // A1: the visible triangles of position p -> vis[] (triangle ids) and stage[] (their vertices, 9 planes of stage_cap
-// floats; shared or global memory), by a group of kNT threads (gt = this thread's index in it; the group starts at
+// floats; shared or global memory), by a team of threads (gt = this thread's index in it; the team starts at
 // a warp boundary).  Returns their number.  The CTA runs it for the position it is about to render; in rows mode the
 // copy warps also run it for the NEXT position while the others rasterise (vis / stage in the workspace), so that
 // the latency of its three dependent trips to L2 (cell rows -> cell lists -> vertices) is off the critical path.
-template <int kNT, int kBar>
-__device__ int cull_position(const RenderParams& rp, int p, int gt, int* vis, float* stage, int stage_cap, CullScratch& sc) {
+__device__ int cull_position(const RenderParams& rp, const Team& tm, int p, int gt, int* vis, float* stage, int stage_cap, CullScratch& sc) {
+    const int kNT = tm.n;
     const int lane = gt & 31;
     const double px = rp.pos[3 * p + 0], py = rp.pos[3 * p + 1], pz = rp.pos[3 * p + 2];
     const double h = rp.horizon;
     const double h2_max = rp.horizon_sq_max;     // sqrt_rn(s) <= horizon  <=>  s <= h2_max (set by the host)
     if (gt == 0) sc.count = 0;
-    group_sync<kNT, kBar>();
+    tm.sync();
     // ---- A1: cull (world.py:97-98) ----
     // Candidates come from the world's xy cell grid (isy_world_create): a visible triangle has a vertex
     // within the horizon, so it is listed in a cell that meets the disc around the eye.  A triangle is
@@ -135,7 +129,7 @@ __device__ int cull_position(const RenderParams& rp, int p, int gt, int* vis, fl
         if (gt < nrows) sc.rowbeg[gt] = beg, sc.rowoff[gt] = incl - cnt;
         if (gt == nrows - 1) sc.rowoff[nrows] = incl;
     }
-    group_sync<kNT, kBar>();
+    tm.sync();
     const unsigned int ncand = sc.rowoff[nrows];
     // two candidates per thread and trip: their list reads and vertex gathers (two dependent trips to L2
     // each) overlap
@@ -205,8 +199,8 @@ __device__ int cull_position(const RenderParams& rp, int p, int gt, int* vis, fl
             }
         }
     }
-    group_sync<kNT, kBar>();
-    group_sync<kNT, kBar>();
+    tm.sync();
+    tm.sync();
     return sc.count;
 }
 
@@ -215,7 +209,7 @@ static_assert(9 * kStage * sizeof(float) <= sizeof(unsigned short) * kBestCap, "
 static_assert(9 * kStage * sizeof(float) <= sizeof(SmemBins), "... and the bin lists (built after the projection)");
 
 template <bool kRuns>
-__device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* entries, Exact* exacts,
+__device__ int cull_and_project(const RenderParams& rp, const Team& tm, int p, int* vis, Entry* entries, Exact* exacts,
                                 SmemLayout& sm, CullScratch* sc, const CullScratch* ahead, const float* ahead_stage,
                                 int ahead_cap, int* s_nent, int* s_band, long long* t_mid = nullptr) {
     // ahead != null: position p was culled ahead (vis[] filled, vertices in ahead_stage, ahead->count of them)
@@ -236,7 +230,7 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
         s_band[0] = float_key(CUDART_INF_F);
         s_band[1] = float_key(-CUDART_INF_F);
     }
-    __syncthreads();
+    tm.sync();
 
     // ---- A1: cull (world.py:97-98), unless the copy warps did it while the previous position was rasterised ----
     int V;
@@ -244,7 +238,7 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
         V = ahead->count;
         stage = ahead_stage, stage_cap = ahead_cap;
     } else {
-        V = cull_position<kThreads, 0>(rp, p, tid, vis, reinterpret_cast<float*>(&sm.ras), kStage, *sc);
+        V = cull_position(rp, tm, p, tid, vis, reinterpret_cast<float*>(&sm.ras), kStage, *sc);
     }
 #ifdef ISY_PHASE_DETAIL
     *t_mid = clock64();   // (profiling build only) end of the cull
@@ -255,7 +249,7 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
     }
 
     // ---- A2: angular projection of the visible triangles (world.py:109-120) ----
-    for (int j = tid; j < V; j += kThreads) {
+    for (int j = tid; j < V; j += tm.n) {
         int t = vis[j];
         double v[3][3];
         if (j < stage_cap) {
@@ -315,7 +309,7 @@ __device__ int cull_and_project(const RenderParams& rp, int p, int* vis, Entry* 
             }
         }
     }
-    __syncthreads();
+    tm.sync();
     int E = *s_nent;
     if (E > rp.slab_cap) {
         if (tid == 0) atomicExch(rp.status, (int)ISY_ERR_OVERFLOW);

@@ -77,7 +77,7 @@ __device__ __forceinline__ void post_copy_u32(unsigned int* slot, const Entry* t
 // sorts the group's wrapped headings (head_val[0..Hcur)); returns true (to every thread) when they are evenly
 // spaced over the full circle -- every scan of the reference's simulations, and a single heading -- so that
 // the window walk can use arithmetic; otherwise it also builds the azimuth look-up table
-__device__ bool sort_headings(SmemLayout& sm, int Hcur) {
+__device__ bool sort_headings(SmemLayout& sm, const Team& tm, int Hcur) {
     const int tid = threadIdx.x;
     if (tid < Hcur) {
         const float h = (float)sm.head_val[tid];
@@ -94,14 +94,14 @@ __device__ bool sort_headings(SmemLayout& sm, int Hcur) {
         sm.ras.hperm[pos + Hcur] = (unsigned char)tid;
         sm.ras.hinv[tid] = (unsigned char)pos;
     }
-    __syncthreads();
+    tm.sync();
     const float h0 = sm.ras.hsort[0];
     const float delta = (float)kTwoPi / (float)Hcur;
     const bool mine = tid >= Hcur || fabsf(sm.ras.hsort[tid] - (h0 + tid * delta)) < 5e-7f;
-    const bool uniform = __syncthreads_and(mine);
+    const bool uniform = tm.sync_and(mine);
     if (tid == 0) sm.ras.uni[0] = h0, sm.ras.uni[1] = delta, sm.ras.uni[2] = 1.0f / delta, sm.ras.uni[3] = uniform ? 1.f : 0.f;
     if (!uniform) {
-        for (int s = tid; s < kHeadLut; s += kThreads) {
+        for (int s = tid; s < kHeadLut; s += tm.n) {
             // first sorted slot whose heading is not below this azimuth slot (minus a guard band):
             // windows start their walk here; whatever they pick up below `lower` just fails the edge test
             const float start = -(float)kPi + s * ((float)kTwoPi / kHeadLut) - 1e-4f;
@@ -222,6 +222,397 @@ __device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& s
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Column walk (evenly spaced headings over the full circle: every scan of the reference's simulations).
+// With headings h0 + k*delta, delta = 2 pi / H, the azimuth of (ray j, heading k) is
+//     yaw_j + h0 + k*delta  =  phase_j + (b_j + k)*delta - pi   (mod 2 pi),   phase_j in [0, delta),
+// so the H queries of a ray fall one into each of the H azimuth columns [c*delta - pi, (c+1)*delta - pi), and column
+// c holds every ray exactly once -- at heading k = (c - b_j) mod H.  A copy is therefore tested against
+// (rays of its pitch run) x (columns its azimuth range touches): no window set-up per ray, no walk over headings,
+// all lanes busy.  E_k(pitch, phase + off) = (A pitch + B phase + C) + B off: the bracket is formed once per ray, a
+// column costs one FMA per edge.  build_phases makes the tables once per CTA while the headings stay the same.
+// fp32 budget of the edge value: coefficients 3 pi u, pitch pi/2 u, phase + column offset (delta + pi) u, three FMA
+// roundings (delta + 2 pi) u + (2.5 pi + delta) u + 3.5 pi u  ->  2.4e-6, plus the 7.5e-7 between h0 + k*delta
+// and the true heading admitted by the uniformity check: 3.1e-6 < kEdgeEps.
+// ------------------------------------------------------------------------------------------
+__device__ void build_phases(const RenderParams& rp, SmemLayout& sm, const Team& tm, int Hcur, int r_n, unsigned jbase) {
+    const double h0 = sm.head_val[sm.ras.hperm[0]];
+    const bool same = sm.ras.ph_H == Hcur && sm.ras.ph_lo == (int)jbase && sm.ras.ph_h0 == h0;
+    tm.sync();
+    if (same) return;
+    const double delta = kTwoPi / (double)Hcur, inv = (double)Hcur / kTwoPi;
+    for (int j = threadIdx.x; j < r_n; j += tm.n) {
+        const int ray = __ldg(rp.grid_sorted_ray + jbase + j);
+        const double x = rp.eye_py[2 * (size_t)ray + 1] + h0 + kPi;      // (-pi, 3 pi]
+        double b = floor(x * inv), phi = x - b * delta;
+        if (phi < 0.0) phi += delta, b -= 1.0;
+        else if (phi >= delta) phi -= delta, b += 1.0;
+        int bm = (int)b % Hcur;
+        if (bm < 0) bm += Hcur;
+        sm.ras.phase[j] = (float)phi;
+        sm.ras.colb[j] = (unsigned char)bm;
+    }
+    for (int i = threadIdx.x; i < Hcur + 2; i += tm.n) sm.ras.coloff[i] = (float)((double)(i - 1) * delta - kPi);
+    if (threadIdx.x == 0) sm.ras.ph_H = Hcur, sm.ras.ph_lo = (int)jbase, sm.ras.ph_h0 = h0;
+}
+
+// 32 * RU consecutive pitch-sorted rays from jb against copy e in columns c_lo .. c_hi (-1 and H are the aliases of
+// H - 1 and 0 beyond the seam: only the queries within 3e-4 rad of +-pi are looked at there, in fp64)
+template <int RU>
+__device__ __forceinline__ void column_chunk(const RenderParams& rp, SmemLayout& sm, const Exact* exacts, const Entry& ent,
+                                             int e, unsigned jb, unsigned jend, int c_lo, int c_hi, int Hcur, int R,
+                                             unsigned jbase) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int best_s = (unsigned int)__cvta_generic_to_shared(sm.ras.best);
+    float g0[RU], g1[RU], g2[RU], ph[RU];
+    const float ninf = __int_as_float(0xff800000);
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+        const unsigned j = jb + u * 32 + lane;
+        ISY_BOUND(jend <= (unsigned)kGridRaysSmem);
+        const bool ok = j < jend;
+        const float pitch = ok ? sm.ras.sorted[j].x : 0.f;
+        ph[u] = ok ? sm.ras.phase[j] : 0.f;
+        g0[u] = ok ? fmaf(ent.A0, pitch, fmaf(ent.B0, ph[u], ent.C0)) : ninf;
+        g1[u] = fmaf(ent.A1, pitch, fmaf(ent.B1, ph[u], ent.C1));
+        g2[u] = fmaf(ent.A2, pitch, fmaf(ent.B2, ph[u], ent.C2));
+    }
+    for (int c = c_lo; c <= c_hi; ++c) {
+        const float off = sm.ras.coloff[c + 1];
+        const bool edge = c <= 0 || c >= Hcur - 1;          // columns that touch the seam
+        float m[RU];
+        bool cand[RU], any = false;
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            m[u] = fminf(fmaf(ent.B0, off, g0[u]), fminf(fmaf(ent.B1, off, g1[u]), fmaf(ent.B2, off, g2[u])));
+            cand[u] = m[u] >= -kEdgeEps;
+        }
+        if (edge) {
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                const float af = fabsf(ph[u] + off);
+                cand[u] = jb + u * 32 + lane < jend && af <= 3.1419f && (af > 3.14159f || cand[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) any |= cand[u];
+        if (!__any_sync(0xffffffffu, any)) continue;
+        const int cw = c < 0 ? c + Hcur : (c >= Hcur ? c - Hcur : c);
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            if (!cand[u]) continue;
+            const unsigned j = jb + u * 32 + lane;
+            int ks = cw - (int)sm.ras.colb[j];               // sorted slot of the heading that puts ray j into column c
+            if (ks < 0) ks += Hcur;
+            const bool seam = edge && fabsf(ph[u] + off) > 3.14159f;
+            bool in = m[u] > kEdgeEps && !seam;
+            if (!in) {
+                // the rounding band of an edge, or a query within 3e-6 rad of the seam: redo the query in fp64
+                // exactly as the reference composes it
+                const int hh = sm.ras.hperm[ks];
+                const int ray = __ldg(rp.grid_sorted_ray + jbase + j);
+                double yg = rp.eye_py[2 * (size_t)ray + 1] + sm.head_val[hh];
+                if (yg > kPi) yg -= kTwoPi;
+                else if (yg <= -kPi) yg += kTwoPi;
+                const float f = (float)yg, pitch = sm.ras.sorted[j].x;
+                const float e0 = fmaf(ent.A0, pitch, fmaf(ent.B0, f, ent.C0));
+                const float e1 = fmaf(ent.A1, pitch, fmaf(ent.B1, f, ent.C1));
+                const float e2 = fmaf(ent.A2, pitch, fmaf(ent.B2, f, ent.C2));
+                const float mm = fminf(e0, fminf(e1, e2));
+                in = mm > kEdgeEps;
+                if (!in && mm >= -kEdgeEps) in = inside_exact(exacts[e], rp.eye_py[2 * (size_t)ray], yg);
+            }
+            if (in) post_copy_u16(best_s, (unsigned)ks * R + j, sm.tile, __hiloint2double(ent.dist_hi, ent.dist_lo), ent.tri, e);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Tile walk (the same evenly spaced headings): the queries of a position are cut into tiles of kTileRays consecutive
+// pitch-sorted rays x one azimuth column.  The copies are first filed into the tiles their pitch run and azimuth
+// range touch (count, scan, fill: lists of Entry byte offsets kept where bbox / order were); then a warp takes a tile,
+// its lanes kTileU queries each, and tests the tile's copies one after the other -- every load is a broadcast, the
+// nearest containing copy of a query stays in registers, and the winner buffer is written once per hit, without
+// atomics.  A position whose lists would not fit falls back to the column walk.
+// The fp32 query azimuth is fl(phase + column offset): three roundings (< 2.5e-7) + 7.5e-7 between h0 + k*delta and
+// the true heading: inside the 1.9e-6 that kEdgeEps admits for it (isy_common.cuh).
+// ------------------------------------------------------------------------------------------
+#ifndef ISY_BIN_SOLO
+#define ISY_BIN_SOLO 8
+#endif
+#ifndef ISY_TILE_U
+#define ISY_TILE_U 2
+#endif
+constexpr int kBinSolo = ISY_BIN_SOLO;       // a copy that touches up to this many tiles is filed by its own lane
+constexpr int kTileU = ISY_TILE_U;           // queries per lane in a tile
+constexpr int kTileRays = 32 * kTileU, kTileShift = kTileU == 1 ? 5 : (kTileU == 2 ? 6 : 7);
+static_assert(kTileU == 1 || kTileU == 2 || kTileU == 4, "tiles of 32, 64 or 128 rays");
+
+// one lane of the warp takes n items from a shared-memory counter (elect.sync keeps ptxas from wrapping the atomic
+// into its warp-aggregation sequence); returns the first to every lane
+__device__ __forceinline__ int warp_fetch(int* counter, int n) {
+    int v = 0;
+    const unsigned int a = (unsigned int)__cvta_generic_to_shared(counter);
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t@p atom.shared.add.s32 %0, [%1], %2;\n\t}"
+                 : "+r"(v) : "r"(a), "r"(n) : "memory");
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+
+template <bool kFill>
+__device__ __forceinline__ void bin_add(SmemLayout& sm, unsigned short* tlist, int tile, int e) {
+    ISY_BOUND(tile >= 0 && tile < kMaxTiles);
+    const int at = smem_atomic_add(reinterpret_cast<int*>(&sm.ras.tile_cnt[tile]), 1);
+    if (kFill) {
+        ISY_BOUND(at >= 0 && at < kMaxE * 24);
+        tlist[at] = (unsigned short)(e * (int)sizeof(Entry));
+    }
+}
+
+// place of chunk q in the walk's queue: the chunks at and above the horizon (the middle of a pitch-sorted eye) hold
+// nearly all the work and go first, from the horizon upwards; the chunks below it follow
+__device__ __forceinline__ int chunk_place(int q, int q_h) { return q <= q_h ? q_h - q : q; }
+
+template <bool kFill>
+__device__ void bin_pass(SmemLayout& sm, const Team& tm, int E, int Hcur, int q_h, unsigned short* tlist) {
+    const int lane = threadIdx.x & 31;
+    for (int base = (int)(threadIdx.x >> 5) * 32; base < E; base += tm.n) {   // warp-uniform trip count
+        const int e = base + lane;
+        int q0 = 0, nq = 0, c0 = 0, nc = 0;
+        if (e < E) {
+            const unsigned int jr = sm.jrange[e], cr = sm.ras.crange[e];
+            const unsigned jbeg = jr & 0xffffu, jend = jr >> 16;
+            if (jbeg < jend)
+                q0 = (int)(jbeg >> kTileShift), nq = (int)((jend - 1) >> kTileShift) - q0 + 1, c0 = (int)(cr & 0xffu) - 1, nc = (int)(cr >> 8);
+        }
+        const int nt = nq * nc;
+        if (nt > 0 && nt <= kBinSolo) {
+            int c = c0 < 0 ? c0 + Hcur : c0, q = q0, tq = chunk_place(q, q_h) * Hcur, k = 0;
+            for (int i = 0; i < nt; ++i) {
+                bin_add<kFill>(sm, tlist, tq + c, e);
+                ++k, ++c;
+                if (c >= Hcur) c -= Hcur;
+                if (k == nc) k = 0, c = c0 < 0 ? c0 + Hcur : c0, ++q, tq = chunk_place(q, q_h) * Hcur;
+            }
+        }
+        // larger copies: the warp files them together, a tile per lane
+        unsigned int big = __ballot_sync(0xffffffffu, nt > kBinSolo);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const int be = base + src, bq0 = __shfl_sync(0xffffffffu, q0, src), bc0 = __shfl_sync(0xffffffffu, c0, src);
+            const int bnc = __shfl_sync(0xffffffffu, nc, src), bnt = __shfl_sync(0xffffffffu, nt, src);
+            const float rnc = 1.0f / (float)bnc;
+            for (int t = lane; t < bnt; t += 32) {
+                const int dq = (int)(((float)t + 0.5f) * rnc);        // t / bnc, exact for these sizes
+                int c = bc0 + (t - dq * bnc);
+                c = c < 0 ? c + Hcur : (c >= Hcur ? c - Hcur : c);
+                bin_add<kFill>(sm, tlist, chunk_place(bq0 + dq, q_h) * Hcur + c, be);
+            }
+        }
+    }
+}
+
+// files the E copies of the position into the tiles of Rrow rays x Hcur columns; false (to every thread): the lists
+// do not fit.  Called by the whole team; the lists are complete after the callers' next barrier.
+// where a position's tile lists go: over bbox + order when nothing needs the boxes any more (one group of headings,
+// no bands), else into what the E copies leave free of the Entry tile
+__device__ __forceinline__ unsigned short* tile_lists(SmemLayout& sm, int E, bool boxes_free, int& cap) {
+    const int tail = (kMaxE - E) * (int)(sizeof(Entry) / sizeof(unsigned short));
+    if (boxes_free && tail < kTileListCap) {
+        cap = kTileListCap;
+        return reinterpret_cast<unsigned short*>(sm.bbox);
+    }
+    cap = tail;
+    return reinterpret_cast<unsigned short*>(sm.tile + E);
+}
+
+__device__ bool bin_copies(SmemLayout& sm, const Team& tm, int E, int Hcur, int Rrow, unsigned int* s_warp, unsigned short* tlist,
+                           int cap) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NQ = (Rrow + kTileRays - 1) >> kTileShift, NT = NQ * Hcur, q_h = min(NQ - 1, NQ / 2);
+    ISY_BOUND(NT <= kMaxTiles && NT <= 2 * tm.n);
+    const float pi_f = (float)kPi, inv_delta = sm.ras.uni[2];
+    for (int i = tid; i <= NT; i += tm.n) sm.ras.tile_cnt[i] = 0;
+    for (int e = tid; e < E; e += tm.n) {          // the columns of each copy (the lists will overwrite the boxes)
+        const float4 bb = sm.bbox[e];
+        const float glo = fmaxf(bb.z, -pi_f - kBinMargin) - kBinMargin, ghi = fminf(bb.w, pi_f + kBinMargin) + kBinMargin;
+        unsigned int cr = 0;
+        if (glo <= ghi) {
+            const int c_lo = (int)floorf((glo + pi_f) * inv_delta), c_hi = (int)floorf((ghi + pi_f) * inv_delta);
+            ISY_BOUND(c_lo >= -1 && c_hi <= Hcur);
+            cr = (unsigned)(c_lo + 1) | ((unsigned)min(c_hi - c_lo + 1, Hcur) << 8);   // -1 and H alias H - 1 and 0
+        }
+        sm.ras.crange[e] = (unsigned short)cr;
+    }
+    tm.sync();
+    bin_pass<false>(sm, tm, E, Hcur, q_h, tlist);
+    tm.sync();
+    // exclusive scan of the counts (two tiles per thread)
+    const int i0 = 2 * tid;
+    const unsigned a = i0 < NT ? sm.ras.tile_cnt[i0] : 0u, b = i0 + 1 < NT ? sm.ras.tile_cnt[i0 + 1] : 0u;
+    unsigned incl = a + b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    tm.sync();
+    unsigned w = lane < (tm.n >> 5) ? s_warp[lane] : 0u, before = lane < warp ? w : 0u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        w += __shfl_xor_sync(0xffffffffu, w, d);
+        before += __shfl_xor_sync(0xffffffffu, before, d);
+    }
+    const unsigned total = w;
+    if (total > (unsigned)cap) return false;
+    const unsigned excl = before + incl - (a + b);
+    if (i0 < NT) sm.ras.tile_cnt[i0] = excl;
+    if (i0 + 1 < NT) sm.ras.tile_cnt[i0 + 1] = excl + a;
+    tm.sync();
+    bin_pass<true>(sm, tm, E, Hcur, q_h, tlist);      // tile_cnt[t] ends as the END of tile t's list
+    return true;
+}
+
+// the winner a query holds while its tile is walked
+struct TileBest {
+    unsigned int off, lo;   // Entry byte offset of the nearest containing copy (0xffffffff: none), low word of its distance
+    int hi, tri;            // high word of the distance, triangle index
+};
+
+// copy `eo` may contain the query (edge value m within the rounding band or above, or a query at the seam): settle
+// it -- in fp64 where the fp32 value cannot -- and keep the copy if it is nearer than what the query holds
+__device__ __forceinline__ void tile_candidate(const RenderParams& rp, SmemLayout& sm, const Exact* exacts, const float4& a,
+                                               const float4& b, const float4& d, unsigned eo, float pitch, float m, bool seam,
+                                               int ks, unsigned j, unsigned jbase, TileBest& w) {
+    bool in = m > kEdgeEps && !seam;
+    if (!in) {
+        // the rounding band of an edge, or a query within 3e-6 rad of the seam: redo the query in fp64 exactly as
+        // the reference composes it
+        const int hh = sm.ras.hperm[ks];
+        const int ray = __ldg(rp.grid_sorted_ray + jbase + j);
+        double yg = rp.eye_py[2 * (size_t)ray + 1] + sm.head_val[hh];
+        if (yg > kPi) yg -= kTwoPi;
+        else if (yg <= -kPi) yg += kTwoPi;
+        const float fe = (float)yg;
+        const float mm = fminf(fmaf(a.x, pitch, fmaf(a.y, fe, a.z)),
+                               fminf(fmaf(a.w, pitch, fmaf(b.x, fe, b.y)), fmaf(b.z, pitch, fmaf(b.w, fe, d.x))));
+        in = mm > kEdgeEps;
+        if (!in && mm >= -kEdgeEps) in = inside_exact(exacts[eo / (unsigned)sizeof(Entry)], rp.eye_py[2 * (size_t)ray], yg);
+    }
+    if (in) {
+        // nearer? (distance, then triangle index, then slot: as nearer())
+        const int dhi = __float_as_int(d.w), tri = __float_as_int(d.y);
+        const unsigned dlo = (unsigned)__float_as_int(d.z);
+        bool nr = dhi < w.hi;                  // the upper word decides almost always
+        if (dhi == w.hi) nr = dlo < w.lo || (dlo == w.lo && (tri < w.tri || (tri == w.tri && eo < w.off)));
+        if (nr) w.hi = dhi, w.lo = dlo, w.tri = tri, w.off = eo;
+    }
+}
+
+// one copy against the kTileU queries of every lane: edge values, and whether any may be inside
+struct TileCopy {
+    float4 a, b, d;     // the Entry: (A0 B0 C0 A1) (B1 C1 A2 B2) (C2 tri dist_lo dist_hi)
+    unsigned eo;        // its byte offset in the tile
+    float m[kTileU];
+};
+__device__ __forceinline__ void tile_load(TileCopy& t, const char* tile_b, unsigned eo) {
+    t.eo = eo;
+    t.a = *reinterpret_cast<const float4*>(tile_b + eo);
+    t.b = *reinterpret_cast<const float4*>(tile_b + eo + 16);
+    t.d = *reinterpret_cast<const float4*>(tile_b + eo + 32);
+}
+__device__ __forceinline__ float tile_eval(TileCopy& t, const float (&pitch)[kTileU], const float (&f)[kTileU]) {
+    float mx = -CUDART_INF_F;
+#pragma unroll
+    for (int u = 0; u < kTileU; ++u) {
+        t.m[u] = fminf(fmaf(t.a.x, pitch[u], fmaf(t.a.y, f[u], t.a.z)),
+                       fminf(fmaf(t.a.w, pitch[u], fmaf(t.b.x, f[u], t.b.y)), fmaf(t.b.z, pitch[u], fmaf(t.b.w, f[u], t.d.x))));
+        mx = fmaxf(mx, t.m[u]);
+    }
+    return mx;      // (NaN edge values -- lanes beyond the eye -- never raise it)
+}
+
+// the copies [i0, i1) of a tile's list against the queries of the tile; kSeam: some query of the tile lies within
+// 3e-6 rad of the seam and meets every copy in fp64
+template <bool kSeam>
+__device__ __forceinline__ void tile_list(const RenderParams& rp, SmemLayout& sm, const Exact* exacts, const unsigned short* lp,
+                                          const unsigned short* le, const float (&pitch)[kTileU], const float (&f)[kTileU],
+                                          const bool (&seam)[kTileU], const int (&ks)[kTileU], unsigned j0, unsigned jbase,
+                                          TileBest (&w)[kTileU]) {
+    const int lane = threadIdx.x & 31;
+    const char* const tile_b = reinterpret_cast<const char*>(sm.tile);
+    for (; lp < le; ++lp) {
+        TileCopy c0;
+        tile_load(c0, tile_b, lp[0]);
+        const float mx = tile_eval(c0, pitch, f);
+        if (!__any_sync(0xffffffffu, kSeam || mx >= -kEdgeEps)) continue;
+#pragma unroll
+        for (int u = 0; u < kTileU; ++u) {
+            const bool sl = kSeam && seam[u];
+            if (c0.m[u] >= -kEdgeEps || sl)
+                tile_candidate(rp, sm, exacts, c0.a, c0.b, c0.d, c0.eo, pitch[u], c0.m[u], sl, ks[u], j0 + u * 32 + lane, jbase, w[u]);
+        }
+        __syncwarp();
+    }
+}
+
+#ifndef ISY_TILE_HEAVY_ROWS
+#define ISY_TILE_HEAVY_ROWS 4
+#endif
+__device__ void raster_tiles(const RenderParams& rp, SmemLayout& sm, const Exact* exacts, const unsigned short* tlist, int Hcur,
+                             int* s_next, int Rrow, unsigned jbase, int stop_after = 0x7fffffff) {
+    const int lane = threadIdx.x & 31;
+    const int NQ = (Rrow + kTileRays - 1) >> kTileShift, NT = NQ * Hcur;
+    const int q_h = min(NQ - 1, NQ / 2);
+    const int heavy = ISY_TILE_HEAVY_ROWS * Hcur;   // the first places of the queue are taken one at a time, the rest four at a time
+    const float rH = 1.0f / (float)Hcur;
+    const float qnan = __int_as_float(0x7fc00000);
+    int take = 1;
+    for (;;) {
+        const int t0 = warp_fetch(s_next, take);
+        if (t0 >= NT) break;
+        const int t1 = min(t0 + take, NT);
+        if (t0 >= heavy) take = 4;
+        for (int t = t0; t < t1; ++t) {
+            const unsigned i1 = sm.ras.tile_cnt[t], i0 = t ? sm.ras.tile_cnt[t - 1] : 0u;
+            if (i0 == i1) continue;
+            // place t of the queue -> tile (q, c)
+            const int tq = (int)(((float)t + 0.5f) * rH), c = t - tq * Hcur, q = chunk_place(tq, q_h);   // (its own inverse)
+            ISY_BOUND(q >= 0 && q < NQ && c >= 0 && c < Hcur && i1 <= (unsigned)(kMaxE * 24));
+            const float off = sm.ras.coloff[c + 1];
+            const bool edge = c == 0 || c == Hcur - 1;
+            const unsigned j0 = (unsigned)q * kTileRays;
+            float pitch[kTileU], f[kTileU];
+            bool seam[kTileU], any_seam = false;
+            int ks[kTileU];
+            TileBest w[kTileU];
+#pragma unroll
+            for (int u = 0; u < kTileU; ++u) {
+                const unsigned j = j0 + u * 32 + lane;
+                const bool ok = j < (unsigned)Rrow;
+                pitch[u] = ok ? sm.ras.sorted[j].x : qnan;      // (a NaN pitch fails every test)
+                f[u] = (ok ? sm.ras.phase[j] : 0.f) + off;
+                seam[u] = ok && edge && fabsf(f[u]) > 3.14159f;
+                any_seam |= seam[u];
+                ks[u] = c - (ok ? (int)sm.ras.colb[j] : 0);      // sorted slot of the heading that puts ray j into column c
+                if (ks[u] < 0) ks[u] += Hcur;
+                w[u].off = 0xffffffffu, w[u].lo = 0u, w[u].hi = 0x7fffffff, w[u].tri = 0;
+            }
+            if (edge && __any_sync(0xffffffffu, any_seam)) tile_list<true>(rp, sm, exacts, tlist + i0, tlist + i1, pitch, f, seam, ks, j0, jbase, w);
+            else tile_list<false>(rp, sm, exacts, tlist + i0, tlist + i1, pitch, f, seam, ks, j0, jbase, w);
+#pragma unroll
+            for (int u = 0; u < kTileU; ++u)
+                if (w[u].off != 0xffffffffu) {
+                    const unsigned j = j0 + u * 32 + lane;
+                    ISY_BOUND((unsigned)ks[u] * Rrow + j < (unsigned)kBestCap);
+                    sm.ras.best[(unsigned)ks[u] * Rrow + j] = (unsigned short)(w[u].off / (unsigned)sizeof(Entry));
+                }
+        }
+        if (t1 > stop_after) break;
+    }
+}
+
 // The pitch-run walk of one group of headings over one band of rays (a small eye is one band): the band's sorted
 // ray table and the winner buffer (u16 slots, Rrow per heading) live in shared memory.
 // The hot path is fp32: query azimuth = fl(yaw_f + heading_f) wrapped in fp32; kEdgeEps covers that
@@ -259,8 +650,22 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, const Exac
         const float width = ghi - glo;
         const Entry ent = sm.tile[e];
         const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
-        // kRU rays per lane while that many warps' worth are left, then one ray per lane for the tail
         unsigned jb = jbeg;
+        if (kUniform) {   // column walk
+            const float inv_delta = sm.ras.uni[2];
+            const int c_lo = (int)floorf((glo + pi_f) * inv_delta), c_hi = (int)floorf((ghi + pi_f) * inv_delta);
+            ISY_BOUND(c_lo >= -1 && c_hi <= Hcur);
+            for (; jb + 32 * (kRU - 1) < jend; jb += 32 * kRU) {
+                __syncwarp();
+                column_chunk<kRU>(rp, sm, exacts, ent, e, jb, jend, c_lo, c_hi, Hcur, Rrow, jbase);
+            }
+            for (; jb < jend; jb += 32) {
+                __syncwarp();
+                column_chunk<1>(rp, sm, exacts, ent, e, jb, jend, c_lo, c_hi, Hcur, Rrow, jbase);
+            }
+            continue;
+        }
+        // kRU rays per lane while that many warps' worth are left, then one ray per lane for the tail
         for (; jb + 32 * (kRU - 1) < jend; jb += 32 * kRU) {   // warp-uniform trip counts
             __syncwarp();                                       // keep the lanes converged across iterations
             walk_chunk<kUniform, kRU>(rp, sm, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur, Rrow, jbase);

@@ -14,12 +14,25 @@
 #ifndef ISY_COPY_WARPS
 #define ISY_COPY_WARPS 4
 #endif
+#ifndef ISY_ROWS_ALL
+#define ISY_ROWS_ALL 0
+#endif
+// Rows mode, scans: the copy warps start on the position's rows the moment the position starts and leave the cull,
+// the projection and the filing of the copies to the team of the other warps; they join the rasterisation when their
+// rows are out.  (0: they take part in everything and copy while the others rasterise.)
+#ifndef ISY_EARLY_ROWS
+#define ISY_EARLY_ROWS 1
+#endif
 
 namespace isy {
 
 // the template rows are written when this many copies are left to take: about what the other warps rasterise in the
 // 25-30 k cycles the rows need on the store path (short positions start at once, long ones later than a fixed share)
 constexpr int kLateCopies = ISY_LATE_COPIES;
+#ifndef ISY_LATE_TILES
+#define ISY_LATE_TILES 64
+#endif
+constexpr int kLateTiles = ISY_LATE_TILES;   // tile walk: ... when this many 256ths of the tile queue have been taken
 constexpr int kCopyWarps = ISY_COPY_WARPS;   // warps that stream the template rows of a position while the rest rasterise
 
 enum { kModeBrute = 0, kModeBins = 1, kModeRaster = 2 };
@@ -59,18 +72,30 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
         if (tid == 0) sm.sun0 = rp.sun[0];
     }
     float* const ahead_stage = (ISY_CULL_AHEAD && rp.slab_stage) ? rp.slab_stage + (size_t)blockIdx.x * 9 * rp.stage_cap : nullptr;
-    if (tid == 0) s_ahead_item = 0xffffffffu;
+    __shared__ volatile int s_join[3];             // early rows: (item, group) whose lists are ready + 1, how to walk them, E
+    __shared__ int s_E;
+    __shared__ volatile int s_ahead_go;
+    if (tid == 0) s_ahead_item = 0xffffffffu, sm.ras.ph_H = -1, s_join[0] = 0;
+    const bool early_rows = ISY_EARLY_ROWS && !ISY_ROWS_ALL && rows_mode && rp.H / rp.ngroups > kSmallH;
+    const Team tm = early_rows ? Team{kThreads - 32 * kCopyWarps, 1} : Team{kThreads, 0};
+    const bool copier = early_rows && tid >= tm.n;   // (never true outside rows mode)
     if (kEye == kEyeSmall && rp.row_bg)   // rows mode (the tail of the layout is allocated)
         for (int i = tid; i < rp.R; i += kThreads) sm.sorted_ray16[i] = (unsigned short)rp.grid_sorted_ray[i];
     if (smem_grid) {   // the eye's static tables: nothing else uses this memory in a yaw-only launch
-        for (int i = tid; i <= kPitchLut; i += kThreads) sm.ras.plut[i] = rp.grid_plut[i];
+        for (int i = tid; i <= kPitchLut; i += kThreads) sm.ras.plut[i] = (unsigned short)rp.grid_plut[i];
         for (int i = tid; i < rp.R; i += kThreads) {
             sm.ras.sorted[i] = reinterpret_cast<const float2*>(rp.grid_sorted)[i];
             sm.ras.cell_list[i] = (unsigned short)rp.cells_list[i];
         }
-        for (int i = tid; i <= rp.cells_rows * rp.cells_cols; i += kThreads) sm.ras.cell_start[i] = rp.cells_start[i];
+        for (int i = tid; i <= rp.cells_rows * rp.cells_cols; i += kThreads) sm.ras.cell_start[i] = (unsigned short)rp.cells_start[i];
     }
     long long t_phase[4] = {0, 0, 0, 0};   // project, accel (bins / raster), final ray pass, positions
+#ifdef ISY_RASTER_DETAIL
+    // profiling build: when the last rasterising warp / the last copy warp is done, and the whole phase (replace phases 0..2)
+    __shared__ unsigned long long s_tend[3];
+    if (tid == 0) s_tend[0] = 0, s_tend[1] = 0, s_tend[2] = 0;
+    long long t_rd[3] = {0, 0, 0};
+#endif
 #ifdef ISY_PHASE_DETAIL
     long long t_detail[3] = {0, 0, 0};     // profiling build: cull, projection, raster set-up (replace phases 0..2)
 #endif
@@ -93,21 +118,23 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 
 #ifdef ISY_PHASE_DETAIL
         long long t_sub[1] = {t0};   // end of the cull
-        const int E = smem_grid ? cull_and_project<true>(rp, p, vis, entries, exacts, sm, &s_cull, ahead, ahead_stage, rp.stage_cap, &s_nent, s_band, t_sub)
-                                : cull_and_project<false>(rp, p, vis, entries, exacts, sm, &s_cull, ahead, ahead_stage, rp.stage_cap, &s_nent, s_band, t_sub);
+        int E = copier ? 0 : smem_grid ? cull_and_project<true>(rp, tm, p, vis, entries, exacts, sm, &s_cull, ahead, ahead_stage, rp.stage_cap, &s_nent, s_band, t_sub)
+                                : cull_and_project<false>(rp, tm, p, vis, entries, exacts, sm, &s_cull, ahead, ahead_stage, rp.stage_cap, &s_nent, s_band, t_sub);
         const long long g_detail_t = t_sub[0];
 #else
-        const int E = smem_grid ? cull_and_project<true>(rp, p, vis, entries, exacts, sm, &s_cull, ahead, ahead_stage, rp.stage_cap, &s_nent, s_band)
-                                : cull_and_project<false>(rp, p, vis, entries, exacts, sm, &s_cull, ahead, ahead_stage, rp.stage_cap, &s_nent, s_band);
+        int E = copier ? 0 : smem_grid ? cull_and_project<true>(rp, tm, p, vis, entries, exacts, sm, &s_cull, ahead, ahead_stage, rp.stage_cap, &s_nent, s_band)
+                                : cull_and_project<false>(rp, tm, p, vis, entries, exacts, sm, &s_cull, ahead, ahead_stage, rp.stage_cap, &s_nent, s_band);
 #endif
-        if (tid == 0) s_item_next = pulled;   // (the item after this one: requested when this one started)
+        if (tid == 0) s_item_next = pulled, s_E = E;   // (the item after this one: requested when this one started)
         long long t1 = clock64();
 #ifdef ISY_PHASE_DETAIL
         t_detail[0] += g_detail_t - t0, t_detail[1] += t1 - g_detail_t;
 #endif
         int mode = kModeBrute;
         BinGrid grid;
-        if (!(rp.flags & ISY_FLAG_BRUTE_FORCE) && E <= kMaxE) {
+        if (copier) {
+            mode = kModeRaster;     // (corrected after the group's barrier if the tile overflowed)
+        } else if (!(rp.flags & ISY_FLAG_BRUTE_FORCE) && E <= kMaxE) {
             if (kEye != kEyeAny) {
                 mode = kModeRaster;
             } else if (build_bins(sm, grid, E, s_band, s_warp)) {
@@ -124,7 +151,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 #ifdef ISY_PHASE_DETAIL
             long long t_walk = t3;
 #endif
-            __syncthreads();
+            if (early_rows && grp == split) {   // nothing of an earlier group to wait for: the copy warps go straight to their rows
+                if (!copier) tm.sync();
+            } else {
+                __syncthreads();
+            }
             if (yaw_only && tid < Hcur) {
                 const double hw = wrap_yaw(rp.yaw ? rp.yaw[(size_t)p * rp.H + grp + (size_t)tid * rp.ngroups] : 0.0);
                 sm.head_val[tid] = hw;
@@ -133,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
             // A large eye under a scan plan is rendered band by band (kBandRays consecutive rays, sorted by pitch on
             // their own): each band goes through the shared-memory winner buffer like a small eye.  Everything
             // else is a single pass over all rays.
-            const bool is_raster = kEye != kEyeAny && mode == kModeRaster;
+            bool is_raster = kEye != kEyeAny && mode == kModeRaster;
             const bool walk_bands = banded && is_raster;
             const int nbands = walk_bands ? (rp.R + kBandRays - 1) / kBandRays : 1;
             bool uniform = false;
@@ -144,30 +175,91 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
             long long t3b = clock64();
             if (is_raster) {
                 if (band > 0) __syncthreads();     // the previous band's final pass is done with the buffers
+#if ISY_ROWS_ALL
+                // rows mode: every warp takes its share of the position's rows (sky, responses, templates of hit /
+                // depth / rgb) before anything else: the stores drain while the position is rasterised
+                if (rows_mode) {
+                    if (rp.rows_vec4) copy_rows<float4, true, true>(rp, p, grp, Hcur, 0, kWarps);
+                    else copy_rows<float, true, true>(rp, p, grp, Hcur, 0, kWarps);
+                }
+#endif
+                if (copier) {
+                    // early rows: everything of this group's views that does not depend on where the eye stands
+                    if (rp.rows_vec4) copy_rows<float4, true, true>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
+                    else copy_rows<float, true, true>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
+#ifdef ISY_RASTER_DETAIL
+                    if (lane == 0) atomicMax(&s_tend[1], (unsigned long long)(clock64() - t0));
+#endif
+#if ISY_CULL_AHEAD
+                    // ... then the cull of the NEXT position (the team is past this one's: its lists are filed), so that
+                    // the three dependent trips to L2 of a cull are off the team's critical path
+                    if (ahead_stage && grp == split && rp.T > 0) {
+                        // (the copy warps decide together: the cull has barriers of its own)
+                        const Team cw = Team{kCopyWarps * 32, 2};
+                        cw.sync();
+                        if (tid == tm.n) s_ahead_go = s_join[0] == (int)(item * (unsigned)rp.ngroups + (unsigned)grp) + 1;
+                        cw.sync();
+                        __threadfence_block();
+                        const unsigned int nxt = *reinterpret_cast<volatile unsigned int*>(&s_item_next);
+                        if (s_ahead_go && nxt < (unsigned)rp.items) {
+                            const int gt = tid - tm.n;
+                            cull_position(rp, Team{kCopyWarps * 32, 2}, (int)(nxt / (rp.splits * rp.ray_splits)), gt, vis, ahead_stage,
+                                          rp.stage_cap, s_cull_ahead);
+                            if (gt == 0) s_ahead_item = nxt;
+                        }
+                    }
+#endif
+                    // ... then the rasterisation, if the team has the copies filed by now
+                    if (s_join[0] == (int)(item * (unsigned)rp.ngroups + (unsigned)grp) + 1) {
+                        __threadfence_block();
+                        const int how = s_join[1];
+                        E = s_join[2];
+                        int tcap;
+                        if (how == 1) raster_tiles(rp, sm, exacts, tile_lists(sm, E, rp.ngroups == rp.splits, tcap), Hcur, &s_count, r_n, (unsigned)r_lo);
+                        else if (how == 2) raster_copies<true>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo);
+                        else raster_copies<false>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo);
+                    }
+                } else {
                 if (best_smem) {
                     unsigned int* b32 = reinterpret_cast<unsigned int*>(sm.ras.best);
-                    for (int i = tid; i < (Hcur * r_n + 1) / 2; i += kThreads) b32[i] = 0xffffffffu;
+                    for (int i = tid; i < (Hcur * r_n + 1) / 2; i += tm.n) b32[i] = 0xffffffffu;
                 } else {
-                    for (int i = tid; i < Hcur * rp.R; i += kThreads) gbest[i] = kNoCopy;
+                    for (int i = tid; i < Hcur * rp.R; i += tm.n) gbest[i] = kNoCopy;
                 }
                 if (walk_bands) {                  // this band's sorted rays and pitch look-up table
                     const float2* gs = reinterpret_cast<const float2*>(rp.grid_sorted) + r_lo;
-                    for (int i = tid; i < r_n; i += kThreads) sm.ras.sorted[i] = gs[i];
+                    for (int i = tid; i < r_n; i += tm.n) sm.ras.sorted[i] = gs[i];
                     const unsigned int* gp = rp.grid_plut + (size_t)band * (kPitchLut + 1);
-                    for (int i = tid; i <= kPitchLut; i += kThreads) sm.ras.plut[i] = gp[i];
+                    for (int i = tid; i <= kPitchLut; i += tm.n) sm.ras.plut[i] = (unsigned short)gp[i];
                 }
-                __syncthreads();
+                tm.sync();
                 if (tid == 0) s_count = 0;     // (the cull's counter is free again: next copy to rasterise)
-                if (band == 0) uniform = sort_headings(sm, Hcur);
+                if (band == 0) uniform = sort_headings(sm, tm, Hcur);
                 if (walk_bands) band_runs(sm, E);
-                __syncthreads();
+                const bool scan = kEye == kEyeSmall ? Hcur > kSmallH : walk_bands;
+                bool tiles = false;
+                int tcap = 0;
+                const unsigned short* const tlist = tile_lists(sm, E, !walk_bands && rp.ngroups == rp.splits, tcap);
+                if (scan && uniform) {
+                    build_phases(rp, sm, tm, Hcur, r_n, (unsigned)r_lo);   // (cached while the headings stay the same)
+                    tm.sync();
+                    tiles = !(rp.flags & ISY_FLAG_NO_TILES) && bin_copies(sm, tm, E, Hcur, r_n, s_warp, const_cast<unsigned short*>(tlist), tcap);
+                }
+                tm.sync();
+                if (early_rows && tid == 0) {   // the copy warps may join
+                    s_join[1] = tiles ? 1 : (uniform ? 2 : 3), s_join[2] = E;
+                    __threadfence_block();
+                    s_join[0] = (int)(item * (unsigned)rp.ngroups + (unsigned)grp) + 1;
+                }
 #ifdef ISY_PHASE_DETAIL
                 t_walk = clock64();
 #endif
                 // rows mode: the copy warps write the sky rows now and the template rows of hit / depth / rgb when
                 // kLateCopies copies are left (scans) -- the later, the likelier the patches find them in L2
-                const bool scan = kEye == kEyeSmall ? Hcur > kSmallH : walk_bands;
-                const bool copy_warp = rows_mode && warp >= kWarps - kCopyWarps;
+                const bool copy_warp = !ISY_ROWS_ALL && rows_mode && !early_rows && warp >= kWarps - kCopyWarps;
+#ifdef ISY_RASTER_DETAIL
+                const long long t_rd0 = early_rows ? t0 : clock64();
+#endif
                 if (copy_warp) {
                     if (rp.rows_vec4) copy_rows<float4, true, false>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
                     else copy_rows<float, true, false>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
@@ -177,30 +269,54 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                         const unsigned int nxt = s_item_next;
                         if (nxt < (unsigned)rp.items) {
                             const int gt = tid - (kWarps - kCopyWarps) * 32;
-                            cull_position<kCopyWarps * 32, 1>(rp, (int)(nxt / (rp.splits * rp.ray_splits)), gt, vis, ahead_stage, rp.stage_cap,
-                                                              s_cull_ahead);
+                            cull_position(rp, Team{kCopyWarps * 32, 2}, (int)(nxt / (rp.splits * rp.ray_splits)), gt, vis, ahead_stage,
+                                          rp.stage_cap, s_cull_ahead);
                             if (gt == 0) s_ahead_item = nxt;
                         }
                     }
 #endif
                     if (scan) {
                         const int half = max(E - kLateCopies, 0);
-                        if (uniform) raster_copies<true>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo, half);
+                        if (tiles) raster_tiles(rp, sm, exacts, tlist, Hcur, &s_count, r_n, (unsigned)r_lo, (((r_n + kTileRays - 1) >> kTileShift) * Hcur * kLateTiles) >> 8);
+                        else if (uniform) raster_copies<true>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo, half);
                         else raster_copies<false>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo, half);
                     }
                     if (rp.rows_vec4) copy_rows<float4, false, true>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
                     else copy_rows<float, false, true>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
                 }
+#ifdef ISY_RASTER_DETAIL
+                if (copy_warp && lane == 0) atomicMax(&s_tend[1], (unsigned long long)(clock64() - t_rd0));
+#endif
                 if (scan) {
-                    if (uniform) raster_copies<true>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo);
+                    if (tiles) raster_tiles(rp, sm, exacts, tlist, Hcur, &s_count, r_n, (unsigned)r_lo);
+                    else if (uniform) raster_copies<true>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo);
                     else raster_copies<false>(rp, sm, exacts, E, Hcur, &s_count, r_n, (unsigned)r_lo);
+#ifdef ISY_RASTER_DETAIL
+                    if (lane == 0 && !copy_warp) {
+                        atomicMax(&s_tend[0], (unsigned long long)(clock64() - t_rd0));
+                        atomicAdd(&s_tend[2], (unsigned long long)(clock64() - t_rd0));
+                    }
+#endif
                 } else if (kEye == kEyeSmall) {
                     raster_cells<true>(rp, sm, gbest, exacts, E, Hcur, &s_count);
                 } else {   // large eye, one heading at a time
                     raster_cells<false>(rp, sm, gbest, exacts, E, Hcur, &s_count);
                 }
+                }   // (the team)
             }
             __syncthreads();
+#ifdef ISY_RASTER_DETAIL
+            // max end of the rasterising warps, end of the copy warps' rows, mean end of the rasterising warps
+            if (tid == 0) {
+                t_rd[0] += s_tend[0], t_rd[1] += s_tend[1], t_rd[2] += s_tend[2] / (kWarps - ((rows_mode && !ISY_ROWS_ALL) ? kCopyWarps : 0));
+                s_tend[0] = 0, s_tend[1] = 0, s_tend[2] = 0;
+            }
+#endif
+            if (copier) {   // what the team found
+                E = s_E;
+                mode = E <= kMaxE ? kModeRaster : kModeBrute;
+                is_raster = kEye != kEyeAny && mode == kModeRaster;
+            }
             long long t4 = clock64();
             t_phase[1] += t4 - t3b;
 #ifdef ISY_PHASE_DETAIL
@@ -377,6 +493,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
     if (tid == 0) {
 #ifdef ISY_PHASE_DETAIL
         for (int k = 0; k < 3; ++k) t_phase[k] = t_detail[k];
+#endif
+#ifdef ISY_RASTER_DETAIL
+        for (int k = 0; k < 3; ++k) t_phase[k] = t_rd[k];
 #endif
         for (int k = 0; k < 4; ++k) atomicAdd(&rp.phase_cycles[k], (unsigned long long)t_phase[k]);
     }

@@ -141,11 +141,13 @@ class Renderer(object):
         return self._workspace
 
     def render(self, pos, yaw=None, quat=None, sun=None, outputs=("rgb", "Y", "dop", "aop"), init_from_sky=False,
-               brute_force=False, f64=False, out=None, sky=None, per_view_sky=False, sensor=None, irgbu=None):
+               brute_force=False, f64=False, out=None, sky=None, per_view_sky=False, sensor=None, irgbu=None,
+               no_tiles=False):
         """
         irgbu: (rows, 5) spectral weights: the luminance of every view goes through spectrum_influence(y, irgbu).sum(axis=1)
         as `Sky.__call__(ori, irgbu=...)` does per call (sky.py:342-344); rows = 1 or a divisor of the ommatidia count.
         per_view_sky: evaluate the sky for every view even when all positions share their headings (cross-check).
+        no_tiles: rasterise evenly spaced scans copy by copy instead of tile by tile (cross-check).
         sensor: _lib.SensorParams for the "resp" output -- (B,N,3) photoreceptor responses, or (B,N) PN inputs with
         channels=1 (include/isy_b200.h, isy_sensor_params).
         pos (P,3) metres; yaw (P,H) radians about +Z *or* quat (P,H,4) full eye orientations;
@@ -183,6 +185,8 @@ class Renderer(object):
             flags |= _lib.FLAG_BRUTE_FORCE
         if per_view_sky:
             flags |= _lib.FLAG_PER_VIEW_SKY
+        if no_tiles:
+            flags |= _lib.FLAG_NO_TILES
         if f64:
             flags |= _lib.FLAG_OUT_F64
         fdt = torch.float64 if f64 else torch.float32

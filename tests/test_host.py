@@ -31,7 +31,7 @@ def test_flag_constants_match_the_header():
     flags = {m.group(1): 1 << int(m.group(2)) for m in re.finditer(r"\b(ISY_FLAG_[A-Z_0-9]+)\s*=\s*1\s*<<\s*(\d+)", header)}
     assert flags == {"ISY_FLAG_INIT_FROM_SKY": _lib.FLAG_INIT_FROM_SKY, "ISY_FLAG_BRUTE_FORCE": _lib.FLAG_BRUTE_FORCE,
                      "ISY_FLAG_SUN_PER_VIEW": _lib.FLAG_SUN_PER_VIEW, "ISY_FLAG_OUT_F64": _lib.FLAG_OUT_F64,
-                     "ISY_FLAG_PER_VIEW_SKY": _lib.FLAG_PER_VIEW_SKY}
+                     "ISY_FLAG_PER_VIEW_SKY": _lib.FLAG_PER_VIEW_SKY, "ISY_FLAG_NO_TILES": _lib.FLAG_NO_TILES}
 
 
 def test_product_never_imports_the_oracle():
