@@ -107,6 +107,31 @@ static_assert(sizeof(SmemLayout) <= 224 * 1024, "rows mode: 227 KB per CTA is th
 constexpr int kTileListCap = (int)((sizeof(float4) + sizeof(unsigned short)) * kMaxE / sizeof(unsigned short));   // 10 368 entries
 static_assert(offsetof(SmemLayout, order) == offsetof(SmemLayout, bbox) + sizeof(float4) * kMaxE, "the tile lists span bbox + order");
 
+// ---- tile walk (isy_raster.cuh): tiles of kTileRays consecutive pitch-sorted rays x one azimuth column
+#ifndef ISY_BIN_SOLO
+#define ISY_BIN_SOLO 8
+#endif
+#ifndef ISY_TILE_U
+#define ISY_TILE_U 2
+#endif
+constexpr int kBinSolo = ISY_BIN_SOLO;       // a copy that touches up to this many tiles is filed by its own lane
+constexpr int kTileU = ISY_TILE_U;           // queries per lane in a tile
+constexpr int kTileRays = 32 * kTileU, kTileShift = kTileU == 1 ? 5 : (kTileU == 2 ? 6 : 7);
+static_assert(kTileU == 1 || kTileU == 2 || kTileU == 4, "tiles of 32, 64 or 128 rays");
+
+// place of chunk q in the walk's queue: the chunks at and above the horizon (the middle of a pitch-sorted eye) hold
+// nearly all the work and go first, from the horizon upwards; the chunks below it follow
+__device__ __forceinline__ int chunk_place(int q, int q_h) { return q <= q_h ? q_h - q : q; }
+
+// columns of a copy with azimuth box [plo, phi] (margin included): (first + 1) | (number << 8); -1 and H alias H - 1 and 0
+__device__ __forceinline__ unsigned int copy_columns(float plo, float phi, float inv_delta, int Hcur) {
+    const float pi_f = (float)kPi;
+    const float glo = fmaxf(plo, -pi_f - kBinMargin) - kBinMargin, ghi = fminf(phi, pi_f + kBinMargin) + kBinMargin;
+    if (!(glo <= ghi)) return 0u;
+    const int c_lo = (int)floorf((glo + pi_f) * inv_delta), c_hi = (int)floorf((ghi + pi_f) * inv_delta);
+    return (unsigned)(c_lo + 1) | ((unsigned)min(c_hi - c_lo + 1, Hcur) << 8);
+}
+
 struct RayOut {
     double r, g, b;
     double Y, P, A;

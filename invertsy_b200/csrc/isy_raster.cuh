@@ -337,17 +337,6 @@ __device__ __forceinline__ void column_chunk(const RenderParams& rp, SmemLayout&
 // The fp32 query azimuth is fl(phase + column offset): three roundings (< 2.5e-7) + 7.5e-7 between h0 + k*delta and
 // the true heading: inside the 1.9e-6 that kEdgeEps admits for it (isy_common.cuh).
 // ------------------------------------------------------------------------------------------
-#ifndef ISY_BIN_SOLO
-#define ISY_BIN_SOLO 8
-#endif
-#ifndef ISY_TILE_U
-#define ISY_TILE_U 2
-#endif
-constexpr int kBinSolo = ISY_BIN_SOLO;       // a copy that touches up to this many tiles is filed by its own lane
-constexpr int kTileU = ISY_TILE_U;           // queries per lane in a tile
-constexpr int kTileRays = 32 * kTileU, kTileShift = kTileU == 1 ? 5 : (kTileU == 2 ? 6 : 7);
-static_assert(kTileU == 1 || kTileU == 2 || kTileU == 4, "tiles of 32, 64 or 128 rays");
-
 // one lane of the warp takes n items from a shared-memory counter (elect.sync keeps ptxas from wrapping the atomic
 // into its warp-aggregation sequence); returns the first to every lane
 __device__ __forceinline__ int warp_fetch(int* counter, int n) {
@@ -361,25 +350,42 @@ __device__ __forceinline__ int warp_fetch(int* counter, int n) {
 template <bool kFill>
 __device__ __forceinline__ void bin_add(SmemLayout& sm, unsigned short* tlist, int tile, int e) {
     ISY_BOUND(tile >= 0 && tile < kMaxTiles);
-    const int at = smem_atomic_add(reinterpret_cast<int*>(&sm.ras.tile_cnt[tile]), 1);
+    const unsigned int a = (unsigned int)__cvta_generic_to_shared(&sm.ras.tile_cnt[tile]);
     if (kFill) {
+        int at;
+        asm volatile("atom.shared.add.s32 %0, [%1], 1;" : "=r"(at) : "r"(a) : "memory");
         ISY_BOUND(at >= 0 && at < kMaxE * 24);
+#ifdef ISY_DEBUG_BOUNDS
+        if (at < 0 || at >= kMaxE * 24) return;
+#endif
         tlist[at] = (unsigned short)(e * (int)sizeof(Entry));
+    } else {
+        asm volatile("red.shared.add.s32 [%0], 1;" ::"r"(a) : "memory");    // counting: nothing comes back
     }
 }
 
-// place of chunk q in the walk's queue: the chunks at and above the horizon (the middle of a pitch-sorted eye) hold
-// nearly all the work and go first, from the horizon upwards; the chunks below it follow
-__device__ __forceinline__ int chunk_place(int q, int q_h) { return q <= q_h ? q_h - q : q; }
-
+// One pass over the copies: kFill = false works out the columns of every copy (from its box, which the lists may
+// overwrite later) and counts the copies of every tile; kFill = true files them.  A copy that touches a few tiles is
+// filed by its own lane, larger ones by the warp together, a tile per lane.  Lane l of warp w takes copies
+// l * (warps) + w, ...: neighbouring slots hold neighbouring triangles -- the large copies of a tussock next to the
+// eye come in runs -- and this way every warp gets its share of them.
 template <bool kFill>
 __device__ void bin_pass(SmemLayout& sm, const Team& tm, int E, int Hcur, int q_h, unsigned short* tlist) {
-    const int lane = threadIdx.x & 31;
-    for (int base = (int)(threadIdx.x >> 5) * 32; base < E; base += tm.n) {   // warp-uniform trip count
-        const int e = base + lane;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = tm.n >> 5;
+    const float inv_delta = sm.ras.uni[2];
+    for (int base = 0; base < E; base += tm.n) {   // warp-uniform trip count
+        const int e = base + lane * nw + warp;
         int q0 = 0, nq = 0, c0 = 0, nc = 0;
         if (e < E) {
-            const unsigned int jr = sm.jrange[e], cr = sm.ras.crange[e];
+            unsigned int cr;
+            if (kFill) {
+                cr = sm.ras.crange[e];
+            } else {
+                const float4 bb = sm.bbox[e];
+                cr = copy_columns(bb.z, bb.w, inv_delta, Hcur);
+                sm.ras.crange[e] = (unsigned short)cr;
+            }
+            const unsigned int jr = sm.jrange[e];
             const unsigned jbeg = jr & 0xffffu, jend = jr >> 16;
             if (jbeg < jend)
                 q0 = (int)(jbeg >> kTileShift), nq = (int)((jend - 1) >> kTileShift) - q0 + 1, c0 = (int)(cr & 0xffu) - 1, nc = (int)(cr >> 8);
@@ -399,7 +405,7 @@ __device__ void bin_pass(SmemLayout& sm, const Team& tm, int E, int Hcur, int q_
         while (big) {
             const int src = __ffs(big) - 1;
             big &= big - 1;
-            const int be = base + src, bq0 = __shfl_sync(0xffffffffu, q0, src), bc0 = __shfl_sync(0xffffffffu, c0, src);
+            const int be = base + src * nw + warp, bq0 = __shfl_sync(0xffffffffu, q0, src), bc0 = __shfl_sync(0xffffffffu, c0, src);
             const int bnc = __shfl_sync(0xffffffffu, nc, src), bnt = __shfl_sync(0xffffffffu, nt, src);
             const float rnc = 1.0f / (float)bnc;
             for (int t = lane; t < bnt; t += 32) {
@@ -427,26 +433,17 @@ __device__ __forceinline__ unsigned short* tile_lists(SmemLayout& sm, int E, boo
 }
 
 __device__ bool bin_copies(SmemLayout& sm, const Team& tm, int E, int Hcur, int Rrow, unsigned int* s_warp, unsigned short* tlist,
-                           int cap) {
+                           int cap, long long* tdbg = nullptr) {
+    const long long td0 = clock64();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NQ = (Rrow + kTileRays - 1) >> kTileShift, NT = NQ * Hcur, q_h = min(NQ - 1, NQ / 2);
     ISY_BOUND(NT <= kMaxTiles && NT <= 2 * tm.n);
-    const float pi_f = (float)kPi, inv_delta = sm.ras.uni[2];
     for (int i = tid; i <= NT; i += tm.n) sm.ras.tile_cnt[i] = 0;
-    for (int e = tid; e < E; e += tm.n) {          // the columns of each copy (the lists will overwrite the boxes)
-        const float4 bb = sm.bbox[e];
-        const float glo = fmaxf(bb.z, -pi_f - kBinMargin) - kBinMargin, ghi = fminf(bb.w, pi_f + kBinMargin) + kBinMargin;
-        unsigned int cr = 0;
-        if (glo <= ghi) {
-            const int c_lo = (int)floorf((glo + pi_f) * inv_delta), c_hi = (int)floorf((ghi + pi_f) * inv_delta);
-            ISY_BOUND(c_lo >= -1 && c_hi <= Hcur);
-            cr = (unsigned)(c_lo + 1) | ((unsigned)min(c_hi - c_lo + 1, Hcur) << 8);   // -1 and H alias H - 1 and 0
-        }
-        sm.ras.crange[e] = (unsigned short)cr;
-    }
     tm.sync();
     bin_pass<false>(sm, tm, E, Hcur, q_h, tlist);
+    const long long td1 = clock64();
     tm.sync();
+    const long long td2 = clock64();
     // exclusive scan of the counts (two tiles per thread)
     const int i0 = 2 * tid;
     const unsigned a = i0 < NT ? sm.ras.tile_cnt[i0] : 0u, b = i0 + 1 < NT ? sm.ras.tile_cnt[i0 + 1] : 0u;
@@ -470,7 +467,9 @@ __device__ bool bin_copies(SmemLayout& sm, const Team& tm, int E, int Hcur, int 
     if (i0 < NT) sm.ras.tile_cnt[i0] = excl;
     if (i0 + 1 < NT) sm.ras.tile_cnt[i0 + 1] = excl + a;
     tm.sync();
+    const long long td3 = clock64();
     bin_pass<true>(sm, tm, E, Hcur, q_h, tlist);      // tile_cnt[t] ends as the END of tile t's list
+    if (tdbg) tdbg[0] += td1 - td0, tdbg[1] += td2 - td1, tdbg[2] += clock64() - td3;   // (profiling: count, wait, fill of thread 0)
     return true;
 }
 
@@ -577,6 +576,9 @@ __device__ void raster_tiles(const RenderParams& rp, SmemLayout& sm, const Exact
         for (int t = t0; t < t1; ++t) {
             const unsigned i1 = sm.ras.tile_cnt[t], i0 = t ? sm.ras.tile_cnt[t - 1] : 0u;
             if (i0 == i1) continue;
+#ifdef ISY_DEBUG_BOUNDS
+            if (i1 < i0 || i1 > (unsigned)(kMaxE * 24)) { ISY_BOUND(false); continue; }   // (keep the debug build alive)
+#endif
             // place t of the queue -> tile (q, c)
             const int tq = (int)(((float)t + 0.5f) * rH), c = t - tq * Hcur, q = chunk_place(tq, q_h);   // (its own inverse)
             ISY_BOUND(q >= 0 && q < NQ && c >= 0 && c < Hcur && i1 <= (unsigned)(kMaxE * 24));

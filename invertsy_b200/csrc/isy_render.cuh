@@ -96,6 +96,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
     if (tid == 0) s_tend[0] = 0, s_tend[1] = 0, s_tend[2] = 0;
     long long t_rd[3] = {0, 0, 0};
 #endif
+#ifdef ISY_SETUP_DETAIL
+    long long t_sd[3] = {0, 0, 0};         // profiling build: clear + heading sort, phases, (phases +) filing of the copies
+#endif
 #ifdef ISY_PHASE_DETAIL
     long long t_detail[3] = {0, 0, 0};     // profiling build: cull, projection, raster set-up (replace phases 0..2)
 #endif
@@ -237,15 +240,28 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
                 if (band == 0) uniform = sort_headings(sm, tm, Hcur);
                 if (walk_bands) band_runs(sm, E);
                 const bool scan = kEye == kEyeSmall ? Hcur > kSmallH : walk_bands;
+#ifdef ISY_SETUP_DETAIL
+                const long long t_sd1 = clock64();
+#endif
                 bool tiles = false;
                 int tcap = 0;
                 const unsigned short* const tlist = tile_lists(sm, E, !walk_bands && rp.ngroups == rp.splits, tcap);
                 if (scan && uniform) {
                     build_phases(rp, sm, tm, Hcur, r_n, (unsigned)r_lo);   // (cached while the headings stay the same)
                     tm.sync();
-                    tiles = !(rp.flags & ISY_FLAG_NO_TILES) && bin_copies(sm, tm, E, Hcur, r_n, s_warp, const_cast<unsigned short*>(tlist), tcap);
+#if defined(ISY_SETUP_DETAIL) && !defined(ISY_BIN_DETAIL)
+                    t_sd[1] += clock64() - t_sd1;
+#endif
+                    tiles = !(rp.flags & ISY_FLAG_NO_TILES) && bin_copies(sm, tm, E, Hcur, r_n, s_warp, const_cast<unsigned short*>(tlist), tcap
+#ifdef ISY_BIN_DETAIL
+                                                                            , t_sd
+#endif
+                                                                            );
                 }
                 tm.sync();
+#if defined(ISY_SETUP_DETAIL) && !defined(ISY_BIN_DETAIL)
+                t_sd[0] += t_sd1 - t3b, t_sd[2] += clock64() - t_sd1;
+#endif
                 if (early_rows && tid == 0) {   // the copy warps may join
                     s_join[1] = tiles ? 1 : (uniform ? 2 : 3), s_join[2] = E;
                     __threadfence_block();
@@ -496,6 +512,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 #endif
 #ifdef ISY_RASTER_DETAIL
         for (int k = 0; k < 3; ++k) t_phase[k] = t_rd[k];
+#endif
+#ifdef ISY_SETUP_DETAIL
+        for (int k = 0; k < 3; ++k) t_phase[k] = t_sd[k];
 #endif
         for (int k = 0; k < 4; ++k) atomicAdd(&rp.phase_cycles[k], (unsigned long long)t_phase[k]);
     }
