@@ -365,10 +365,10 @@ __device__ __forceinline__ void bin_add(SmemLayout& sm, unsigned short* tlist, i
 }
 
 // One pass over the copies: kFill = false works out the columns of every copy (from its box, which the lists may
-// overwrite later) and counts the copies of every tile; kFill = true files them.  A copy that touches a few tiles is
-// filed by its own lane, larger ones by the warp together, a tile per lane.  Lane l of warp w takes copies
+// overwrite later) and counts the copies of every tile; kFill = true files them.  Lane l of warp w takes copies
 // l * (warps) + w, ...: neighbouring slots hold neighbouring triangles -- the large copies of a tussock next to the
-// eye come in runs -- and this way every warp gets its share of them.
+// eye come in runs -- and this way every warp gets its share of them.  The (copy, tile) pairs of a warp's 32 copies
+// are then lined up by a prefix sum and dealt one per lane and trip, whatever the sizes of the copies.
 template <bool kFill>
 __device__ void bin_pass(SmemLayout& sm, const Team& tm, int E, int Hcur, int q_h, unsigned short* tlist) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = tm.n >> 5;
@@ -390,36 +390,39 @@ __device__ void bin_pass(SmemLayout& sm, const Team& tm, int E, int Hcur, int q_
             if (jbeg < jend)
                 q0 = (int)(jbeg >> kTileShift), nq = (int)((jend - 1) >> kTileShift) - q0 + 1, c0 = (int)(cr & 0xffu) - 1, nc = (int)(cr >> 8);
         }
-        const int nt = nq * nc;
-        if (nt > 0 && nt <= kBinSolo) {
-            int c = c0 < 0 ? c0 + Hcur : c0, q = q0, tq = chunk_place(q, q_h) * Hcur, k = 0;
-            for (int i = 0; i < nt; ++i) {
-                bin_add<kFill>(sm, tlist, tq + c, e);
-                ++k, ++c;
-                if (c >= Hcur) c -= Hcur;
-                if (k == nc) k = 0, c = c0 < 0 ? c0 + Hcur : c0, ++q, tq = chunk_place(q, q_h) * Hcur;
-            }
+        const unsigned nt = (unsigned)(nq * nc);
+        const float rnc = 1.0f / (float)max(nc, 1);
+        unsigned inc = nt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += v;
         }
-        // larger copies: the warp files them together, a tile per lane
-        unsigned int big = __ballot_sync(0xffffffffu, nt > kBinSolo);
-        while (big) {
-            const int src = __ffs(big) - 1;
-            big &= big - 1;
-            const int be = base + src * nw + warp, bq0 = __shfl_sync(0xffffffffu, q0, src), bc0 = __shfl_sync(0xffffffffu, c0, src);
-            const int bnc = __shfl_sync(0xffffffffu, nc, src), bnt = __shfl_sync(0xffffffffu, nt, src);
-            const float rnc = 1.0f / (float)bnc;
-            for (int t = lane; t < bnt; t += 32) {
-                const int dq = (int)(((float)t + 0.5f) * rnc);        // t / bnc, exact for these sizes
-                int c = bc0 + (t - dq * bnc);
+        const unsigned total = __shfl_sync(0xffffffffu, inc, 31), exc = inc - nt;
+        for (unsigned tb = 0; tb < total; tb += 32) {          // warp-uniform trip count
+            const unsigned t = tb + lane;
+            int k = 0;                                         // the lane whose copy holds pair t: smallest k with inc_k > t
+#pragma unroll
+            for (int b2 = 16; b2 > 0; b2 >>= 1) {
+                const unsigned v = __shfl_sync(0xffffffffu, inc, k + b2 - 1);
+                if (v <= t) k += b2;
+            }
+            k = min(k, 31);
+            const unsigned ek = __shfl_sync(0xffffffffu, exc, k);
+            const int se = __shfl_sync(0xffffffffu, e, k), sq0 = __shfl_sync(0xffffffffu, q0, k);
+            const int sc0 = __shfl_sync(0xffffffffu, c0, k), snc = __shfl_sync(0xffffffffu, nc, k);
+            const float srnc = __shfl_sync(0xffffffffu, rnc, k);
+            if (t < total) {
+                const int i = (int)(t - ek);
+                const int dq = (int)(((float)i + 0.5f) * srnc);        // i / snc, exact for these sizes
+                int c = sc0 + (i - dq * snc);
                 c = c < 0 ? c + Hcur : (c >= Hcur ? c - Hcur : c);
-                bin_add<kFill>(sm, tlist, chunk_place(bq0 + dq, q_h) * Hcur + c, be);
+                bin_add<kFill>(sm, tlist, chunk_place(sq0 + dq, q_h) * Hcur + c, se);
             }
         }
     }
 }
 
-// files the E copies of the position into the tiles of Rrow rays x Hcur columns; false (to every thread): the lists
-// do not fit.  Called by the whole team; the lists are complete after the callers' next barrier.
 // where a position's tile lists go: over bbox + order when nothing needs the boxes any more (one group of headings,
 // no bands), else into what the E copies leave free of the Entry tile
 __device__ __forceinline__ unsigned short* tile_lists(SmemLayout& sm, int E, bool boxes_free, int& cap) {
