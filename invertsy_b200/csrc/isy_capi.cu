@@ -579,8 +579,9 @@ int launch_render(const isy_world* w, const isy_eye* e, int64_t P, int64_t H, co
         }
         rp.slab_stage = ISY_CULL_AHEAD ? (float*)(base + pl.off_stage) : nullptr, rp.stage_cap = pl.stage_cap;
     }
-    const size_t smem = rp.row_bg ? sizeof(SmemLayout) : kSmemBase;   // (rows mode adds the tail of the layout)
     const int eye_kind = (vquat || !e->d_sorted) ? kEyeAny : (pl.global_best ? kEyeLarge : kEyeSmall);
+    // (rows mode adds the tail of the layout; launches whose heading groups are scans add the scan tables before it)
+    const size_t smem = rp.row_bg ? sizeof(SmemLayout) : ((eye_kind != kEyeAny && rp.Hg > kSmallH) ? kSmemScan : kSmemBase);
     const bool f64 = (flags & ISY_FLAG_OUT_F64) != 0;
 #define ISY_LAUNCH(F64, EYE)                                                                                              \
     do {                                                                                                                  \

@@ -278,13 +278,41 @@ fam_recheck_kernel(const float* __restrict__ queries, long long ldq, const float
     const bool vec = (K & 3) == 0 && (ldq & 3) == 0 && (lds & 3) == 0 && ((uintptr_t)queries & 15) == 0 && ((uintptr_t)stored & 15) == 0;
     float best = __int_as_float(0x7f800000), xx = 0.f, margin = __int_as_float(0x7f800000);
     int best_i = -1;
+    // Vectors of up to 1024 floats (the usual eye): the query is read ONCE, eight 16-byte loads per lane issued
+    // together (the kernel streams the queries from HBM: what bounds it is how many bytes a warp has in flight), and kept
+    // in registers for all its candidates.  The sums run over the same elements in the same order as the general path.
+    constexpr int kQV = 8;
+    const int K4 = K >> 2;
+    const bool in_regs = vec && K4 <= 32 * kQV;
+    float4 xa[kQV];
+    if (in_regs) {
+#pragma unroll
+        for (int u = 0; u < kQV; ++u) {
+            const int k = lane + 32 * u;
+            xa[u] = k < K4 ? __ldg(reinterpret_cast<const float4*>(x) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
 #pragma unroll
     for (int t = 0; t < kTopK; ++t) {
         const int m = c[t];
         if (m < 0 || v[t] > v[0] + margin) continue;           // (warp-uniform: the candidates are the query's)
         const float* y = stored + (size_t)m * lds;
         float s0 = 0.f, s1 = 0.f, n0 = 0.f;
-        if (vec) {
+        if (in_regs) {
+            float4 yb[kQV];
+#pragma unroll
+            for (int u = 0; u < kQV; ++u) {
+                const int k = lane + 32 * u;
+                yb[u] = k < K4 ? __ldg(reinterpret_cast<const float4*>(y) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < kQV; ++u) {      // (elements beyond K are zeros in both: they leave the sums as they are)
+                const float4 a = xa[u], b = yb[u];
+                const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+                s0 = fmaf(d0, d0, s0), s1 = fmaf(d1, d1, s1), s0 = fmaf(d2, d2, s0), s1 = fmaf(d3, d3, s1);
+                if (t == 0) n0 = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, n0))));
+            }
+        } else if (vec) {
             const float4* x4 = reinterpret_cast<const float4*>(x);
             const float4* y4 = reinterpret_cast<const float4*>(y);
             for (int k = lane; k < (K >> 2); k += 32) {

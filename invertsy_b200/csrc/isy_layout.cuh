@@ -66,6 +66,11 @@ struct SmemRaster {
     float uni[4];                     // {h0, delta, 1/delta, flag}: sorted headings are h0 + k*delta over the full circle
     unsigned short cell_start[kCellsSmem + 4];    // the eye's static (pitch, yaw) ray grid: first list entry of each cell
     unsigned short cell_list[kGridRaysSmem];      // ... and the pitch-sorted positions of the rays in each cell
+};
+
+// Scans with evenly spaced headings (column walk / tile walk, isy_raster.cuh).  Launches that cannot scan -- single views,
+// routes, general orientations -- do not allocate it: what they leave of the 228 KB is their L1.
+struct SmemScan {
     // column walk (evenly spaced headings h0 + k*delta): the query azimuth of (ray j, sorted heading k) is
     // phase[j] + c*delta - pi in column c = (colb[j] + k) mod H -- every column holds every ray exactly once
     float phase[kGridRaysSmem];       // yaw_j + h0 + pi folded into [0, delta)
@@ -94,14 +99,16 @@ struct SmemLayout {
         SmemBins bins;
         SmemRaster ras;
     };
+    SmemScan scan;                    // (launches whose groups hold more than kSmallH headings)
     // rows mode only (isy_shade.cuh): what final_pass_patch looks up per hit, so that it issues no global load.
     // Launches that are not in rows mode do not allocate this tail (kSmemBase bytes of dynamic shared memory).
     float rgb[kMaxE * 3];                         // colour of each copy's triangle
     unsigned short sorted_ray16[kGridRaysSmem];   // ray index of each pitch-sorted position
     float resp1[kMaxE];                           // PN response of a ray that hits each copy's triangle (out.resp, 1 channel)
 };
-constexpr size_t kSmemBase = offsetof(SmemLayout, rgb);
-static_assert(kSmemBase <= 200 * 1024, "leave some of the 228 KB for L1");
+constexpr size_t kSmemBase = offsetof(SmemLayout, scan);   // no scans, no rows mode
+constexpr size_t kSmemScan = offsetof(SmemLayout, rgb);    // scans, per-view final passes
+static_assert(kSmemBase <= 192 * 1024, "leave some of the 228 KB for L1");
 static_assert(sizeof(SmemLayout) <= 224 * 1024, "rows mode: 227 KB per CTA is the limit");
 
 constexpr int kTileListCap = (int)((sizeof(float4) + sizeof(unsigned short)) * kMaxE / sizeof(unsigned short));   // 10 368 entries

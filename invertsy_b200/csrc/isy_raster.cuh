@@ -237,7 +237,7 @@ __device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& s
 // ------------------------------------------------------------------------------------------
 __device__ void build_phases(const RenderParams& rp, SmemLayout& sm, const Team& tm, int Hcur, int r_n, unsigned jbase) {
     const double h0 = sm.head_val[sm.ras.hperm[0]];
-    const bool same = sm.ras.ph_H == Hcur && sm.ras.ph_lo == (int)jbase && sm.ras.ph_h0 == h0;
+    const bool same = sm.scan.ph_H == Hcur && sm.scan.ph_lo == (int)jbase && sm.scan.ph_h0 == h0;
     tm.sync();
     if (same) return;
     const double delta = kTwoPi / (double)Hcur, inv = (double)Hcur / kTwoPi;
@@ -249,11 +249,11 @@ __device__ void build_phases(const RenderParams& rp, SmemLayout& sm, const Team&
         else if (phi >= delta) phi -= delta, b += 1.0;
         int bm = (int)b % Hcur;
         if (bm < 0) bm += Hcur;
-        sm.ras.phase[j] = (float)phi;
-        sm.ras.colb[j] = (unsigned char)bm;
+        sm.scan.phase[j] = (float)phi;
+        sm.scan.colb[j] = (unsigned char)bm;
     }
-    for (int i = threadIdx.x; i < Hcur + 2; i += tm.n) sm.ras.coloff[i] = (float)((double)(i - 1) * delta - kPi);
-    if (threadIdx.x == 0) sm.ras.ph_H = Hcur, sm.ras.ph_lo = (int)jbase, sm.ras.ph_h0 = h0;
+    for (int i = threadIdx.x; i < Hcur + 2; i += tm.n) sm.scan.coloff[i] = (float)((double)(i - 1) * delta - kPi);
+    if (threadIdx.x == 0) sm.scan.ph_H = Hcur, sm.scan.ph_lo = (int)jbase, sm.scan.ph_h0 = h0;
 }
 
 // 32 * RU consecutive pitch-sorted rays from jb against copy e in columns c_lo .. c_hi (-1 and H are the aliases of
@@ -272,13 +272,13 @@ __device__ __forceinline__ void column_chunk(const RenderParams& rp, SmemLayout&
         ISY_BOUND(jend <= (unsigned)kGridRaysSmem);
         const bool ok = j < jend;
         const float pitch = ok ? sm.ras.sorted[j].x : 0.f;
-        ph[u] = ok ? sm.ras.phase[j] : 0.f;
+        ph[u] = ok ? sm.scan.phase[j] : 0.f;
         g0[u] = ok ? fmaf(ent.A0, pitch, fmaf(ent.B0, ph[u], ent.C0)) : ninf;
         g1[u] = fmaf(ent.A1, pitch, fmaf(ent.B1, ph[u], ent.C1));
         g2[u] = fmaf(ent.A2, pitch, fmaf(ent.B2, ph[u], ent.C2));
     }
     for (int c = c_lo; c <= c_hi; ++c) {
-        const float off = sm.ras.coloff[c + 1];
+        const float off = sm.scan.coloff[c + 1];
         const bool edge = c <= 0 || c >= Hcur - 1;          // columns that touch the seam
         float m[RU];
         bool cand[RU], any = false;
@@ -302,7 +302,7 @@ __device__ __forceinline__ void column_chunk(const RenderParams& rp, SmemLayout&
         for (int u = 0; u < RU; ++u) {
             if (!cand[u]) continue;
             const unsigned j = jb + u * 32 + lane;
-            int ks = cw - (int)sm.ras.colb[j];               // sorted slot of the heading that puts ray j into column c
+            int ks = cw - (int)sm.scan.colb[j];               // sorted slot of the heading that puts ray j into column c
             if (ks < 0) ks += Hcur;
             const bool seam = edge && fabsf(ph[u] + off) > 3.14159f;
             bool in = m[u] > kEdgeEps && !seam;
@@ -350,7 +350,7 @@ __device__ __forceinline__ int warp_fetch(int* counter, int n) {
 template <bool kFill>
 __device__ __forceinline__ void bin_add(SmemLayout& sm, unsigned short* tlist, int tile, int e) {
     ISY_BOUND(tile >= 0 && tile < kMaxTiles);
-    const unsigned int a = (unsigned int)__cvta_generic_to_shared(&sm.ras.tile_cnt[tile]);
+    const unsigned int a = (unsigned int)__cvta_generic_to_shared(&sm.scan.tile_cnt[tile]);
     if (kFill) {
         int at;
         asm volatile("atom.shared.add.s32 %0, [%1], 1;" : "=r"(at) : "r"(a) : "memory");
@@ -379,11 +379,11 @@ __device__ void bin_pass(SmemLayout& sm, const Team& tm, int E, int Hcur, int q_
         if (e < E) {
             unsigned int cr;
             if (kFill) {
-                cr = sm.ras.crange[e];
+                cr = sm.scan.crange[e];
             } else {
                 const float4 bb = sm.bbox[e];
                 cr = copy_columns(bb.z, bb.w, inv_delta, Hcur);
-                sm.ras.crange[e] = (unsigned short)cr;
+                sm.scan.crange[e] = (unsigned short)cr;
             }
             const unsigned int jr = sm.jrange[e];
             const unsigned jbeg = jr & 0xffffu, jend = jr >> 16;
@@ -441,7 +441,7 @@ __device__ bool bin_copies(SmemLayout& sm, const Team& tm, int E, int Hcur, int 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NQ = (Rrow + kTileRays - 1) >> kTileShift, NT = NQ * Hcur, q_h = min(NQ - 1, NQ / 2);
     ISY_BOUND(NT <= kMaxTiles && NT <= 2 * tm.n);
-    for (int i = tid; i <= NT; i += tm.n) sm.ras.tile_cnt[i] = 0;
+    for (int i = tid; i <= NT; i += tm.n) sm.scan.tile_cnt[i] = 0;
     tm.sync();
     bin_pass<false>(sm, tm, E, Hcur, q_h, tlist);
     const long long td1 = clock64();
@@ -449,7 +449,7 @@ __device__ bool bin_copies(SmemLayout& sm, const Team& tm, int E, int Hcur, int 
     const long long td2 = clock64();
     // exclusive scan of the counts (two tiles per thread)
     const int i0 = 2 * tid;
-    const unsigned a = i0 < NT ? sm.ras.tile_cnt[i0] : 0u, b = i0 + 1 < NT ? sm.ras.tile_cnt[i0 + 1] : 0u;
+    const unsigned a = i0 < NT ? sm.scan.tile_cnt[i0] : 0u, b = i0 + 1 < NT ? sm.scan.tile_cnt[i0 + 1] : 0u;
     unsigned incl = a + b;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -467,8 +467,8 @@ __device__ bool bin_copies(SmemLayout& sm, const Team& tm, int E, int Hcur, int 
     const unsigned total = w;
     if (total > (unsigned)cap) return false;
     const unsigned excl = before + incl - (a + b);
-    if (i0 < NT) sm.ras.tile_cnt[i0] = excl;
-    if (i0 + 1 < NT) sm.ras.tile_cnt[i0 + 1] = excl + a;
+    if (i0 < NT) sm.scan.tile_cnt[i0] = excl;
+    if (i0 + 1 < NT) sm.scan.tile_cnt[i0 + 1] = excl + a;
     tm.sync();
     const long long td3 = clock64();
     bin_pass<true>(sm, tm, E, Hcur, q_h, tlist);      // tile_cnt[t] ends as the END of tile t's list
@@ -577,7 +577,7 @@ __device__ void raster_tiles(const RenderParams& rp, SmemLayout& sm, const Exact
         const int t1 = min(t0 + take, NT);
         if (t0 >= heavy) take = 4;
         for (int t = t0; t < t1; ++t) {
-            const unsigned i1 = sm.ras.tile_cnt[t], i0 = t ? sm.ras.tile_cnt[t - 1] : 0u;
+            const unsigned i1 = sm.scan.tile_cnt[t], i0 = t ? sm.scan.tile_cnt[t - 1] : 0u;
             if (i0 == i1) continue;
 #ifdef ISY_DEBUG_BOUNDS
             if (i1 < i0 || i1 > (unsigned)(kMaxE * 24)) { ISY_BOUND(false); continue; }   // (keep the debug build alive)
@@ -585,7 +585,7 @@ __device__ void raster_tiles(const RenderParams& rp, SmemLayout& sm, const Exact
             // place t of the queue -> tile (q, c)
             const int tq = (int)(((float)t + 0.5f) * rH), c = t - tq * Hcur, q = chunk_place(tq, q_h);   // (its own inverse)
             ISY_BOUND(q >= 0 && q < NQ && c >= 0 && c < Hcur && i1 <= (unsigned)(kMaxE * 24));
-            const float off = sm.ras.coloff[c + 1];
+            const float off = sm.scan.coloff[c + 1];
             const bool edge = c == 0 || c == Hcur - 1;
             const unsigned j0 = (unsigned)q * kTileRays;
             float pitch[kTileU], f[kTileU];
@@ -597,10 +597,10 @@ __device__ void raster_tiles(const RenderParams& rp, SmemLayout& sm, const Exact
                 const unsigned j = j0 + u * 32 + lane;
                 const bool ok = j < (unsigned)Rrow;
                 pitch[u] = ok ? sm.ras.sorted[j].x : qnan;      // (a NaN pitch fails every test)
-                f[u] = (ok ? sm.ras.phase[j] : 0.f) + off;
+                f[u] = (ok ? sm.scan.phase[j] : 0.f) + off;
                 seam[u] = ok && edge && fabsf(f[u]) > 3.14159f;
                 any_seam |= seam[u];
-                ks[u] = c - (ok ? (int)sm.ras.colb[j] : 0);      // sorted slot of the heading that puts ray j into column c
+                ks[u] = c - (ok ? (int)sm.scan.colb[j] : 0);      // sorted slot of the heading that puts ray j into column c
                 if (ks[u] < 0) ks[u] += Hcur;
                 w[u].off = 0xffffffffu, w[u].lo = 0u, w[u].hi = 0x7fffffff, w[u].tri = 0;
             }

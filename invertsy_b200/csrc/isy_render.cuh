@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
     __shared__ volatile int s_join[3];             // early rows: (item, group) whose lists are ready + 1, how to walk them, E
     __shared__ int s_E;
     __shared__ volatile int s_ahead_go;
-    if (tid == 0) s_ahead_item = 0xffffffffu, sm.ras.ph_H = -1, s_join[0] = 0;
+    if (tid == 0) {
+        s_ahead_item = 0xffffffffu, s_join[0] = 0;
+        if (kEye != kEyeAny && rp.Hg > kSmallH) sm.scan.ph_H = -1;    // (the launch allocated SmemScan, isy_capi.cu)
+    }
     const bool early_rows = ISY_EARLY_ROWS && !ISY_ROWS_ALL && rows_mode && rp.H / rp.ngroups > kSmallH;
     const Team tm = early_rows ? Team{kThreads - 32 * kCopyWarps, 1} : Team{kThreads, 0};
     const bool copier = early_rows && tid >= tm.n;   // (never true outside rows mode)
