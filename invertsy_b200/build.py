@@ -13,7 +13,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libisy_b200.so")
 SOURCES = ["isy_capi.cu"]
 DEPS = ["isy_capi.cu", "isy_kernels.cuh", "isy_common.cuh", "isy_layout.cuh", "isy_setup.cuh", "isy_project.cuh",
-        "isy_bins.cuh", "isy_raster.cuh", "isy_shade.cuh", "isy_render.cuh", "isy_sky_kernels.cuh",
+        "isy_bins.cuh", "isy_raster.cuh", "isy_shade.cuh", "isy_render.cuh", "isy_sky_kernels.cuh", "isy_fam.cuh",
+        "isy_willshaw.cuh",
         os.path.join("..", "..", "include", "isy_b200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -1,4 +1,4 @@
-// Triangle-centric rasterisers for yaw-only views: pitch-run walk and ray-grid walk.
+// Rasterisers for yaw-only views: tile walk and column walk (evenly spaced headings), pitch-run walk, ray-grid walk.
 #pragma once
 #include "isy_bins.cuh"
 
