@@ -75,8 +75,8 @@ __device__ __forceinline__ void post_copy_u32(unsigned int* slot, const Entry* t
 }
 
 // sorts the group's wrapped headings (head_val[0..Hcur)); returns true (to every thread) when they are evenly
-// spaced over the full circle -- every scan of the reference's simulations, and a single heading -- so that
-// the window walk can use arithmetic; otherwise it also builds the azimuth look-up table
+// spaced over the full circle -- every scan of the reference's simulations, and a single heading: the column /
+// tile walk applies; otherwise it also builds the azimuth look-up table of the pitch-run walk
 __device__ bool sort_headings(SmemLayout& sm, const Team& tm, int Hcur) {
     const int tid = threadIdx.x;
     if (tid < Hcur) {
@@ -116,14 +116,13 @@ __device__ bool sort_headings(SmemLayout& sm, const Team& tm, int Hcur) {
 // One step of the pitch-run walk: RU rays per lane (32 * RU consecutive pitch-sorted rays from jb) against copy e.
 // Their window walks and edge tests are independent instruction streams, which is what hides the
 // shared-memory and branch latencies here.
-template <bool kUniform, int RU>
+template <int RU>
 __device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& sm, const Exact* exacts,
                                            const Entry& ent, const float4 bb, double dist, int e, unsigned jb, unsigned jend,
                                            float glo, float width, int Hcur, int R, unsigned jbase) {
     // R: rays per row of the winner buffer (the eye, or the band of a large eye); jbase: first sorted position of the band
     const int lane = threadIdx.x & 31, H2 = 2 * Hcur;
     const float pi_f = (float)kPi, twopi_f = (float)kTwoPi;
-    const float uh0 = sm.ras.uni[0], udelta = sm.ras.uni[1], uinv = sm.ras.uni[2];
     const unsigned int best_s = (unsigned int)__cvta_generic_to_shared(sm.ras.best);
     float2 py[RU];
     int k[RU], ks[RU];    // window cursor; sorted slot of the heading under the cursor
@@ -142,19 +141,9 @@ __device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& s
         if (lower < -pi_f) lower += twopi_f;
         else if (lower >= pi_f) lower -= twopi_f;
         const bool band = py[u].x >= bb.x && py[u].x <= bb.y;
-        if (kUniform) {
-            // headings are h0 + k*delta (k mod H): the window is the index range [k0, k1];
-            // k[] counts the headings left in the window, ks[] is the sorted slot of the next one
-            const float a = (lower - uh0) * uinv;
-            const int k0 = (int)ceilf(a - 2e-4f), k1 = (int)floorf(fmaf(width, uinv, a) + 2e-4f);
-            k[u] = band ? min(k1 - k0 + 1, Hcur) : 0;            // lower in [-pi, pi): k0 in [-H, H]
-            ks[u] = k0 < 0 ? k0 + Hcur : (k0 >= Hcur ? k0 - Hcur : k0);
-            upper[u] = 0.f;
-        } else {
-            const int ls = min(max((int)((lower + pi_f) * (kHeadLut / twopi_f)), 0), kHeadLut - 1);
-            k[u] = band ? (int)sm.ras.hlut[ls] : H2;
-            upper[u] = lower + width;
-        }
+        const int ls = min(max((int)((lower + pi_f) * (kHeadLut / twopi_f)), 0), kHeadLut - 1);
+        k[u] = band ? (int)sm.ras.hlut[ls] : H2;
+        upper[u] = lower + width;
     }
     // lanes walk their heading windows in lock step (most windows hold 0 or 1 heading)
     for (;;) {
@@ -162,15 +151,10 @@ __device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& s
         float hv[RU];
 #pragma unroll
         for (int u = 0; u < RU; ++u) {
-            if (kUniform) {
-                act[u] = k[u] > 0;
-                hv[u] = fmaf((float)ks[u], udelta, uh0);
-            } else {
-                const int kk = min(k[u], H2 - 1);
-                act[u] = k[u] < H2 && sm.ras.hsort[kk] <= upper[u];
-                hv[u] = sm.ras.hvalf[kk];
-                ks[u] = kk >= Hcur ? kk - Hcur : kk;       // the + 2 pi copy is the same heading
-            }
+            const int kk = min(k[u], H2 - 1);
+            act[u] = k[u] < H2 && sm.ras.hsort[kk] <= upper[u];
+            hv[u] = sm.ras.hvalf[kk];
+            ks[u] = kk >= Hcur ? kk - Hcur : kk;           // the + 2 pi copy is the same heading
             any |= act[u];
         }
         if (!__any_sync(0xffffffffu, any)) break;
@@ -210,14 +194,7 @@ __device__ __forceinline__ void walk_chunk(const RenderParams& rp, SmemLayout& s
             if (in) {
                 post_copy_u16(best_s, (unsigned)ks[u] * R + j, sm.tile, dist, ent.tri, e);
             }
-            if (kUniform) {
-                if (act[u]) {
-                    --k[u];
-                    ks[u] = ks[u] + 1 == Hcur ? 0 : ks[u] + 1;
-                }
-            } else if (act[u]) {
-                ++k[u];
-            }
+            if (act[u]) ++k[u];
         }
     }
 }
@@ -654,9 +631,8 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, const Exac
         if (glo > ghi) continue;
         const float width = ghi - glo;
         const Entry ent = sm.tile[e];
-        const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
         unsigned jb = jbeg;
-        if (kUniform) {   // column walk
+        if constexpr (kUniform) {   // column walk
             const float inv_delta = sm.ras.uni[2];
             const int c_lo = (int)floorf((glo + pi_f) * inv_delta), c_hi = (int)floorf((ghi + pi_f) * inv_delta);
             ISY_BOUND(c_lo >= -1 && c_hi <= Hcur);
@@ -668,16 +644,16 @@ __device__ void raster_copies(const RenderParams& rp, SmemLayout& sm, const Exac
                 __syncwarp();
                 column_chunk<1>(rp, sm, exacts, ent, e, jb, jend, c_lo, c_hi, Hcur, Rrow, jbase);
             }
-            continue;
-        }
-        // kRU rays per lane while that many warps' worth are left, then one ray per lane for the tail
-        for (; jb + 32 * (kRU - 1) < jend; jb += 32 * kRU) {   // warp-uniform trip counts
-            __syncwarp();                                       // keep the lanes converged across iterations
-            walk_chunk<kUniform, kRU>(rp, sm, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur, Rrow, jbase);
-        }
-        for (; jb < jend; jb += 32) {
-            __syncwarp();
-            walk_chunk<kUniform, 1>(rp, sm, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur, Rrow, jbase);
+        } else {                     // pitch-run walk: kRU rays per lane while that many warps' worth are left, then one
+            const double dist = __hiloint2double(ent.dist_hi, ent.dist_lo);
+            for (; jb + 32 * (kRU - 1) < jend; jb += 32 * kRU) {   // warp-uniform trip counts
+                __syncwarp();                                       // keep the lanes converged across iterations
+                walk_chunk<kRU>(rp, sm, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur, Rrow, jbase);
+            }
+            for (; jb < jend; jb += 32) {
+                __syncwarp();
+                walk_chunk<1>(rp, sm, exacts, ent, bb, dist, e, jb, jend, glo, width, Hcur, Rrow, jbase);
+            }
         }
     }
 }

@@ -28,7 +28,8 @@ if __name__ == "__main__":
         build_debug()
     args = [a for a in sys.argv[1:] if a != "--rebuild"] or [
         "tests/test_gpu_parity.py", "tests/test_gpu_skytab.py", "tests/test_gpu_bands.py", "tests/test_gpu_edges.py",
-        "tests/test_gpu_familiarity.py", "tests/test_gpu_sensor.py", "tests/test_gpu_configs.py", "tests/test_gpu_variants.py"]
+        "tests/test_gpu_familiarity.py", "tests/test_gpu_sensor.py", "tests/test_gpu_configs.py", "tests/test_gpu_variants.py",
+        "tests/test_gpu_tiles.py"]
     env = dict(os.environ, ISY_B200_LIB=DBG, ISY_REPORT_BOUNDS="1")
     rc = subprocess.call([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider"] + args, cwd=ROOT, env=env)
     print("pytest exit code %d (the per-process violation count is printed by tests/conftest.py at session end)" % rc)
