@@ -14,9 +14,6 @@
 #ifndef ISY_COPY_WARPS
 #define ISY_COPY_WARPS 4
 #endif
-#ifndef ISY_ROWS_ALL
-#define ISY_ROWS_ALL 0
-#endif
 // Rows mode, scans: the copy warps start on the position's rows the moment the position starts and leave the cull,
 // the projection and the filing of the copies to the team of the other warps; they join the rasterisation when their
 // rows are out.  (0: they take part in everything and copy while the others rasterise.)
@@ -79,7 +76,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
         s_ahead_item = 0xffffffffu, s_join[0] = 0;
         if (kEye != kEyeAny && rp.Hg > kSmallH) sm.scan.ph_H = -1;    // (the launch allocated SmemScan, isy_capi.cu)
     }
-    const bool early_rows = ISY_EARLY_ROWS && !ISY_ROWS_ALL && rows_mode && rp.H / rp.ngroups > kSmallH;
+    const bool early_rows = ISY_EARLY_ROWS && rows_mode && rp.H / rp.ngroups > kSmallH;
     const Team tm = early_rows ? Team{kThreads - 32 * kCopyWarps, 1} : Team{kThreads, 0};
     const bool copier = early_rows && tid >= tm.n;   // (never true outside rows mode)
     if (kEye == kEyeSmall && rp.row_bg)   // rows mode (the tail of the layout is allocated)
@@ -181,14 +178,6 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
             long long t3b = clock64();
             if (is_raster) {
                 if (band > 0) __syncthreads();     // the previous band's final pass is done with the buffers
-#if ISY_ROWS_ALL
-                // rows mode: every warp takes its share of the position's rows (sky, responses, templates of hit /
-                // depth / rgb) before anything else: the stores drain while the position is rasterised
-                if (rows_mode) {
-                    if (rp.rows_vec4) copy_rows<float4, true, true>(rp, p, grp, Hcur, 0, kWarps);
-                    else copy_rows<float, true, true>(rp, p, grp, Hcur, 0, kWarps);
-                }
-#endif
                 if (copier) {
                     // early rows: everything of this group's views that does not depend on where the eye stands
                     if (rp.rows_vec4) copy_rows<float4, true, true>(rp, p, grp, Hcur, kWarps - kCopyWarps, kCopyWarps);
@@ -275,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 #endif
                 // rows mode: the copy warps write the sky rows now and the template rows of hit / depth / rgb when
                 // kLateCopies copies are left (scans) -- the later, the likelier the patches find them in L2
-                const bool copy_warp = !ISY_ROWS_ALL && rows_mode && !early_rows && warp >= kWarps - kCopyWarps;
+                const bool copy_warp = rows_mode && !early_rows && warp >= kWarps - kCopyWarps;
 #ifdef ISY_RASTER_DETAIL
                 const long long t_rd0 = early_rows ? t0 : clock64();
 #endif
@@ -327,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const RenderParams 
 #ifdef ISY_RASTER_DETAIL
             // max end of the rasterising warps, end of the copy warps' rows, mean end of the rasterising warps
             if (tid == 0) {
-                t_rd[0] += s_tend[0], t_rd[1] += s_tend[1], t_rd[2] += s_tend[2] / (kWarps - ((rows_mode && !ISY_ROWS_ALL) ? kCopyWarps : 0));
+                t_rd[0] += s_tend[0], t_rd[1] += s_tend[1], t_rd[2] += s_tend[2] / (kWarps - (rows_mode ? kCopyWarps : 0));
                 s_tend[0] = 0, s_tend[1] = 0, s_tend[2] = 0;
             }
 #endif
